@@ -1,0 +1,403 @@
+#!/usr/bin/env python
+"""bench.py -- headline benchmark of the FusedMM CSR SpMM hot path on B200.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference]
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node N ... bench.py --gpus N ...
+
+Metric (BASELINE.json): SpMM effective HBM GB/s on the Reddit-shaped synthetic graph
+(232,965 nodes, 114,615,892 nnz, K=128, fp32 values, reduce=sum):
+    effective GB/s = B_alg / t,   B_alg = 4(M+1) + 4 nnz + 4 nnz + 4 K nnz + 4 K M
+(SURVEY.md section 8d / BASELINE.md section 3).  One "step" = one SpMM forward over the
+whole graph.  N > 1: the same global graph, 1-D row partition, X all-gathered over
+NCCL/NVLink every step with the local column block overlapped (isplib_b200/dist.py):
+total work is fixed -> "scaling": "strong"; value = B_alg(global) / max-over-ranks time.
+
+One JSON line on stdout (rank 0).  `--impl reference` times the reference's own CPU
+path instead: the unmodified csrc/fusedmm.cpp operator layer (oracle/_ref/_fusedmm_cpu.so)
+on top of the restated fusedMM_csr kernel (oracle/fusedmm_oracle.c; the real kernel
+library is un-vendored, configure:2-7), all host threads, same metric on a bounded
+row-sample of the same shape.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+SHAPE = "reddit"
+K_FEAT = 128
+REDUCE = "sum"
+
+
+def parse_args():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--shape", default=SHAPE)
+    ap.add_argument("--k", type=int, default=K_FEAT)
+    ap.add_argument("--reduce", default=REDUCE)
+    ap.add_argument("--variant", type=int, default=None, help="force a kernel variant (default: on-device autotune)")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--cpu-seconds", type=float, default=12.0, help="budget for the cpu_baseline leg")
+    return ap.parse_args()
+
+
+def peaks():
+    """(hbm_gbs, source) -- MEASURED_PEAKS.json if the driver wrote it, else the recipe's fallback."""
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    try:
+        with open(p) as f:
+            return float(json.load(f)["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+    except Exception:
+        return 6650.0, "fallback (B200_PROFILING.md 6.65 TB/s)"
+
+
+# --------------------------------------------------------------------------------------
+# clocks sampler (nvidia-smi during the timed region)
+# --------------------------------------------------------------------------------------
+class ClockSampler:
+    Q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index: int):
+        self.idx = gpu_index
+        self.samples = []
+        self.proc = None
+        self.thread = None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(
+                ["nvidia-smi", f"--id={self.idx}", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "100"],
+                stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+        except Exception:
+            self.proc = None
+            return
+        def pump():
+            for line in self.proc.stdout:
+                self.samples.append((time.time(), line.strip()))
+        self.thread = threading.Thread(target=pump, daemon=True)
+        self.thread.start()
+
+    def stop(self, t0, t1):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:
+            self.proc.kill()
+        rows = [l for (t, l) in self.samples if t0 - 0.05 <= t <= t1 + 0.15] or [l for (_, l) in self.samples]
+        sm, mx, reasons = [], None, set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for l in rows:
+            parts = [p.strip() for p in l.split(",")]
+            if len(parts) < 6:
+                continue
+            try:
+                sm.append(float(parts[0]))
+                mx = float(parts[1])
+            except ValueError:
+                continue
+            for n, v in zip(names, parts[2:6]):
+                if v.lower().startswith("active"):
+                    reasons.add(n)
+        sm.sort()
+        med = sm[len(sm) // 2] if sm else None
+        return {"sm_mhz": med, "sm_max_mhz": mx, "reasons": sorted(reasons), "samples": len(sm)}
+
+
+# --------------------------------------------------------------------------------------
+# reference arm (CPU)
+# --------------------------------------------------------------------------------------
+def cpu_sample_graph(shape, rows, seed=0):
+    """A row-sample of the named shape: `rows` rows with the shape's degree law and mean
+    degree, columns over the FULL node range (so the gather footprint is the real one)."""
+    from isplib_b200 import synth
+    m0, nnz0, law, param = synth.SHAPES[shape]
+    rows = min(rows, m0)
+    nnz = int(round(nnz0 * rows / m0))
+    return synth.make_graph(rows, nnz, n=m0, law=law, param=param, values="uniform", seed=seed, device="cpu")
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return 0
+    os.environ["ISPLIB_B200_SKIP_EXTENSION"] = "1"   # our CUDA ops must not be on this path
+    import torch
+    from isplib_b200 import synth
+    ref_so = os.path.join(ROOT, "oracle", "_ref", "_fusedmm_cpu.so")
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    os.environ.setdefault("OMP_NUM_THREADS", str(cores))
+    kind = "reference"
+    if os.path.exists(ref_so):
+        torch.ops.load_library(ref_so)
+
+        def spmm(row, rowptr, col, val, x):
+            # the two trailing cached tensors are only read by the backward (csrc/fusedmm.cpp:246-247)
+            return torch.ops.isplib.fusedmm_spmm(None, rowptr, col, val, None, None, x, val, col)
+        impl_desc = "unmodified csrc/fusedmm.cpp operator layer + restated fusedMM_csr (OpenMP)"
+    else:
+        from oracle import oracle
+        kind = "port"
+
+        def spmm(row, rowptr, col, val, x):
+            return torch.from_numpy(oracle.spmm_c(rowptr.numpy(), col.numpy(), val.numpy(), x.numpy(), oracle.SUM)[0])
+        impl_desc = "oracle/fusedmm_oracle.c (OpenMP port)"
+
+    m0, nnz0, _, _ = synth.SHAPES[args.shape]
+    K = args.k
+    # size the sample so that one step is ~1.5 s of CPU work: probe on 1/64 of the rows
+    probe = cpu_sample_graph(args.shape, max(256, m0 // 64))
+    x = torch.randn(m0, K, generator=torch.Generator().manual_seed(0))
+    spmm(None, probe.rowptr, probe.col, probe.value, x)
+    t = time.perf_counter()
+    spmm(None, probe.rowptr, probe.col, probe.value, x)
+    dt = max(time.perf_counter() - t, 1e-4)
+    rows = int(min(m0, max(probe.m, probe.m * 1.5 / dt)))
+    g = cpu_sample_graph(args.shape, rows)
+    for _ in range(max(1, min(args.warmup, 2))):
+        spmm(None, g.rowptr, g.col, g.value, x)
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        spmm(None, g.rowptr, g.col, g.value, x)
+    dt = (time.perf_counter() - t0) / args.steps
+    b_alg = synth.algorithmic_bytes(g.m, g.nnz, K, True, args.reduce)
+    val = b_alg / dt / 1e9
+    sample = f"first-{g.m}-row sample of {args.shape}-shape ({g.nnz} nnz, columns over all {m0} nodes), K={K}"
+    line = {
+        "impl": "reference", "metric": "spmm_sum_effective_gbs", "value": round(val, 3), "unit": "GB/s",
+        "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": round(dt * 1e3, 3),
+        "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": f"{args.shape}-shape SpMM-{args.reduce} K={K} fp32 (int64 CSR, CPU)", "sample": sample,
+                   "impl": impl_desc},
+        "cpu_baseline": {"value": round(val, 3), "unit": "GB/s", "cores": cores, "kind": kind, "sample": sample},
+        "e2e": {"value": round(val, 3), "unit": "GB/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gflops": round(2.0 * g.nnz * K / dt / 1e9, 2),
+    }
+    print(json.dumps(line), flush=True)
+    return 0
+
+
+# --------------------------------------------------------------------------------------
+# our arm
+# --------------------------------------------------------------------------------------
+def cpu_baseline_leg(args, budget_s):
+    """oracle C port on the host cores, bounded sample (rank 0, N=1 only)."""
+    import torch
+    from isplib_b200 import synth
+    from oracle import oracle
+    m0 = synth.SHAPES[args.shape][0]
+    K = args.k
+    cores = oracle.num_threads()
+    x = torch.randn(m0, K, generator=torch.Generator().manual_seed(0)).numpy()
+    probe = cpu_sample_graph(args.shape, max(256, m0 // 64))
+    code = oracle.REDUCE_CODE[args.reduce]
+    oracle.spmm_c(probe.rowptr.numpy(), probe.col.numpy(), probe.value.numpy(), x, code)
+    t = time.perf_counter()
+    oracle.spmm_c(probe.rowptr.numpy(), probe.col.numpy(), probe.value.numpy(), x, code)
+    dt = max(time.perf_counter() - t, 1e-4)
+    rows = int(min(m0, max(probe.m, probe.m * (budget_s / 3.0) / dt)))
+    g = cpu_sample_graph(args.shape, rows)
+    rp, co, va = g.rowptr.numpy(), g.col.numpy(), g.value.numpy()
+    times = []
+    t_end = time.perf_counter() + budget_s
+    while len(times) < 3 or (time.perf_counter() < t_end and len(times) < 10):
+        t = time.perf_counter()
+        oracle.spmm_c(rp, co, va, x, code)
+        times.append(time.perf_counter() - t)
+    times.sort()
+    dt = times[len(times) // 2]
+    b = synth.algorithmic_bytes(g.m, g.nnz, K, True, args.reduce)
+    return {"value": round(b / dt / 1e9, 3), "unit": "GB/s", "cores": cores, "kind": "port",
+            "sample": f"first-{g.m}-row sample of {args.shape}-shape ({g.nnz} nnz, columns over all {m0} nodes), "
+                      f"K={K}, median of {len(times)} runs, oracle/fusedmm_oracle.c OpenMP",
+            "ms": round(dt * 1e3, 2), "gflops": round(2.0 * g.nnz * K / dt / 1e9, 2)}
+
+
+def run_ours(args):
+    import torch
+    import torch.distributed as dist
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device -- this arm has no CPU fallback (use --impl reference)")
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+
+    import isplib_b200  # noqa: F401  loads the extension (fails loudly if missing)
+    from isplib_b200 import capi, synth
+    from isplib_b200.dist import RowPartitionedSpMM
+    import torch_sparse
+    from isplib import iSpLibPlugin
+
+    K, reduce = args.k, args.reduce
+    g = synth.make_graph(args.shape, values="uniform", seed=0, device=dev)   # same graph on every rank
+    M, N, nnz = g.m, g.n, g.nnz
+    b_alg = synth.algorithmic_bytes(M, nnz, K, True, reduce)
+    gen = torch.Generator(device=dev).manual_seed(0)
+    xs = [torch.randn(N, K, device=dev, generator=gen) for _ in range(2)]   # rotated so X is never warm in L2
+
+    # --- build the operator -------------------------------------------------------------
+    if world == 1:
+        rp32 = capi.narrow_i64_to_i32(g.rowptr)
+        co32 = capi.narrow_i64_to_i32(g.col)
+        plan = capi.Plan(rp32, nnz)
+        if args.variant is None:
+            best, times = capi.spmm_autotune(reduce, rp32, co32, g.value, xs[0], plan, iters=3)
+        else:
+            best, times = args.variant, []
+        out = torch.empty(M, K, device=dev)
+        arg = torch.empty(M, K, dtype=torch.int64, device=dev) if reduce in ("max", "min") else None
+
+        def step(i):
+            capi.spmm_csr(reduce, rp32, co32, g.value, xs[i & 1], plan, best, out=out, arg_out=arg)
+        launches_per_step = 1 + (1 if plan.info.num_split_rows > 0 else 0)
+        variant_name = capi.variant_names()[best]
+        tune = {capi.variant_names()[v]: round(t, 3) for v, t in enumerate(times) if t >= 0}
+    else:
+        op = RowPartitionedSpMM(g.rowptr, g.col, g.value, N, device=dev)
+        slices = [op.pad_x(x[rank * op.Rc: min((rank + 1) * op.Rc, N)]) for x in xs]
+        if args.variant is not None:
+            op.variant = args.variant
+
+        def step(i):
+            op.forward(slices[i & 1], reduce)
+        step(0)
+        launches_per_step = op.launches_per_forward()
+        variant_name = "auto" if args.variant is None else capi.variant_names()[args.variant]
+        tune = {}
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    for i in range(max(args.warmup, 3)):
+        step(i)
+    barrier()
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()
+        time.sleep(0.25)
+    barrier()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    w0 = time.time()
+    e0.record()
+    for i in range(args.steps):
+        step(i)
+    e1.record()
+    barrier()
+    w1 = time.time()
+    ms_total = e0.elapsed_time(e1)
+    if world > 1:
+        t = torch.tensor([ms_total], device=dev, dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms_total = float(t.item())
+    clocks = sampler.stop(w0, w1) if rank == 0 else None
+    ms_step = ms_total / args.steps
+    value = b_alg / (ms_step * 1e-3) / 1e9
+
+    # --- e2e: through the plugin (torch_sparse.matmul) with HOST buffers ---------------------
+    e2e = None
+    if world == 1:
+        adj = g.sparse_tensor()
+        x_host = [x.cpu().pin_memory() for x in xs]
+        out_host = torch.empty((M, K), dtype=torch.float32).pin_memory()
+        iSpLibPlugin.patch_pyg()
+        try:
+            def e2e_step(i):
+                xd = x_host[i & 1].to(dev, non_blocking=True)
+                o = torch_sparse.matmul(adj, xd, reduce)
+                out_host.copy_(o, non_blocking=True)
+            for i in range(3):
+                e2e_step(i)
+            torch.cuda.synchronize()
+            n_e2e = max(3, min(args.steps, 10))
+            a0, a1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            a0.record()
+            for i in range(n_e2e):
+                e2e_step(i)
+            a1.record()
+            torch.cuda.synchronize()
+            ms_e2e = a0.elapsed_time(a1) / n_e2e
+        finally:
+            iSpLibPlugin.unpatch_pyg()
+        e2e = {"value": round(b_alg / (ms_e2e * 1e-3) / 1e9, 2), "unit": "GB/s",
+               "h2d_bytes_per_step": N * K * 4, "d2h_bytes_per_step": M * K * 4, "ms_per_step": round(ms_e2e, 3),
+               "path": "iSpLibPlugin.patch_pyg() -> torch_sparse.matmul(adj_t, X) -> torch.ops.isplib.fusedmm_spmm; "
+                       "X from pinned host memory and out back to pinned host memory every step; adjacency resident "
+                       "on the device (uploaded once per graph, as the plugin caches per graph)"}
+        del adj
+
+    if rank != 0:
+        if world > 1:
+            dist.barrier()
+            dist.destroy_process_group()
+        return 0
+
+    peak, peak_src = peaks()
+    roofline = {"bound": "hbm", "achieved": round(value / world, 2) if world > 1 else round(value, 2), "peak": peak,
+                "unit": "GB/s", "frac": round((value / world) / peak, 4), "traffic": None,
+                "kernel": "isplib::spmm_seg_kernel (+ spmm_fixup_kernel, same launch pair)",
+                "peak_source": peak_src,
+                "algorithmic_bytes_per_launch": b_alg // world,
+                "note": "achieved = B_alg per step / CUDA-event step time; a step is the segment kernel plus its "
+                        "fix-up launch. B_alg counts one K-row gather per stored entry, so it can exceed HBM "
+                        "traffic when X rows hit in L2 (ncu dram bytes in profiles/)."}
+    line = {
+        "metric": "spmm_sum_effective_gbs", "value": round(value, 2), "unit": "GB/s", "n_gpus": world,
+        "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": round(ms_step, 4),
+        "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": f"{args.shape}-shape SpMM-{reduce} K={K} fp32, int32 CSR, {M} nodes, {nnz} nnz "
+                               f"(synthetic log-normal degrees, uniform columns, seed 0)",
+                   "reduce": reduce, "K": K, "variant": variant_name, "max_degree": g.max_degree,
+                   "degree_gini": round(g.gini, 3),
+                   "l2": "inputs 1.04 GB (col+val+X) > 126 MB L2 and two X buffers rotated between steps; no flush",
+                   "parallelism": "single GPU" if world == 1 else f"1-D row partition x{world}, X all-gathered per step "
+                                                                   f"over NCCL with local-block overlap"},
+        "gflops": round(2.0 * nnz * K / (ms_step * 1e-3) / 1e9, 1),
+        "roofline": roofline,
+        "gpu_launches": launches_per_step * args.steps,
+        "clocks": clocks,
+    }
+    if tune:
+        line["autotune_ms"] = tune
+    if e2e is not None:
+        line["e2e"] = e2e
+    if world == 1 and not args.no_cpu_baseline:
+        try:
+            line["cpu_baseline"] = cpu_baseline_leg(args, args.cpu_seconds)
+        except Exception as ex:  # the baseline leg must never kill the GPU number
+            line["cpu_baseline"] = {"value": None, "unit": "GB/s", "cores": os.cpu_count(), "kind": "port",
+                                    "sample": f"failed: {ex}"}
+    print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+    return 0
+
+
+def main():
+    args = parse_args()
+    if args.impl == "reference":
+        return run_reference(args)
+    return run_ours(args)
+
+
+if __name__ == "__main__":
+    sys.exit(main())

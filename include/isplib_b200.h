@@ -1,0 +1,206 @@
+/*
+ * isplib_b200.h -- C ABI of the B200-native FusedMM CSR SpMM path.
+ *
+ * This header is the drop-in boundary.  It replaces the single C entry point the
+ * reference's hot path bottoms out in,
+ *
+ *     int fusedMM_csr(imsg, m, n, k, alpha, nnz, rows, cols, val, indx, pntrb,
+ *                     pntre, x, ldx, y, ldy, beta, z, ldz, z_arg)
+ *         declared  /root/reference/csrc/fusedMM.h:77-99, csrc/fusedmm.cpp:63-85
+ *         called    /root/reference/csrc/fusedmm.cpp:198  (from fusedmm_spmm_fw)
+ *
+ * whose body lives in an un-vendored CPU library (configure:2-7).  Differences
+ * from that interface, all deliberate:
+ *   - DEVICE pointers, int32 CSR indices, an explicit cudaStream_t; every call
+ *     except the plan builder is asynchronous on that stream;
+ *   - no allocation inside: derived metadata ("plan") and scratch ("workspace")
+ *     live in caller-owned device buffers sized by the *_bytes queries;
+ *   - the 5-stage VOP/ROP/SOP/VSC/AOP message is narrowed to the four reductions
+ *     the wrapper actually sends (csrc/fusedmm.cpp:168-186), using the wrapper's
+ *     own reduction codes (csrc/fusedmm.cpp:147-152);
+ *   - val == NULL means "all ones" (the reference materialises a ones vector,
+ *     isplib/__init__.py:51-57);
+ *   - the status int is meant to be checked (the reference ignores it,
+ *     csrc/fusedmm.cpp:198).
+ * A literal host-pointer/int64 `fusedMM_csr` replacement with the reference's
+ * exact signature is exported as isplib_b200_fusedmm_csr_host for maintainers
+ * who want to relink csrc/fusedmm.cpp unchanged.
+ *
+ * No torch types appear here.  Only <stdint.h>/<stddef.h> are required; the
+ * stream is passed as an opaque pointer (a cudaStream_t).
+ */
+#ifndef ISPLIB_B200_H
+#define ISPLIB_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define ISPLIB_B200_ABI_VERSION 1
+
+/* reduction codes == `reduction` of fusedmm_spmm_fw, csrc/fusedmm.cpp:147-186 */
+#define ISPLIB_REDUCE_SUM  0
+#define ISPLIB_REDUCE_MAX  1
+#define ISPLIB_REDUCE_MIN  2
+#define ISPLIB_REDUCE_MEAN 3
+
+/* status codes: 0/1/-1/128 keep the meaning of csrc/fusedMM.h:105-114 */
+#define ISPLIB_SUCCESS          0
+#define ISPLIB_FAIL             1     /* FUSEDMM_FAIL_RETURN */
+#define ISPLIB_NOT_ENOUGH_MEM  (-1)   /* FUSEDMM_NOT_ENOUGH_MEM: plan/workspace too small */
+#define ISPLIB_NO_OPT_IMPL      128   /* FUSEDMM_NO_OPT_IMPL: unsupported message/variant */
+#define ISPLIB_INVALID_ARG      256   /* null/negative/misaligned/overflowing argument */
+#define ISPLIB_CUDA_ERROR_BASE  1000  /* 1000 + cudaError_t */
+
+/* flags for isplib_b200_spmm_csr_ex */
+#define ISPLIB_FLAG_ACCUMULATE  0x1   /* merge into the existing out/arg_out instead of overwriting */
+#define ISPLIB_FLAG_EMPTY_ZERO  0x2   /* max/min: rows with no entry produce 0 (torch_sparse
+                                         convention) instead of keeping lowest()/max()
+                                         (what csrc/fusedmm.cpp:147-150 leaves behind) */
+
+#define ISPLIB_VARIANT_AUTO (-1)
+
+typedef void* isplib_stream_t; /* cudaStream_t */
+
+/* Host-side description of a built plan (POD; filled by isplib_b200_plan_build). */
+typedef struct isplib_b200_plan_info {
+    int64_t m;                /* rows */
+    int64_t nnz;              /* stored entries */
+    int32_t seg_len;          /* max entries one warp work-item covers */
+    int32_t reserved;
+    int64_t num_items;        /* work items = sum_i max(1, ceil(deg_i / seg_len)) */
+    int64_t num_split_rows;   /* rows covered by more than one item */
+    int64_t num_split_items;  /* items that belong to split rows (= partial slots) */
+    int64_t max_degree;
+    int64_t num_empty_rows;
+    uint64_t plan_bytes;      /* bytes of the device plan buffer actually used */
+} isplib_b200_plan_info;
+
+/* ---- library info ---------------------------------------------------------- */
+int         isplib_b200_abi_version(void);
+const char* isplib_b200_status_string(int status);
+
+/* ---- plan: degree-aware work decomposition (replaces nothing in the reference;
+ *      it is the metadata half of the `findbestk.py` replacement) -- */
+/* Upper bound on the device plan buffer for (m, nnz, seg_len). seg_len <= 0 = default. */
+int isplib_b200_plan_bytes(int64_t m, int64_t nnz, int32_t seg_len, size_t* bytes);
+/* Builds the plan into plan_dev.  Synchronises `stream` once (reads back counts). */
+int isplib_b200_plan_build(int64_t m, int64_t nnz, const int32_t* rowptr, int32_t seg_len,
+                           void* plan_dev, size_t plan_dev_bytes,
+                           isplib_b200_plan_info* info, isplib_stream_t stream);
+/* Scratch needed by isplib_b200_spmm_csr* for this plan at feature width k. */
+int isplib_b200_spmm_workspace_bytes(const isplib_b200_plan_info* info, int64_t k,
+                                     int reduce, size_t* bytes);
+
+/* ---- forward: replaces fusedMM_csr as called at csrc/fusedmm.cpp:198 --------
+ * out[i,:] = REDUCE_{e in row i} val[e] * x[col[e],:]        (mean: / max(deg_i,1))
+ * max/min also write arg_out[i,kk] = winning edge id e, or nnz if row i is empty
+ * (csrc/fusedmm.cpp:171).  out (and arg_out) are fully written: no pre-init is
+ * needed (the reference pre-fills them, csrc/fusedmm.cpp:147-152,171).
+ * x: [n,k] fp32 row-major with row stride ldx; out: [m,k] with row stride ldo;
+ * arg_out: [m,k] int64 with row stride ldo, required iff reduce is max/min.      */
+int isplib_b200_spmm_csr(int reduce, int64_t m, int64_t n, int64_t k, int64_t nnz,
+                         const int32_t* rowptr, const int32_t* col, const float* val,
+                         const float* x, int64_t ldx, float* out, int64_t ldo,
+                         int64_t* arg_out,
+                         const isplib_b200_plan_info* info, const void* plan_dev,
+                         void* workspace, size_t workspace_bytes,
+                         int variant, isplib_stream_t stream);
+
+/* Extended form used by the row-partitioned multi-GPU path:
+ *   flags         ISPLIB_FLAG_*
+ *   row_divisor   [m] or NULL: out[i,:] is divided by row_divisor[i] at the end
+ *                 (sum with an explicit divisor == mean over a partitioned row)
+ *   edge_ids      [nnz] or NULL: arg_out receives edge_ids[e] instead of e (global
+ *                 edge ids of a column block); must be increasing within a row
+ *   arg_sentinel  value written to arg_out where no entry won (nnz when edge_ids==NULL) */
+int isplib_b200_spmm_csr_ex(int reduce, int64_t m, int64_t n, int64_t k, int64_t nnz,
+                            const int32_t* rowptr, const int32_t* col, const float* val,
+                            const float* x, int64_t ldx, float* out, int64_t ldo,
+                            int64_t* arg_out,
+                            const isplib_b200_plan_info* info, const void* plan_dev,
+                            void* workspace, size_t workspace_bytes,
+                            int variant, int flags, const float* row_divisor,
+                            const int32_t* edge_ids, int64_t arg_sentinel,
+                            isplib_stream_t stream);
+
+/* ---- kernel variants + on-device selection: replaces autotuner/findbestk.py:29-41
+ *      (an offline K sweep) by timing the eligible row-split / K-tile / unroll
+ *      variants on the device, on the caller's own graph and buffers ------------ */
+int         isplib_b200_variant_count(void);
+const char* isplib_b200_variant_name(int variant);
+/* 1 if `variant` can run this problem, else 0 */
+int         isplib_b200_variant_supported(int variant, int reduce, int64_t k, int64_t ldx,
+                                          int64_t ldo, const void* x, const void* out);
+/* Heuristic default for (k, reduce, average degree). */
+int         isplib_b200_variant_default(int reduce, int64_t k, int64_t ldx, int64_t ldo,
+                                        const void* x, const void* out, double avg_degree);
+/* Times every supported variant (1 warm-up + iters timed launches each, CUDA events
+ * on `stream`), writes ms per launch to times_ms[variant] (negative = unsupported),
+ * returns the fastest in *best_variant.  Overwrites out/arg_out.  Synchronises. */
+int isplib_b200_spmm_autotune(int reduce, int64_t m, int64_t n, int64_t k, int64_t nnz,
+                              const int32_t* rowptr, const int32_t* col, const float* val,
+                              const float* x, int64_t ldx, float* out, int64_t ldo,
+                              int64_t* arg_out,
+                              const isplib_b200_plan_info* info, const void* plan_dev,
+                              void* workspace, size_t workspace_bytes,
+                              int iters, int* best_variant, float* times_ms,
+                              isplib_stream_t stream);
+
+/* ---- backward ----------------------------------------------------------------
+ * sum/mean backward is the forward over the CSC view (csrc/fusedmm.cpp:285,375):
+ * these two build that view once per graph on the device, replacing the
+ * torch_sparse csr2csc()/colptr() argsort and the two index_selects the plugin
+ * caches (isplib/__init__.py:69-99).                                             */
+int isplib_b200_csr_transpose_workspace_bytes(int64_t m, int64_t n, int64_t nnz, size_t* bytes);
+/* colptr[n+1], row_t[nnz] = row[csr2csc], csr2csc[nnz]: stable by-column order. */
+int isplib_b200_csr_transpose(int64_t m, int64_t n, int64_t nnz,
+                              const int32_t* rowptr, const int32_t* col,
+                              int32_t* colptr, int32_t* row_t, int32_t* csr2csc,
+                              void* workspace, size_t workspace_bytes,
+                              isplib_stream_t stream);
+/* val_t[p] = val[csr2csc[p]]                       (mean_weights == 0; isplib/__init__.py:79)
+ * val_t[p] = val[csr2csc[p]] / max(deg(row_t[p]),1) (mean_weights != 0; isplib/__init__.py:86-93)
+ * val == NULL stands for all ones.  rowptr is the ORIGINAL (untransposed) rowptr. */
+int isplib_b200_permute_values(int64_t nnz, const float* val, const int32_t* csr2csc,
+                               const int32_t* row_t, const int32_t* rowptr,
+                               int mean_weights, float* val_t, isplib_stream_t stream);
+
+/* max/min backward, fused: replaces the 5-8 ATen ops at csrc/fusedmm.cpp:417-446
+ * (and :484-513).  For every (i,kk) with e = arg[i,kk] != arg_sentinel:
+ *     grad_x[col[e], kk]  += (val ? val[e] : 1) * grad_out[i,kk]     (if grad_x)
+ *     grad_val[e]         += x[col[e], kk] * grad_out[i,kk]          (if grad_val)
+ * zero_init != 0 clears grad_x ([n,k], stride ldgx) / grad_val ([nnz]) first.      */
+int isplib_b200_spmm_arg_backward(int64_t m, int64_t n, int64_t k, int64_t nnz,
+                                  const int32_t* col, const float* val,
+                                  const float* x, int64_t ldx,
+                                  const int64_t* arg, int64_t ld_arg, int64_t arg_sentinel,
+                                  const float* grad_out, int64_t ldgo,
+                                  float* grad_x, int64_t ldgx, float* grad_val,
+                                  int zero_init, isplib_stream_t stream);
+
+/* ---- index helpers ------------------------------------------------------------- */
+/* int64 -> int32 narrowing of rowptr/col as the ops receive them
+ * (csrc/fusedmm.cpp:128-129 reads int64).  *overflow_flag_dev (device int, may be
+ * NULL) is set to 1 if any value does not fit. */
+int isplib_b200_narrow_i64_to_i32(int64_t count, const int64_t* src, int32_t* dst,
+                                  int32_t* overflow_flag_dev, isplib_stream_t stream);
+
+/* ---- literal replacement of the reference entry point ---------------------------
+ * Same signature and HOST-pointer/int64 contract as fusedMM_csr
+ * (csrc/fusedMM.h:77-99): z/z_arg pre-initialised by the caller, accumulated into.
+ * Uploads, runs the kernels above on the current device, downloads; synchronous.  */
+int isplib_b200_fusedmm_csr_host(int32_t imessage, int64_t m, int64_t n, int64_t k,
+                                 float alpha, int64_t nnz, int64_t rows, int64_t cols,
+                                 const float* val, const int64_t* indx,
+                                 const int64_t* pntrb, const int64_t* pntre,
+                                 const float* x, int64_t ldx, const float* y, int64_t ldy,
+                                 float beta, float* z, int64_t ldz, int64_t* z_arg);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* ISPLIB_B200_H */

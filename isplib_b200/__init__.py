@@ -1,0 +1,164 @@
+"""isplib_b200 -- B200-native drop-in for iSpLib's one hot path.
+
+Same Python surface as /root/reference/isplib/__init__.py:
+``iSpLibPlugin.patch_pyg()`` / ``unpatch_pyg()``, the ``@isplib_autotune`` decorator and
+``torch_sparse.matmul(adj_t, X, reduce)`` diverted to ``torch.ops.isplib.fusedmm_spmm*``
+-- but the ops are hand-written sm_100a CUDA kernels behind the C ABI of
+``include/isplib_b200.h``.  There is no CPU path: importing this package without the
+built extension raises ImportError, and CPU tensors are rejected by the ops.
+
+``import isplib`` (the thin alias package at the repo root) re-exports everything here,
+so ``from isplib import *`` at the top of an existing PyG script keeps working.
+"""
+from __future__ import annotations
+
+import functools
+import importlib.machinery
+import os
+import os.path as osp
+import sys
+
+import torch
+
+__version__ = "0.2.0+b200.r1"
+
+# --- torch_sparse: the real package if present, the compat shim otherwise -------------
+try:  # /root/reference/isplib/__init__.py:6-8 imports it unconditionally
+    import torch_sparse  # type: ignore
+except Exception:  # absent in this image
+    from . import torch_sparse_compat as torch_sparse
+    sys.modules.setdefault("torch_sparse", torch_sparse)
+
+from torch_sparse import SparseTensor, matmul  # noqa: E402  (re-exported like the reference)
+
+try:  # isplib/__init__.py:10-13
+    import torch_geometric.typing  # type: ignore  # noqa: F401
+except Exception:
+    pass
+
+# --- extension loader: mirrors isplib/__init__.py:18-28, CUDA only ---------------------
+_PKG_DIR = osp.dirname(osp.abspath(__file__))
+
+
+def _load_extension() -> str:
+    spec = importlib.machinery.PathFinder().find_spec("_fusedmm_cuda", [_PKG_DIR])
+    if spec is None or spec.origin is None:
+        raise ImportError(
+            f"Could not find module '_fusedmm_cuda' in {_PKG_DIR}. Build it with "
+            "`make -C isplib_b200/csrc all ops` (or __graft_entry__.build()). "
+            "isplib_b200 has no CPU implementation to fall back to.")
+    torch.ops.load_library(spec.origin)
+    return spec.origin
+
+
+EXTENSION_PATH = None
+if os.environ.get("ISPLIB_B200_SKIP_EXTENSION", "0") != "1":
+    EXTENSION_PATH = _load_extension()
+
+
+def _is_sparse_tensor(obj) -> bool:
+    return hasattr(obj, "csr") and hasattr(obj, "storage") and not isinstance(obj, torch.Tensor)
+
+
+class iSpLibPlugin:
+    """Same class-level surface as the reference (isplib/__init__.py:34-40).  The caches
+    are kept for compatibility; the derived per-graph data (int32 CSR, segment plan, CSC
+    view, permuted values, tuned variant) now lives in the C++ op layer, keyed by the
+    graph's storage and dropped when the graph's tensors die (the reference keys by raw
+    data_ptr and never evicts, isplib/__init__.py:50)."""
+    backup = []
+    value_cache = {}
+    cache = {}
+    row_cache = {}
+    is_cached = False
+    value_cached = False
+    # 'reference': max/min leave lowest()/max() in rows without entries, as
+    # csrc/fusedmm.cpp:147-150 does; nothing else is configurable here.
+    empty_row_mode = "reference"
+
+    @staticmethod
+    def spmm(src, other, reduce: str = "sum"):
+        """The patched ``torch_sparse.matmul``: body of ``spmm_autotuned``
+        (isplib/__init__.py:48-157) on the CUDA ops."""
+        if not _is_sparse_tensor(src):
+            # torch.sparse.mm is patched too (isplib/__init__.py:178); genuine torch sparse
+            # tensors go to the original function instead of crashing on src.csr()
+            for orig in reversed(iSpLibPlugin.backup[1::2]):      # the saved torch.sparse.mm's
+                if orig is not iSpLibPlugin.spmm:
+                    return orig(src, other)
+            raise TypeError("isplib: expected a torch_sparse.SparseTensor")
+        rowptr, col, value = src.csr()
+        if value is not None:
+            value = value.to(other.dtype)                     # isplib/__init__.py:63-64
+        # value None stays None: the C ABI treats a null value pointer as all-ones, so
+        # the 4*nnz-byte ones vector of isplib/__init__.py:51-57 is never materialised.
+        st = src.storage
+        row, rowcount, csr2csc, colptr = st._row, st._rowcount, st._csr2csc, st._colptr
+        ops = torch.ops.isplib
+        if reduce in ("sum", "add"):
+            return ops.fusedmm_spmm(row, rowptr, col, value, colptr, csr2csc, other, None, None)
+        if reduce == "mean":
+            return ops.fusedmm_spmm_mean(row, rowptr, col, value, rowcount, colptr, csr2csc, other, None, None)
+        if reduce == "max":
+            # the op returns (out, arg_out) like the reference's; matmul returns `out`
+            # (the torch_sparse contract; the reference leaks the tuple, isplib/__init__.py:143)
+            return ops.fusedmm_spmm_max(rowptr, col, value, other)[0]
+        if reduce == "min":
+            return ops.fusedmm_spmm_min(rowptr, col, value, other)[0]
+        raise ValueError(f"isplib: unsupported reduce {reduce!r} (sum, add, mean, max, min)")
+
+    @classmethod
+    def patch_pyg(cls):
+        global matmul
+        try:  # isplib/__init__.py:159-171
+            import torch_geometric.typing as tgt  # type: ignore
+            cls.cache["WITH_PT2"] = getattr(tgt, "WITH_PT2", None)
+            cls.cache["WITH_PT20"] = getattr(tgt, "WITH_PT20", None)
+            tgt.WITH_PT2 = False
+            tgt.WITH_PT20 = False
+        except Exception:
+            pass
+        ts = sys.modules["torch_sparse"]
+        cls.backup.append(ts.matmul)                          # isplib/__init__.py:173-174
+        cls.backup.append(torch.sparse.mm)
+        ts.matmul = cls.spmm                                  # isplib/__init__.py:177-178
+        torch.sparse.mm = cls.spmm
+        matmul = cls.spmm
+
+    @classmethod
+    def unpatch_pyg(cls):
+        global matmul
+        if len(cls.backup) > 0:                               # isplib/__init__.py:190-195
+            torch.sparse.mm = cls.backup.pop()
+            ts = sys.modules["torch_sparse"]
+            ts.matmul = cls.backup.pop()
+            matmul = ts.matmul
+            try:
+                import torch_geometric.typing as tgt  # type: ignore
+                if cls.cache.get("WITH_PT2") is not None:
+                    tgt.WITH_PT2 = cls.cache["WITH_PT2"]
+                if cls.cache.get("WITH_PT20") is not None:
+                    tgt.WITH_PT20 = cls.cache["WITH_PT20"]
+            except Exception:
+                pass
+
+    @classmethod
+    def is_patched(cls) -> bool:
+        return len(cls.backup) > 0
+
+
+def isplib_autotune(fn):
+    """patch -> call -> unpatch (isplib/__init__.py:204-210); unlike the reference the
+    unpatch also happens when ``fn`` raises."""
+    @functools.wraps(fn)
+    def wrapper(*args, **kwargs):
+        iSpLibPlugin.patch_pyg()
+        try:
+            return fn(*args, **kwargs)
+        finally:
+            iSpLibPlugin.unpatch_pyg()
+    return wrapper
+
+
+__all__ = ["iSpLibPlugin", "isplib_autotune", "SparseTensor", "matmul", "torch", "torch_sparse",
+           "__version__"]

@@ -1,0 +1,245 @@
+"""ctypes binding of the C ABI in ``include/isplib_b200.h``.
+
+This is the host-side mirror used by the parity tests (which call the kernels
+through the C ABI, not through torch ops) and by the multi-GPU layer.  Tensors are
+only used as owners of device memory: every call passes raw ``data_ptr()`` values,
+sizes and the current CUDA stream.  Nothing here falls back to the CPU -- if the
+library is missing, importing it raises.
+"""
+from __future__ import annotations
+
+import ctypes
+import os
+from typing import Optional, Tuple
+
+import torch
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libisplib_b200.so")
+
+SUM, MAX, MIN, MEAN = 0, 1, 2, 3
+REDUCE_CODE = {"sum": SUM, "add": SUM, "max": MAX, "min": MIN, "mean": MEAN}
+FLAG_ACCUMULATE = 0x1
+FLAG_EMPTY_ZERO = 0x2
+VARIANT_AUTO = -1
+
+# every symbol include/isplib_b200.h declares (checked by tests/test_abi.py)
+EXPORTS = [
+    "isplib_b200_abi_version", "isplib_b200_status_string",
+    "isplib_b200_plan_bytes", "isplib_b200_plan_build", "isplib_b200_spmm_workspace_bytes",
+    "isplib_b200_spmm_csr", "isplib_b200_spmm_csr_ex",
+    "isplib_b200_variant_count", "isplib_b200_variant_name", "isplib_b200_variant_supported",
+    "isplib_b200_variant_default", "isplib_b200_spmm_autotune",
+    "isplib_b200_csr_transpose_workspace_bytes", "isplib_b200_csr_transpose",
+    "isplib_b200_permute_values", "isplib_b200_spmm_arg_backward",
+    "isplib_b200_narrow_i64_to_i32", "isplib_b200_fusedmm_csr_host",
+]
+
+
+class PlanInfo(ctypes.Structure):
+    _fields_ = [
+        ("m", ctypes.c_int64), ("nnz", ctypes.c_int64),
+        ("seg_len", ctypes.c_int32), ("reserved", ctypes.c_int32),
+        ("num_items", ctypes.c_int64), ("num_split_rows", ctypes.c_int64),
+        ("num_split_items", ctypes.c_int64), ("max_degree", ctypes.c_int64),
+        ("num_empty_rows", ctypes.c_int64), ("plan_bytes", ctypes.c_uint64),
+    ]
+
+
+_lib: Optional[ctypes.CDLL] = None
+
+
+def lib() -> ctypes.CDLL:
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise ImportError(
+            f"isplib_b200: {LIB_PATH} is missing -- build it with `make -C isplib_b200/csrc` "
+            "(or `python -c 'import __graft_entry__ as g; g.build()'`). There is no CPU fallback.")
+    L = ctypes.CDLL(LIB_PATH)
+    i32, i64, f32, p, sz = ctypes.c_int32, ctypes.c_int64, ctypes.c_float, ctypes.c_void_p, ctypes.c_size_t
+    pinfo = ctypes.POINTER(PlanInfo)
+    L.isplib_b200_abi_version.restype = ctypes.c_int
+    L.isplib_b200_status_string.restype = ctypes.c_char_p
+    L.isplib_b200_status_string.argtypes = [ctypes.c_int]
+    L.isplib_b200_plan_bytes.argtypes = [i64, i64, i32, ctypes.POINTER(sz)]
+    L.isplib_b200_plan_build.argtypes = [i64, i64, p, i32, p, sz, pinfo, p]
+    L.isplib_b200_spmm_workspace_bytes.argtypes = [pinfo, i64, ctypes.c_int, ctypes.POINTER(sz)]
+    spmm_args = [ctypes.c_int, i64, i64, i64, i64, p, p, p, p, i64, p, i64, p, pinfo, p, p, sz]
+    L.isplib_b200_spmm_csr.argtypes = spmm_args + [ctypes.c_int, p]
+    L.isplib_b200_spmm_csr_ex.argtypes = spmm_args + [ctypes.c_int, ctypes.c_int, p, p, i64, p]
+    L.isplib_b200_variant_count.restype = ctypes.c_int
+    L.isplib_b200_variant_name.restype = ctypes.c_char_p
+    L.isplib_b200_variant_name.argtypes = [ctypes.c_int]
+    L.isplib_b200_variant_supported.argtypes = [ctypes.c_int, ctypes.c_int, i64, i64, i64, p, p]
+    L.isplib_b200_variant_default.argtypes = [ctypes.c_int, i64, i64, i64, p, p, ctypes.c_double]
+    L.isplib_b200_spmm_autotune.argtypes = spmm_args + [ctypes.c_int, ctypes.POINTER(ctypes.c_int),
+                                                        ctypes.POINTER(f32), p]
+    L.isplib_b200_csr_transpose_workspace_bytes.argtypes = [i64, i64, i64, ctypes.POINTER(sz)]
+    L.isplib_b200_csr_transpose.argtypes = [i64, i64, i64, p, p, p, p, p, p, sz, p]
+    L.isplib_b200_permute_values.argtypes = [i64, p, p, p, p, ctypes.c_int, p, p]
+    L.isplib_b200_spmm_arg_backward.argtypes = [i64, i64, i64, i64, p, p, p, i64, p, i64, i64, p, i64,
+                                                p, i64, p, ctypes.c_int, p]
+    L.isplib_b200_narrow_i64_to_i32.argtypes = [i64, p, p, p, p]
+    L.isplib_b200_fusedmm_csr_host.argtypes = [i32, i64, i64, i64, f32, i64, i64, i64, p, p, p, p, p, i64,
+                                               p, i64, f32, p, i64, p]
+    for name in EXPORTS:
+        getattr(L, name)  # AttributeError here = the .so does not match include/isplib_b200.h
+    _lib = L
+    return L
+
+
+class IsplibError(RuntimeError):
+    def __init__(self, status: int, where: str):
+        self.status = status
+        msg = lib().isplib_b200_status_string(status).decode()
+        super().__init__(f"{where} failed: {msg} (status {status})")
+
+
+def check(status: int, where: str) -> None:
+    if status != 0:
+        raise IsplibError(status, where)
+
+
+def _p(t: Optional[torch.Tensor]):
+    return None if t is None else ctypes.c_void_p(t.data_ptr())
+
+
+def _stream(device) -> ctypes.c_void_p:
+    return ctypes.c_void_p(torch.cuda.current_stream(device).cuda_stream)
+
+
+def _dev_bytes(nbytes: int, device) -> torch.Tensor:
+    # +256 so the 256-byte aligned window of `nbytes` always fits
+    return torch.empty(int(nbytes) + 256, dtype=torch.uint8, device=device)
+
+
+def _aligned_ptr(t: torch.Tensor) -> ctypes.c_void_p:
+    return ctypes.c_void_p((t.data_ptr() + 255) // 256 * 256)
+
+
+class Plan:
+    """Owner of a device plan buffer + its host-side info (isplib_b200_plan_build)."""
+
+    def __init__(self, rowptr32: torch.Tensor, nnz: int, seg_len: int = 0):
+        assert rowptr32.is_cuda and rowptr32.dtype == torch.int32 and rowptr32.is_contiguous()
+        self.m = rowptr32.numel() - 1
+        self.nnz = int(nnz)
+        nbytes = ctypes.c_size_t(0)
+        check(lib().isplib_b200_plan_bytes(self.m, self.nnz, seg_len, ctypes.byref(nbytes)), "plan_bytes")
+        self.buf = _dev_bytes(nbytes.value, rowptr32.device)
+        self.info = PlanInfo()
+        check(lib().isplib_b200_plan_build(self.m, self.nnz, _p(rowptr32), seg_len, _aligned_ptr(self.buf),
+                                           nbytes.value, ctypes.byref(self.info), _stream(rowptr32.device)),
+              "plan_build")
+
+    @property
+    def ptr(self) -> ctypes.c_void_p:
+        return _aligned_ptr(self.buf)
+
+
+def variant_names():
+    L = lib()
+    return [L.isplib_b200_variant_name(v).decode() for v in range(L.isplib_b200_variant_count())]
+
+
+def spmm_csr(reduce, rowptr32, col32, val, x, plan: Plan, variant: int = VARIANT_AUTO, *,
+             out=None, arg_out=None, flags: int = 0, row_divisor=None, edge_ids=None,
+             arg_sentinel: Optional[int] = None) -> Tuple[torch.Tensor, Optional[torch.Tensor]]:
+    """out[, arg_out] = REDUCE(A, x) through isplib_b200_spmm_csr(_ex)."""
+    code = REDUCE_CODE[reduce] if isinstance(reduce, str) else int(reduce)
+    assert x.is_cuda and x.dtype == torch.float32 and x.dim() == 2 and x.stride(1) == 1
+    M, nnz = plan.m, plan.nnz
+    N, K = x.shape
+    is_arg = code in (MAX, MIN)
+    if out is None:
+        out = torch.empty((M, K), dtype=torch.float32, device=x.device)
+    if is_arg and arg_out is None:
+        arg_out = torch.empty((M, K), dtype=torch.int64, device=x.device)
+    ws_bytes = ctypes.c_size_t(0)
+    check(lib().isplib_b200_spmm_workspace_bytes(ctypes.byref(plan.info), K, code, ctypes.byref(ws_bytes)),
+          "spmm_workspace_bytes")
+    ws = _dev_bytes(ws_bytes.value, x.device)
+    ldx = x.stride(0) if N > 1 else max(K, x.stride(0))
+    ldo = out.stride(0) if M > 1 else max(K, out.stride(0))
+    common = (code, M, N, K, nnz, _p(rowptr32), _p(col32), _p(val), _p(x), ldx, _p(out), ldo,
+              _p(arg_out) if is_arg else None, ctypes.byref(plan.info), plan.ptr, _aligned_ptr(ws), ws_bytes.value)
+    if flags or row_divisor is not None or edge_ids is not None or arg_sentinel is not None:
+        st = lib().isplib_b200_spmm_csr_ex(*common, variant, flags, _p(row_divisor), _p(edge_ids),
+                                           nnz if arg_sentinel is None else int(arg_sentinel), _stream(x.device))
+    else:
+        st = lib().isplib_b200_spmm_csr(*common, variant, _stream(x.device))
+    check(st, "spmm_csr")
+    return out, (arg_out if is_arg else None)
+
+
+def spmm_autotune(reduce, rowptr32, col32, val, x, plan: Plan, iters: int = 3):
+    """(best_variant, [ms per variant]) -- isplib_b200_spmm_autotune."""
+    code = REDUCE_CODE[reduce] if isinstance(reduce, str) else int(reduce)
+    M, nnz = plan.m, plan.nnz
+    N, K = x.shape
+    is_arg = code in (MAX, MIN)
+    out = torch.empty((M, K), dtype=torch.float32, device=x.device)
+    arg_out = torch.empty((M, K), dtype=torch.int64, device=x.device) if is_arg else None
+    ws_bytes = ctypes.c_size_t(0)
+    check(lib().isplib_b200_spmm_workspace_bytes(ctypes.byref(plan.info), K, code, ctypes.byref(ws_bytes)),
+          "spmm_workspace_bytes")
+    ws = _dev_bytes(ws_bytes.value, x.device)
+    nv = lib().isplib_b200_variant_count()
+    times = (ctypes.c_float * nv)()
+    best = ctypes.c_int(0)
+    check(lib().isplib_b200_spmm_autotune(code, M, N, K, nnz, _p(rowptr32), _p(col32), _p(val), _p(x), x.stride(0),
+                                          _p(out), K, _p(arg_out), ctypes.byref(plan.info), plan.ptr,
+                                          _aligned_ptr(ws), ws_bytes.value, iters, ctypes.byref(best), times,
+                                          _stream(x.device)), "spmm_autotune")
+    return best.value, list(times)
+
+
+def csr_transpose(rowptr32, col32, n: int):
+    """(colptr, row_t, csr2csc), all int32 on the device -- isplib_b200_csr_transpose."""
+    m, nnz = rowptr32.numel() - 1, col32.numel()
+    dev = rowptr32.device
+    colptr = torch.empty(n + 1, dtype=torch.int32, device=dev)
+    row_t = torch.empty(nnz, dtype=torch.int32, device=dev)
+    csr2csc = torch.empty(nnz, dtype=torch.int32, device=dev)
+    ws_bytes = ctypes.c_size_t(0)
+    check(lib().isplib_b200_csr_transpose_workspace_bytes(m, n, nnz, ctypes.byref(ws_bytes)), "transpose_ws")
+    ws = _dev_bytes(ws_bytes.value, dev)
+    check(lib().isplib_b200_csr_transpose(m, n, nnz, _p(rowptr32), _p(col32), _p(colptr), _p(row_t), _p(csr2csc),
+                                          _aligned_ptr(ws), ws_bytes.value, _stream(dev)), "csr_transpose")
+    return colptr, row_t, csr2csc
+
+
+def permute_values(val, csr2csc, row_t, rowptr32, mean_weights: bool):
+    nnz = csr2csc.numel()
+    out = torch.empty(nnz, dtype=torch.float32, device=csr2csc.device)
+    check(lib().isplib_b200_permute_values(nnz, _p(val), _p(csr2csc), _p(row_t), _p(rowptr32),
+                                           1 if mean_weights else 0, _p(out), _stream(csr2csc.device)),
+          "permute_values")
+    return out
+
+
+def spmm_arg_backward(col32, val, x, arg, grad_out, n: int, need_grad_x=True, need_grad_val=False,
+                      arg_sentinel: Optional[int] = None):
+    M, K = grad_out.shape
+    nnz = col32.numel()
+    dev = grad_out.device
+    gx = torch.empty((n, K), dtype=torch.float32, device=dev) if need_grad_x else None
+    gv = torch.empty(nnz, dtype=torch.float32, device=dev) if need_grad_val else None
+    check(lib().isplib_b200_spmm_arg_backward(M, n, K, nnz, _p(col32), _p(val), _p(x), K if x is None else x.stride(0),
+                                              _p(arg), arg.stride(0), nnz if arg_sentinel is None else arg_sentinel,
+                                              _p(grad_out), grad_out.stride(0), _p(gx), K, _p(gv), 1, _stream(dev)),
+          "spmm_arg_backward")
+    return gx, gv
+
+
+def narrow_i64_to_i32(src: torch.Tensor) -> torch.Tensor:
+    assert src.is_cuda and src.dtype == torch.int64 and src.is_contiguous()
+    dst = torch.empty(src.shape, dtype=torch.int32, device=src.device)
+    flag = torch.zeros(1, dtype=torch.int32, device=src.device)
+    check(lib().isplib_b200_narrow_i64_to_i32(src.numel(), _p(src), _p(dst), _p(flag), _stream(src.device)),
+          "narrow_i64_to_i32")
+    if int(flag.item()) != 0:
+        raise IsplibError(256, "narrow_i64_to_i32 (value out of int32 range)")
+    return dst

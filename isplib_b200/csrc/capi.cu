@@ -1,0 +1,292 @@
+// capi.cu -- extern "C" entry points declared in include/isplib_b200.h:
+// argument validation, plan/workspace pointer carving, variant selection, on-device
+// autotune, and the literal host-pointer replacement of the reference's fusedMM_csr.
+#include "common.cuh"
+#include <float.h>
+#include <stdio.h>
+#include <string.h>
+#include <vector>
+
+using namespace isplib;
+
+extern "C" int isplib_b200_abi_version(void) { return ISPLIB_B200_ABI_VERSION; }
+
+extern "C" const char* isplib_b200_status_string(int status) {
+    static thread_local char buf[128];
+    switch (status) {
+        case ISPLIB_SUCCESS: return "success";
+        case ISPLIB_FAIL: return "failed (inconsistent CSR structure or plan)";
+        case ISPLIB_NOT_ENOUGH_MEM: return "plan or workspace buffer missing or too small";
+        case ISPLIB_NO_OPT_IMPL: return "no kernel for this reduction/variant/message";
+        case ISPLIB_INVALID_ARG: return "invalid argument (null, negative, misaligned or >= 2^31)";
+        default: break;
+    }
+    if (status >= ISPLIB_CUDA_ERROR_BASE) {
+        snprintf(buf, sizeof(buf), "CUDA error %d: %s", status - ISPLIB_CUDA_ERROR_BASE,
+                 cudaGetErrorString((cudaError_t)(status - ISPLIB_CUDA_ERROR_BASE)));
+        return buf;
+    }
+    snprintf(buf, sizeof(buf), "unknown status %d", status);
+    return buf;
+}
+
+extern "C" int isplib_b200_variant_count(void) { return variant_count(); }
+
+extern "C" const char* isplib_b200_variant_name(int variant) {
+    const VariantDesc* d = variant_desc(variant);
+    return d ? d->name : "invalid";
+}
+
+extern "C" int isplib_b200_variant_supported(int variant, int reduce, int64_t k, int64_t ldx,
+                                             int64_t ldo, const void* x, const void* out) {
+    return spmm_variant_supported(variant, reduce, k, ldx, ldo, x, out) ? 1 : 0;
+}
+
+extern "C" int isplib_b200_variant_default(int reduce, int64_t k, int64_t ldx, int64_t ldo,
+                                           const void* x, const void* out, double avg_degree) {
+    return spmm_variant_default(reduce, k, ldx, ldo, x, out, avg_degree);
+}
+
+static int fill_params(SpmmParams& p, int reduce, int64_t m, int64_t n, int64_t k, int64_t nnz,
+                       const int32_t* rowptr, const int32_t* col, const float* val,
+                       const float* x, int64_t ldx, float* out, int64_t ldo, int64_t* arg_out,
+                       const isplib_b200_plan_info* info, const void* plan_dev,
+                       void* workspace, size_t workspace_bytes, int flags,
+                       const float* row_divisor, const int32_t* edge_ids, int64_t arg_sentinel) {
+    if (reduce < 0 || reduce > 3) return ISPLIB_NO_OPT_IMPL;
+    if (m < 0 || n < 0 || k < 0 || nnz < 0) return ISPLIB_INVALID_ARG;
+    if (m >= INT32_MAX - 1 || nnz >= INT32_MAX || k >= INT32_MAX || n >= INT32_MAX) return ISPLIB_INVALID_ARG;
+    if (m == 0 || k == 0) { memset(&p, 0, sizeof(p)); return ISPLIB_SUCCESS; }
+    if (!rowptr || !out || !info || !plan_dev) return ISPLIB_INVALID_ARG;
+    if (nnz > 0 && (!col || !x)) return ISPLIB_INVALID_ARG;
+    if (ldx < k || ldo < k) return ISPLIB_INVALID_ARG;
+    const bool is_arg = (reduce == ISPLIB_REDUCE_MAX || reduce == ISPLIB_REDUCE_MIN);
+    if (is_arg && !arg_out) return ISPLIB_INVALID_ARG;
+    if (info->m != m || info->nnz != nnz) return ISPLIB_FAIL;
+    if ((reinterpret_cast<uintptr_t>(plan_dev) & 255u) != 0) return ISPLIB_INVALID_ARG;
+
+    size_t need = 0;
+    int st = isplib_b200_spmm_workspace_bytes(info, k, reduce, &need);
+    if (st) return st;
+    const size_t part_elems = (size_t)info->num_split_items * (size_t)k;
+    float* part_val = nullptr;
+    int32_t* part_arg = nullptr;
+    if (part_elems > 0) {
+        if (!workspace || workspace_bytes < need) return ISPLIB_NOT_ENOUGH_MEM;
+        char* w = (char*)align_up((size_t)(uintptr_t)workspace, 256);
+        part_val = (float*)w;
+        if (is_arg) part_arg = (int32_t*)(w + align_up(part_elems * 4, 256));
+    }
+
+    const PlanLayout L = plan_layout(m, nnz, info->seg_len);
+    const char* base = (const char*)plan_dev;
+    p.rowptr = rowptr;
+    p.col = col;
+    p.val = val;
+    p.x = x;
+    p.out = out;
+    p.arg_out = (long long*)arg_out;
+    p.seg_off = (const int32_t*)(base + L.off_seg_off);
+    p.part_off = (const int32_t*)(base + L.off_part_off);
+    p.item_row = (const int32_t*)(base + L.off_item_row);
+    p.split_rows = (const int32_t*)(base + L.off_split_rows);
+    p.part_val = part_val;
+    p.part_arg = part_arg;
+    p.row_div = row_divisor;
+    p.edge_ids = edge_ids;
+    p.ldx = ldx;
+    p.ldo = ldo;
+    p.arg_sentinel = arg_sentinel;
+    p.m = (int)m;
+    p.k = (int)k;
+    p.tile_w = (int)k;
+    p.num_items = (int)info->num_items;
+    p.num_split_rows = (int)info->num_split_rows;
+    p.seg_len = info->seg_len;
+    p.flags = flags;
+    p.div_mode = row_divisor ? 2 : (reduce == ISPLIB_REDUCE_MEAN ? 1 : 0);
+    return ISPLIB_SUCCESS;
+}
+
+extern "C" int isplib_b200_spmm_csr_ex(int reduce, int64_t m, int64_t n, int64_t k, int64_t nnz,
+                                       const int32_t* rowptr, const int32_t* col, const float* val,
+                                       const float* x, int64_t ldx, float* out, int64_t ldo,
+                                       int64_t* arg_out,
+                                       const isplib_b200_plan_info* info, const void* plan_dev,
+                                       void* workspace, size_t workspace_bytes,
+                                       int variant, int flags, const float* row_divisor,
+                                       const int32_t* edge_ids, int64_t arg_sentinel,
+                                       isplib_stream_t stream) {
+    SpmmParams p;
+    int st = fill_params(p, reduce, m, n, k, nnz, rowptr, col, val, x, ldx, out, ldo, arg_out, info,
+                         plan_dev, workspace, workspace_bytes, flags, row_divisor, edge_ids, arg_sentinel);
+    if (st) return st;
+    if (m == 0 || k == 0) return ISPLIB_SUCCESS;
+    if (variant == ISPLIB_VARIANT_AUTO)
+        variant = spmm_variant_default(reduce, k, ldx, ldo, x, out, m > 0 ? (double)nnz / (double)m : 0.0);
+    if (!spmm_variant_supported(variant, reduce, k, ldx, ldo, x, out)) return ISPLIB_NO_OPT_IMPL;
+    return launch_spmm(reduce, p, nnz, variant, (cudaStream_t)stream);
+}
+
+extern "C" int isplib_b200_spmm_csr(int reduce, int64_t m, int64_t n, int64_t k, int64_t nnz,
+                                    const int32_t* rowptr, const int32_t* col, const float* val,
+                                    const float* x, int64_t ldx, float* out, int64_t ldo,
+                                    int64_t* arg_out,
+                                    const isplib_b200_plan_info* info, const void* plan_dev,
+                                    void* workspace, size_t workspace_bytes,
+                                    int variant, isplib_stream_t stream) {
+    return isplib_b200_spmm_csr_ex(reduce, m, n, k, nnz, rowptr, col, val, x, ldx, out, ldo, arg_out, info,
+                                   plan_dev, workspace, workspace_bytes, variant, 0, nullptr, nullptr, nnz,
+                                   stream);
+}
+
+extern "C" int isplib_b200_spmm_autotune(int reduce, int64_t m, int64_t n, int64_t k, int64_t nnz,
+                                         const int32_t* rowptr, const int32_t* col, const float* val,
+                                         const float* x, int64_t ldx, float* out, int64_t ldo,
+                                         int64_t* arg_out,
+                                         const isplib_b200_plan_info* info, const void* plan_dev,
+                                         void* workspace, size_t workspace_bytes,
+                                         int iters, int* best_variant, float* times_ms,
+                                         isplib_stream_t stream_) {
+    cudaStream_t stream = (cudaStream_t)stream_;
+    if (!best_variant) return ISPLIB_INVALID_ARG;
+    if (iters <= 0) iters = 3;
+    SpmmParams p;
+    int st = fill_params(p, reduce, m, n, k, nnz, rowptr, col, val, x, ldx, out, ldo, arg_out, info,
+                         plan_dev, workspace, workspace_bytes, 0, nullptr, nullptr, nnz);
+    if (st) return st;
+    const int nv = variant_count();
+    *best_variant = spmm_variant_default(reduce, k, ldx, ldo, x, out, m > 0 ? (double)nnz / (double)m : 0.0);
+    if (times_ms) for (int v = 0; v < nv; ++v) times_ms[v] = -1.f;
+    if (m == 0 || k == 0) return ISPLIB_SUCCESS;
+
+    cudaEvent_t e0, e1;
+    ISPLIB_CUDA_TRY(cudaEventCreate(&e0));
+    ISPLIB_CUDA_TRY(cudaEventCreate(&e1));
+    float best = FLT_MAX;
+    int rc = ISPLIB_SUCCESS;
+    for (int v = 0; v < nv && rc == ISPLIB_SUCCESS; ++v) {
+        if (!spmm_variant_supported(v, reduce, k, ldx, ldo, x, out)) continue;
+        rc = launch_spmm(reduce, p, nnz, v, stream);  // warm-up
+        if (rc) break;
+        cudaEventRecord(e0, stream);
+        for (int it = 0; it < iters && rc == ISPLIB_SUCCESS; ++it) rc = launch_spmm(reduce, p, nnz, v, stream);
+        cudaEventRecord(e1, stream);
+        cudaError_t ce = cudaEventSynchronize(e1);
+        if (ce != cudaSuccess) { rc = ISPLIB_CUDA_ERROR_BASE + (int)ce; break; }
+        float ms = 0.f;
+        cudaEventElapsedTime(&ms, e0, e1);
+        ms /= (float)iters;
+        if (times_ms) times_ms[v] = ms;
+        if (ms < best) { best = ms; *best_variant = v; }
+    }
+    cudaEventDestroy(e0);
+    cudaEventDestroy(e1);
+    return rc;
+}
+
+// --------------------------------------------------------------------------------------
+// literal replacement of fusedMM_csr (host pointers, int64 indices, accumulate into z)
+// --------------------------------------------------------------------------------------
+namespace {
+struct DevBuf {
+    void* p = nullptr;
+    ~DevBuf() { if (p) cudaFree(p); }
+    int alloc(size_t bytes) { return cudaMalloc(&p, bytes ? bytes : 1) == cudaSuccess ? 0 : ISPLIB_NOT_ENOUGH_MEM; }
+};
+
+__global__ void merge_host_init_kernel(int op, long long m, int k, const float* __restrict__ z_in,
+                                       const long long* __restrict__ a_in, float* __restrict__ z,
+                                       long long* __restrict__ a, long long ldz) {
+    // z/z_arg arrive pre-initialised by the reference wrapper (csrc/fusedmm.cpp:147-152,171)
+    // and fusedMM_csr accumulates into them; fold that initial content back in.
+    const long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= m * k) return;
+    const long long i = t / k;
+    const int kk = (int)(t - i * k);
+    const long long o = i * ldz + kk;
+    if (op == 0) { z[o] = z_in[o] + z[o]; return; }
+    const float cur = z_in[o], cand = z[o];
+    // the pre-existing content comes first in scan order: it stays unless strictly beaten
+    const bool take = (op == 1) ? (cand > cur) : (cand < cur);
+    if (!take) { z[o] = cur; a[o] = a_in[o]; }
+}
+}  // namespace
+
+extern "C" int isplib_b200_fusedmm_csr_host(int32_t imessage, int64_t m, int64_t n, int64_t k,
+                                            float alpha, int64_t nnz, int64_t rows, int64_t cols,
+                                            const float* val, const int64_t* indx,
+                                            const int64_t* pntrb, const int64_t* pntre,
+                                            const float* x, int64_t ldx, const float* y, int64_t ldy,
+                                            float beta, float* z, int64_t ldz, int64_t* z_arg) {
+    (void)alpha; (void)beta; (void)rows; (void)cols; (void)x; (void)ldx;
+    // message decode: csrc/fusedMM.h:18-74; only the four SpMM messages of
+    // csrc/fusedmm.cpp:168-186 are implemented
+    int reduce;
+    switch (imessage) {
+        case 0x11102: reduce = ISPLIB_REDUCE_SUM; break;
+        case 0x21102: reduce = ISPLIB_REDUCE_MAX; break;
+        case 0x31102: reduce = ISPLIB_REDUCE_MIN; break;
+        case 0x13102: reduce = ISPLIB_REDUCE_MEAN; break;
+        default: return ISPLIB_NO_OPT_IMPL;
+    }
+    if (m < 0 || n < 0 || k < 0 || nnz < 0) return ISPLIB_FAIL;
+    if (m == 0 || k == 0) return ISPLIB_SUCCESS;
+    if (!pntrb || !pntre || !z || (nnz > 0 && (!indx || !y))) return ISPLIB_FAIL;
+    if (pntre != pntrb + 1) return ISPLIB_NO_OPT_IMPL;  // the wrapper always passes rowptr+1
+    if (ldy < k || ldz < k) return ISPLIB_FAIL;
+    const bool is_arg = reduce == ISPLIB_REDUCE_MAX || reduce == ISPLIB_REDUCE_MIN;
+    if (is_arg && !z_arg) return ISPLIB_FAIL;
+
+    cudaStream_t stream = 0;
+    DevBuf d_rp64, d_col64, d_rp, d_col, d_val, d_y, d_z, d_zin, d_arg, d_argin, d_plan, d_ws, d_flag;
+    int st;
+    const size_t zbytes = ((size_t)(m - 1) * ldz + k) * 4, abytes = ((size_t)(m - 1) * ldz + k) * 8;
+    const size_t ybytes = n > 0 ? ((size_t)(n - 1) * ldy + k) * 4 : 0;
+    if ((st = d_rp64.alloc((m + 1) * 8)) || (st = d_col64.alloc(nnz * 8)) || (st = d_rp.alloc((m + 1) * 4)) ||
+        (st = d_col.alloc(nnz * 4)) || (st = d_val.alloc(nnz * 4)) || (st = d_y.alloc(ybytes)) ||
+        (st = d_z.alloc(zbytes)) || (st = d_zin.alloc(zbytes)) || (st = d_flag.alloc(4)))
+        return st;
+    if (is_arg && ((st = d_arg.alloc(abytes)) || (st = d_argin.alloc(abytes)))) return st;
+    ISPLIB_CUDA_TRY(cudaMemcpyAsync(d_rp64.p, pntrb, (m + 1) * 8, cudaMemcpyHostToDevice, stream));
+    ISPLIB_CUDA_TRY(cudaMemcpyAsync(d_col64.p, indx, nnz * 8, cudaMemcpyHostToDevice, stream));
+    if (val) ISPLIB_CUDA_TRY(cudaMemcpyAsync(d_val.p, val, nnz * 4, cudaMemcpyHostToDevice, stream));
+    ISPLIB_CUDA_TRY(cudaMemcpyAsync(d_y.p, y, ybytes, cudaMemcpyHostToDevice, stream));
+    ISPLIB_CUDA_TRY(cudaMemcpyAsync(d_zin.p, z, zbytes, cudaMemcpyHostToDevice, stream));
+    if (is_arg) ISPLIB_CUDA_TRY(cudaMemcpyAsync(d_argin.p, z_arg, abytes, cudaMemcpyHostToDevice, stream));
+    // start from the caller's content so row padding (ldz > k) survives the round trip
+    ISPLIB_CUDA_TRY(cudaMemcpyAsync(d_z.p, d_zin.p, zbytes, cudaMemcpyDeviceToDevice, stream));
+    if (is_arg) ISPLIB_CUDA_TRY(cudaMemcpyAsync(d_arg.p, d_argin.p, abytes, cudaMemcpyDeviceToDevice, stream));
+    ISPLIB_CUDA_TRY(cudaMemsetAsync(d_flag.p, 0, 4, stream));
+    if ((st = isplib_b200_narrow_i64_to_i32(m + 1, (const int64_t*)d_rp64.p, (int32_t*)d_rp.p, (int32_t*)d_flag.p, stream))) return st;
+    if ((st = isplib_b200_narrow_i64_to_i32(nnz, (const int64_t*)d_col64.p, (int32_t*)d_col.p, (int32_t*)d_flag.p, stream))) return st;
+    int32_t flag = 0;
+    ISPLIB_CUDA_TRY(cudaMemcpyAsync(&flag, d_flag.p, 4, cudaMemcpyDeviceToHost, stream));
+    ISPLIB_CUDA_TRY(cudaStreamSynchronize(stream));
+    if (flag) return ISPLIB_INVALID_ARG;
+
+    size_t pbytes = 0, wbytes = 0;
+    if ((st = isplib_b200_plan_bytes(m, nnz, 0, &pbytes))) return st;
+    if ((st = d_plan.alloc(pbytes))) return st;
+    isplib_b200_plan_info info;
+    if ((st = isplib_b200_plan_build(m, nnz, (const int32_t*)d_rp.p, 0, d_plan.p, pbytes, &info, stream))) return st;
+    if ((st = isplib_b200_spmm_workspace_bytes(&info, k, reduce, &wbytes))) return st;
+    if ((st = d_ws.alloc(wbytes))) return st;
+    st = isplib_b200_spmm_csr(reduce, m, n, k, nnz, (const int32_t*)d_rp.p, (const int32_t*)d_col.p,
+                              val ? (const float*)d_val.p : nullptr, (const float*)d_y.p, ldy, (float*)d_z.p,
+                              ldz, (int64_t*)d_arg.p, &info, d_plan.p, d_ws.p, wbytes, ISPLIB_VARIANT_AUTO, stream);
+    if (st) return st;
+    if (reduce != ISPLIB_REDUCE_MEAN) {
+        // mean: the wrapper passes zeros (csrc/fusedmm.cpp:152) and sum-then-divide would not
+        // compose with a non-zero initial z anyway; sum/max/min fold the initial z back in.
+        const long long total = (long long)m * k;
+        merge_host_init_kernel<<<(unsigned)((total + 255) / 256), 256, 0, stream>>>(
+            reduce == ISPLIB_REDUCE_SUM ? 0 : (reduce == ISPLIB_REDUCE_MAX ? 1 : 2), (long long)m, (int)k,
+            (const float*)d_zin.p, (const long long*)d_argin.p, (float*)d_z.p, (long long*)d_arg.p, (long long)ldz);
+        ISPLIB_LAUNCH_CHECK();
+    }
+    ISPLIB_CUDA_TRY(cudaMemcpyAsync(z, d_z.p, zbytes, cudaMemcpyDeviceToHost, stream));
+    if (is_arg) ISPLIB_CUDA_TRY(cudaMemcpyAsync(z_arg, d_arg.p, abytes, cudaMemcpyDeviceToHost, stream));
+    ISPLIB_CUDA_TRY(cudaStreamSynchronize(stream));
+    return ISPLIB_SUCCESS;
+}

@@ -1,0 +1,105 @@
+// common.cuh -- shared declarations of the isplib_b200 CUDA library (sm_100a only).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stddef.h>
+#include "../../include/isplib_b200.h"
+
+#if defined(__CUDA_ARCH__) && (__CUDA_ARCH__ < 1000)
+#error "isplib_b200 is written for sm_100a (B200) only"
+#endif
+
+namespace isplib {
+
+#define ISPLIB_CUDA_TRY(expr)                                            \
+    do {                                                                 \
+        cudaError_t _e = (expr);                                         \
+        if (_e != cudaSuccess) return ISPLIB_CUDA_ERROR_BASE + (int)_e;  \
+    } while (0)
+
+#define ISPLIB_LAUNCH_CHECK()                                            \
+    do {                                                                 \
+        cudaError_t _e = cudaGetLastError();                             \
+        if (_e != cudaSuccess) return ISPLIB_CUDA_ERROR_BASE + (int)_e;  \
+    } while (0)
+
+constexpr int kDefaultSegLen = 256;
+constexpr int kNumSMs = 148;  // B200: 2 dies x 74 SMs
+
+static inline size_t align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
+
+// ---- plan layout inside the caller's device buffer ---------------------------------
+// [counters: 8 x int64][seg_off: m+1][part_off: m+1][item_row: wmax][split_rows: m][temp...]
+struct PlanLayout {
+    size_t off_counters, off_seg_off, off_part_off, off_item_row, off_split_rows, off_temp;
+    size_t persistent_bytes;  // everything the SpMM kernels read
+    int64_t wmax;
+};
+
+static inline int32_t effective_seg_len(int32_t seg_len) {
+    if (seg_len <= 0) return kDefaultSegLen;
+    // multiple of 32 so a warp's 32-wide index chunks stay aligned to the segment start
+    int32_t s = (seg_len + 31) / 32 * 32;
+    return s;
+}
+
+static inline PlanLayout plan_layout(int64_t m, int64_t nnz, int32_t seg_len) {
+    PlanLayout L;
+    const int32_t S = effective_seg_len(seg_len);
+    L.wmax = m + nnz / S + 1;
+    size_t o = 0;
+    L.off_counters = o;   o = align_up(o + 8 * sizeof(int64_t), 256);
+    L.off_seg_off = o;    o = align_up(o + (size_t)(m + 1) * 4, 256);
+    L.off_part_off = o;   o = align_up(o + (size_t)(m + 1) * 4, 256);
+    L.off_item_row = o;   o = align_up(o + (size_t)L.wmax * 4, 256);
+    L.off_split_rows = o; o = align_up(o + (size_t)(m > 0 ? m : 1) * 4, 256);
+    L.persistent_bytes = o;
+    L.off_temp = o;
+    return L;
+}
+
+enum PlanCounter { PC_ITEMS = 0, PC_SPLIT_ROWS = 1, PC_SPLIT_ITEMS = 2, PC_MAX_DEG = 3, PC_EMPTY = 4 };
+
+// ---- forward kernel parameter block --------------------------------------------------
+struct SpmmParams {
+    const int32_t* __restrict__ rowptr;
+    const int32_t* __restrict__ col;
+    const float* __restrict__ val;      // nullable
+    const float* __restrict__ x;
+    float* __restrict__ out;
+    long long* __restrict__ arg_out;    // nullable
+    const int32_t* __restrict__ seg_off;
+    const int32_t* __restrict__ part_off;
+    const int32_t* __restrict__ item_row;
+    const int32_t* __restrict__ split_rows;
+    float* __restrict__ part_val;       // [num_split_items, k]
+    int32_t* __restrict__ part_arg;     // [num_split_items, k] (max/min)
+    const float* __restrict__ row_div;  // nullable
+    const int32_t* __restrict__ edge_ids;  // nullable
+    long long ldx, ldo, arg_sentinel;
+    int m, k, tile_w, num_items, num_split_rows, seg_len;
+    int flags;      // ISPLIB_FLAG_*
+    int div_mode;   // 0 none, 1 by max(deg,1), 2 by row_div[]
+};
+
+enum Op { OP_SUM = 0, OP_MAX = 1, OP_MIN = 2 };
+
+struct VariantDesc {
+    const char* name;
+    int method;   // 0 = warp-per-segment register gather
+    int warps;    // warps per CTA
+    int unroll;   // gathers in flight per lane group
+    int kt;       // K tile width in elements, 0 = widest the lane mapping allows
+};
+
+int variant_count();
+const VariantDesc* variant_desc(int v);
+
+// implemented in spmm_fwd.cu
+int launch_spmm(int reduce, const SpmmParams& base, int64_t nnz, int variant, cudaStream_t stream);
+bool spmm_variant_supported(int variant, int reduce, int64_t k, int64_t ldx, int64_t ldo,
+                            const void* x, const void* out);
+int spmm_variant_default(int reduce, int64_t k, int64_t ldx, int64_t ldo, const void* x,
+                         const void* out, double avg_degree);
+
+}  // namespace isplib

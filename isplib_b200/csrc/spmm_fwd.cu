@@ -1,0 +1,485 @@
+// spmm_fwd.cu -- CSR SpMM forward kernels (sum / mean / max / min) for sm_100a.
+//
+// Replaces the body of fusedMM_csr as called at /root/reference/csrc/fusedmm.cpp:198
+// (declared csrc/fusedMM.h:77-99; real body un-vendored, configure:2-7).
+//
+// Design (DESIGN.md "Kernels"): the path is an irregular gather-reduce bound by
+// HBM/L2 bandwidth -- no tensor cores.  Work is cut into row-aligned SEGMENTS of at
+// most seg_len stored entries (the plan, graph_ops.cu); one warp owns one segment.
+//   * col/val are read 32 at a time, coalesced, streaming (ld.global.cs), one chunk
+//     prefetched ahead, and broadcast with warp shuffles;
+//   * a lane group of G lanes covers one K tile of a dense row with 16-byte (float4)
+//     loads, 32/G entries are gathered per warp instruction and U of them are kept in
+//     flight per lane group before the first use (memory-level parallelism);
+//   * fp32 accumulators (and the running arg-edge for max/min) stay in registers;
+//   * rows that fit one segment are finalised in place (mean divide, arg widening to
+//     int64, optional merge with a previous block's result); longer rows write one
+//     partial per segment and a fix-up kernel merges them in segment order, so the
+//     result is deterministic and max/min/arg stay bit-exact however a row is split;
+//   * blockIdx.y walks K tiles slowest, so with a narrow tile the whole grid sweeps
+//     one [N, tile] column slab of X at a time and the slab stays L2-resident.
+#include "common.cuh"
+#include <float.h>
+#include <limits.h>
+
+namespace isplib {
+
+// ------------------------------------------------------------------------------------
+// variant table
+// ------------------------------------------------------------------------------------
+static const VariantDesc kVariants[] = {
+    {"seg/w8/u8/kfull", 0, 8, 8, 0},
+    {"seg/w8/u4/kfull", 0, 8, 4, 0},
+    {"seg/w4/u8/kfull", 0, 4, 8, 0},
+    {"seg/w4/u4/kfull", 0, 4, 4, 0},
+    {"seg/w8/u8/kt128", 0, 8, 8, 128},
+    {"seg/w8/u8/kt64", 0, 8, 8, 64},
+    {"seg/w8/u8/kt32", 0, 8, 8, 32},
+    {"seg/w8/u4/kt64", 0, 8, 4, 64},
+    {"seg/w8/u4/kt32", 0, 8, 4, 32},
+};
+int variant_count() { return (int)(sizeof(kVariants) / sizeof(kVariants[0])); }
+const VariantDesc* variant_desc(int v) {
+    return (v >= 0 && v < variant_count()) ? &kVariants[v] : nullptr;
+}
+
+// ------------------------------------------------------------------------------------
+// small device helpers
+// ------------------------------------------------------------------------------------
+template <int VEC> struct VecT;
+template <> struct VecT<4> { using type = float4; };
+template <> struct VecT<1> { using type = float; };
+
+template <int VEC>
+__device__ __forceinline__ void load_vec(const float* __restrict__ p, float (&v)[VEC]) {
+    if constexpr (VEC == 4) {
+        const float4 t = __ldg(reinterpret_cast<const float4*>(p));
+        v[0] = t.x; v[1] = t.y; v[2] = t.z; v[3] = t.w;
+    } else {
+        v[0] = __ldg(p);
+    }
+}
+
+template <int VEC>
+__device__ __forceinline__ void store_vec_f(float* p, const float (&v)[VEC]) {
+    if constexpr (VEC == 4) {
+        __stcs(reinterpret_cast<float4*>(p), make_float4(v[0], v[1], v[2], v[3]));
+    } else {
+        __stcs(p, v[0]);
+    }
+}
+
+template <int VEC>
+__device__ __forceinline__ void store_vec_i64(long long* p, const long long (&v)[VEC]) {
+    if constexpr (VEC == 4) {
+        __stcs(reinterpret_cast<longlong2*>(p), make_longlong2(v[0], v[1]));
+        __stcs(reinterpret_cast<longlong2*>(p) + 1, make_longlong2(v[2], v[3]));
+    } else {
+        __stcs(p, v[0]);
+    }
+}
+
+template <int VEC>
+__device__ __forceinline__ void store_vec_i32(int* p, const int (&v)[VEC]) {
+    if constexpr (VEC == 4) {
+        *reinterpret_cast<int4*>(p) = make_int4(v[0], v[1], v[2], v[3]);
+    } else {
+        *p = v[0];
+    }
+}
+
+template <int OP> __device__ __forceinline__ float init_value() {
+    // csrc/fusedmm.cpp:147-152: zeros / numeric_limits<float>::lowest() / ::max()
+    return OP == OP_SUM ? 0.f : (OP == OP_MAX ? -FLT_MAX : FLT_MAX);
+}
+
+constexpr int kNoArg = INT_MAX;  // "no entry won yet" (local edge ids are < 2^31-1)
+
+// strict compare, first (smallest edge id) wins: mirrors oracle/fusedmm_oracle.c
+template <int OP>
+__device__ __forceinline__ bool better(float cand, float cur) {
+    return OP == OP_MAX ? (cand > cur) : (cand < cur);
+}
+template <int OP, typename IdT>
+__device__ __forceinline__ bool better_lex(float cand, IdT cand_id, float cur, IdT cur_id) {
+    return better<OP>(cand, cur) || (cand == cur && cand_id < cur_id);
+}
+
+// ------------------------------------------------------------------------------------
+// finalisation shared by the segment kernel (single-segment rows) and the fix-up kernel
+// ------------------------------------------------------------------------------------
+template <int OP, int VEC>
+__device__ __forceinline__ void finalize_store(const SpmmParams& p, int row, int deg, int kk,
+                                               float (&acc)[VEC], int (&arg)[VEC]) {
+    const size_t o = (size_t)row * (size_t)p.ldo + (size_t)kk;
+    if constexpr (OP == OP_SUM) {
+        if (p.flags & ISPLIB_FLAG_ACCUMULATE) {
+            float prev[VEC];
+            if constexpr (VEC == 4) {
+                const float4 t = *reinterpret_cast<const float4*>(p.out + o);
+                prev[0] = t.x; prev[1] = t.y; prev[2] = t.z; prev[3] = t.w;
+            } else {
+                prev[0] = p.out[o];
+            }
+#pragma unroll
+            for (int v = 0; v < VEC; ++v) acc[v] = prev[v] + acc[v];
+        }
+        if (p.div_mode) {
+            const float d = (p.div_mode == 2) ? __ldg(p.row_div + row) : (float)max(deg, 1);
+#pragma unroll
+            for (int v = 0; v < VEC; ++v) acc[v] = __fdiv_rn(acc[v], d);
+        }
+        store_vec_f<VEC>(p.out + o, acc);
+    } else {
+        long long gid[VEC];
+#pragma unroll
+        for (int v = 0; v < VEC; ++v) {
+            if (arg[v] == kNoArg) gid[v] = p.arg_sentinel;
+            else gid[v] = p.edge_ids ? (long long)__ldg(p.edge_ids + arg[v]) : (long long)arg[v];
+        }
+        if (p.flags & ISPLIB_FLAG_ACCUMULATE) {
+#pragma unroll
+            for (int v = 0; v < VEC; ++v) {
+                const float pv = p.out[o + v];
+                const long long pa = p.arg_out[o + v];
+                // previous block wins unless ours is strictly better / equal with smaller id
+                if (!better_lex<OP, long long>(acc[v], gid[v], pv, pa)) { acc[v] = pv; gid[v] = pa; }
+            }
+        }
+        if (p.flags & ISPLIB_FLAG_EMPTY_ZERO) {
+#pragma unroll
+            for (int v = 0; v < VEC; ++v) if (gid[v] == p.arg_sentinel) acc[v] = 0.f;
+        }
+        store_vec_f<VEC>(p.out + o, acc);
+        store_vec_i64<VEC>(p.arg_out + o, gid);
+    }
+}
+
+// ------------------------------------------------------------------------------------
+// main kernel: one warp = one row segment x one K tile
+// ------------------------------------------------------------------------------------
+template <int OP, int VEC, int G, int LPL, int U>
+__global__ void __launch_bounds__(256)
+spmm_seg_kernel(const __grid_constant__ SpmmParams p) {
+    constexpr int NG = 32 / G;         // lane groups per warp = entries gathered per step
+    constexpr unsigned FULL = 0xffffffffu;
+    static_assert(32 % (NG * U) == 0, "a 32-entry chunk must be a whole number of steps");
+
+    const int lane = threadIdx.x & 31;
+    const int item = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    if (item >= p.num_items) return;
+
+    const int row = __ldg(p.item_row + item);
+    const int so = __ldg(p.seg_off + row);
+    const int nseg = __ldg(p.seg_off + row + 1) - so;
+    const int s = item - so;
+    const int rb = __ldg(p.rowptr + row);
+    const int re = __ldg(p.rowptr + row + 1);
+    const int eb = rb + s * p.seg_len;
+    const int ee = min(re, eb + p.seg_len);
+
+    const int g = lane / G;
+    const int lg = lane % G;
+    const int k0 = blockIdx.y * p.tile_w;
+    const int kend = min(p.k, k0 + p.tile_w);
+
+    int koff[LPL];
+    bool kok[LPL];
+#pragma unroll
+    for (int j = 0; j < LPL; ++j) {
+        koff[j] = k0 + (lg + j * G) * VEC;
+        kok[j] = koff[j] < kend;
+    }
+
+    float acc[LPL][VEC];
+    int arg[LPL][VEC];
+#pragma unroll
+    for (int j = 0; j < LPL; ++j)
+#pragma unroll
+        for (int v = 0; v < VEC; ++v) { acc[j][v] = init_value<OP>(); arg[j][v] = kNoArg; }
+
+    const bool has_val = (p.val != nullptr);
+
+    // one 32-entry chunk of (col, val) per lane, one chunk prefetched ahead
+    int c_next = 0;
+    float a_next = 0.f;
+    if (eb + lane < ee) {
+        c_next = __ldcs(p.col + eb + lane);
+        a_next = has_val ? __ldcs(p.val + eb + lane) : 1.f;
+    }
+
+    for (int e0 = eb; e0 < ee; e0 += 32) {
+        const int c = c_next;
+        const float a = a_next;
+        const int cnt = min(32, ee - e0);
+        {
+            const int en = e0 + 32 + lane;
+            if (en < ee) {
+                c_next = __ldcs(p.col + en);
+                a_next = has_val ? __ldcs(p.val + en) : 1.f;
+            }
+        }
+        if (cnt == 32) {
+#pragma unroll
+            for (int t = 0; t < 32; t += NG * U) {
+                float xv[U][LPL][VEC];
+                float aa[U];
+#pragma unroll
+                for (int u = 0; u < U; ++u) {
+                    const int idx = t + u * NG + g;
+                    const int cc = __shfl_sync(FULL, c, idx);
+                    aa[u] = __shfl_sync(FULL, a, idx);
+                    const float* xr = p.x + (size_t)cc * (size_t)p.ldx;
+#pragma unroll
+                    for (int j = 0; j < LPL; ++j) {
+                        if (kok[j]) load_vec<VEC>(xr + koff[j], xv[u][j]);
+                        else {
+#pragma unroll
+                            for (int v = 0; v < VEC; ++v) xv[u][j][v] = 0.f;
+                        }
+                    }
+                }
+#pragma unroll
+                for (int u = 0; u < U; ++u) {
+                    const int e = e0 + t + u * NG + g;
+#pragma unroll
+                    for (int j = 0; j < LPL; ++j)
+#pragma unroll
+                        for (int v = 0; v < VEC; ++v) {
+                            if constexpr (OP == OP_SUM) {
+                                acc[j][v] = fmaf(aa[u], xv[u][j][v], acc[j][v]);
+                            } else {
+                                const float tt = __fmul_rn(aa[u], xv[u][j][v]);
+                                if (better<OP>(tt, acc[j][v])) { acc[j][v] = tt; arg[j][v] = e; }
+                            }
+                        }
+                }
+            }
+        } else {
+            // ragged tail of the segment: same steps, predicated per entry
+            for (int t = 0; t < cnt; t += NG * U) {
+                float xv[U][LPL][VEC];
+                float aa[U];
+                bool ok[U];
+#pragma unroll
+                for (int u = 0; u < U; ++u) {
+                    const int idx = t + u * NG + g;
+                    ok[u] = idx < cnt;
+                    const int cc = __shfl_sync(FULL, c, idx & 31);
+                    aa[u] = __shfl_sync(FULL, a, idx & 31);
+                    const float* xr = p.x + (size_t)cc * (size_t)p.ldx;
+#pragma unroll
+                    for (int j = 0; j < LPL; ++j) {
+                        if (ok[u] && kok[j]) load_vec<VEC>(xr + koff[j], xv[u][j]);
+                        else {
+#pragma unroll
+                            for (int v = 0; v < VEC; ++v) xv[u][j][v] = 0.f;
+                        }
+                    }
+                }
+#pragma unroll
+                for (int u = 0; u < U; ++u) {
+                    const int e = e0 + t + u * NG + g;
+                    if (ok[u]) {
+#pragma unroll
+                        for (int j = 0; j < LPL; ++j)
+#pragma unroll
+                            for (int v = 0; v < VEC; ++v) {
+                                if constexpr (OP == OP_SUM) {
+                                    acc[j][v] = fmaf(aa[u], xv[u][j][v], acc[j][v]);
+                                } else {
+                                    const float tt = __fmul_rn(aa[u], xv[u][j][v]);
+                                    if (better<OP>(tt, acc[j][v])) { acc[j][v] = tt; arg[j][v] = e; }
+                                }
+                            }
+                    }
+                }
+            }
+        }
+    }
+
+    // merge the NG lane groups (they hold interleaved entries of the same segment)
+    if constexpr (NG > 1) {
+#pragma unroll
+        for (int off = G; off < 32; off <<= 1) {
+#pragma unroll
+            for (int j = 0; j < LPL; ++j)
+#pragma unroll
+                for (int v = 0; v < VEC; ++v) {
+                    const float ov = __shfl_xor_sync(FULL, acc[j][v], off);
+                    if constexpr (OP == OP_SUM) {
+                        acc[j][v] += ov;
+                    } else {
+                        const int oa = __shfl_xor_sync(FULL, arg[j][v], off);
+                        if (better_lex<OP, int>(ov, oa, acc[j][v], arg[j][v])) { acc[j][v] = ov; arg[j][v] = oa; }
+                    }
+                }
+        }
+        if (g != 0) return;
+    }
+
+    if (nseg == 1) {
+#pragma unroll
+        for (int j = 0; j < LPL; ++j)
+            if (kok[j]) finalize_store<OP, VEC>(p, row, re - rb, koff[j], acc[j], arg[j]);
+    } else {
+        const size_t slot = (size_t)(__ldg(p.part_off + row) + s);
+#pragma unroll
+        for (int j = 0; j < LPL; ++j) {
+            if (kok[j]) {
+                const size_t o = slot * (size_t)p.k + (size_t)koff[j];
+                if constexpr (VEC == 4) {
+                    *reinterpret_cast<float4*>(p.part_val + o) = make_float4(acc[j][0], acc[j][1], acc[j][2], acc[j][3]);
+                } else {
+                    p.part_val[o] = acc[j][0];
+                }
+                if constexpr (OP != OP_SUM) store_vec_i32<VEC>(p.part_arg + o, arg[j]);
+            }
+        }
+    }
+}
+
+// ------------------------------------------------------------------------------------
+// fix-up: one warp merges the per-segment partials of one split row, in segment order
+// ------------------------------------------------------------------------------------
+template <int OP>
+__global__ void __launch_bounds__(256)
+spmm_fixup_kernel(const __grid_constant__ SpmmParams p) {
+    const int w = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    if (w >= p.num_split_rows) return;
+    const int lane = threadIdx.x & 31;
+    const int row = __ldg(p.split_rows + w);
+    const int nseg = __ldg(p.seg_off + row + 1) - __ldg(p.seg_off + row);
+    const size_t slot0 = (size_t)__ldg(p.part_off + row);
+    const int deg = __ldg(p.rowptr + row + 1) - __ldg(p.rowptr + row);
+    for (int kk = lane; kk < p.k; kk += 32) {
+        float acc[1] = {init_value<OP>()};
+        int arg[1] = {kNoArg};
+        for (int s = 0; s < nseg; ++s) {
+            const size_t o = (slot0 + s) * (size_t)p.k + kk;
+            const float v = p.part_val[o];
+            if constexpr (OP == OP_SUM) {
+                acc[0] += v;
+            } else {
+                const int a = p.part_arg[o];
+                // segments are in increasing edge order: strict compare keeps the first
+                if (better<OP>(v, acc[0])) { acc[0] = v; arg[0] = a; }
+            }
+        }
+        finalize_store<OP, 1>(p, row, deg, kk, acc, arg);
+    }
+}
+
+// ------------------------------------------------------------------------------------
+// host-side dispatch
+// ------------------------------------------------------------------------------------
+struct TileShape { int vec, g, lpl, tile_w, ntiles; };
+
+static bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15u) == 0; }
+
+static int pick_vec(int64_t k, int64_t ldx, int64_t ldo, const void* x, const void* out) {
+    if (k % 4 == 0 && ldx % 4 == 0 && ldo % 4 == 0 && aligned16(x) && aligned16(out)) return 4;
+    return 1;
+}
+
+static TileShape pick_shape(int vec, int64_t k, int kt) {
+    TileShape t;
+    t.vec = vec;
+    const int max_tile = vec * 32 * 4;  // G=32, LPL=4
+    int64_t tw = (kt <= 0 || kt >= k) ? k : kt;
+    if (tw > max_tile) tw = max_tile;
+    if (vec == 4) tw = (tw + 3) / 4 * 4;
+    const int tv = (int)((tw + vec - 1) / vec);  // vectors per tile
+    if (vec == 4 && tv <= 8)       { t.g = 8;  t.lpl = 1; }
+    else if (vec == 4 && tv <= 16) { t.g = 16; t.lpl = 1; }
+    else if (tv <= 32)             { t.g = 32; t.lpl = 1; }
+    else if (tv <= 64)             { t.g = 32; t.lpl = 2; }
+    else                           { t.g = 32; t.lpl = 4; }
+    t.tile_w = (int)tw;
+    t.ntiles = (int)((k + tw - 1) / tw);
+    return t;
+}
+
+typedef void (*SegKernel)(const SpmmParams);
+
+template <int OP, int VEC, int G, int LPL>
+static SegKernel pick_u(int u) {
+    constexpr int NG = 32 / G;
+    // keep (entries per step) * U <= 32 and at most 64 staged floats per lane
+    if constexpr (LPL * VEC * 8 <= 64)
+        if (u >= 8 && NG * 8 <= 32) return spmm_seg_kernel<OP, VEC, G, LPL, 8>;
+    if (NG * 4 <= 32) return spmm_seg_kernel<OP, VEC, G, LPL, 4>;
+    return nullptr;
+}
+
+template <int OP>
+static SegKernel pick_kernel(const TileShape& t, int u) {
+    if (t.vec == 4) {
+        if (t.g == 8 && t.lpl == 1) return pick_u<OP, 4, 8, 1>(u);
+        if (t.g == 16 && t.lpl == 1) return pick_u<OP, 4, 16, 1>(u);
+        if (t.g == 32 && t.lpl == 1) return pick_u<OP, 4, 32, 1>(u);
+        if (t.g == 32 && t.lpl == 2) return pick_u<OP, 4, 32, 2>(u);
+        if (t.g == 32 && t.lpl == 4) return pick_u<OP, 4, 32, 4>(u);
+    } else {
+        if (t.lpl == 1) return pick_u<OP, 1, 32, 1>(u);
+        if (t.lpl == 2) return pick_u<OP, 1, 32, 2>(u);
+        if (t.lpl == 4) return pick_u<OP, 1, 32, 4>(u);
+    }
+    return nullptr;
+}
+
+bool spmm_variant_supported(int variant, int reduce, int64_t k, int64_t ldx, int64_t ldo,
+                            const void* x, const void* out) {
+    const VariantDesc* d = variant_desc(variant);
+    if (!d || reduce < 0 || reduce > 3 || k <= 0) return false;
+    const int vec = pick_vec(k, ldx, ldo, x, out);
+    if (d->kt > 0) {
+        if (d->kt >= k) return false;            // same as kfull: do not time it twice
+        if (vec == 4 && d->kt % 4 != 0) return false;
+    }
+    return true;
+}
+
+int spmm_variant_default(int reduce, int64_t k, int64_t ldx, int64_t ldo, const void* x,
+                         const void* out, double avg_degree) {
+    (void)reduce; (void)ldx; (void)ldo; (void)x; (void)out; (void)avg_degree;
+    return 0;
+}
+
+int launch_spmm(int reduce, const SpmmParams& base, int64_t nnz, int variant, cudaStream_t stream) {
+    (void)nnz;
+    const VariantDesc* d = variant_desc(variant);
+    if (!d) return ISPLIB_NO_OPT_IMPL;
+    if (base.m == 0 || base.k == 0) return ISPLIB_SUCCESS;
+
+    SpmmParams p = base;
+    const int vec = pick_vec(p.k, p.ldx, p.ldo, p.x, p.out);
+    const TileShape t = pick_shape(vec, p.k, d->kt);
+    p.tile_w = t.tile_w;
+    const int op = (reduce == ISPLIB_REDUCE_MAX) ? OP_MAX : (reduce == ISPLIB_REDUCE_MIN ? OP_MIN : OP_SUM);
+
+    SegKernel kern = nullptr;
+    if (op == OP_SUM) kern = pick_kernel<OP_SUM>(t, d->unroll);
+    else if (op == OP_MAX) kern = pick_kernel<OP_MAX>(t, d->unroll);
+    else kern = pick_kernel<OP_MIN>(t, d->unroll);
+    if (!kern) return ISPLIB_NO_OPT_IMPL;
+
+    const int warps = d->warps;
+    const dim3 block(warps * 32);
+    const dim3 grid((unsigned)((p.num_items + warps - 1) / warps), (unsigned)t.ntiles);
+    if (t.ntiles > 65535) return ISPLIB_NO_OPT_IMPL;
+    kern<<<grid, block, 0, stream>>>(p);
+    ISPLIB_LAUNCH_CHECK();
+
+    if (p.num_split_rows > 0) {
+        const int fw = 8;
+        const dim3 fgrid((unsigned)((p.num_split_rows + fw - 1) / fw));
+        if (op == OP_SUM) spmm_fixup_kernel<OP_SUM><<<fgrid, fw * 32, 0, stream>>>(p);
+        else if (op == OP_MAX) spmm_fixup_kernel<OP_MAX><<<fgrid, fw * 32, 0, stream>>>(p);
+        else spmm_fixup_kernel<OP_MIN><<<fgrid, fw * 32, 0, stream>>>(p);
+        ISPLIB_LAUNCH_CHECK();
+    }
+    return ISPLIB_SUCCESS;
+}
+
+}  // namespace isplib

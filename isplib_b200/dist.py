@@ -1,0 +1,184 @@
+"""Row-partitioned multi-GPU SpMM (new functionality; the reference is single-process,
+SURVEY.md section 8e).
+
+One process per GPU (``torchrun``), ``torch.distributed`` over NCCL/NVLink.
+
+* A (M x N) is 1-D partitioned by rows: rank p owns rows ``[p*R, (p+1)*R)`` with
+  ``R = ceil(M / P)`` (rows of X / out are owned the same way, zero-padded to R so the
+  all-gather is regular).
+* Each rank's row block is split by COLUMN OWNER into a *local* CSR block (columns the
+  rank already holds) and a *remote* CSR block (everything else).
+* forward:   all-gather X slices on a side stream  ||  local-block SpMM
+             -> wait -> remote-block SpMM with ISPLIB_FLAG_ACCUMULATE into the same rows.
+  sum: plain accumulate.  mean: both blocks as sums, the second call divides by the full
+  row degree (``row_divisor``).  max/min: both blocks carry their GLOBAL edge ids
+  (``edge_ids``), the merge is (value, edge id)-lexicographic, so out/arg are bit-identical
+  to the single-GPU result.
+* backward (sum/mean): the same operator built from A^T (each rank owns the rows of A^T
+  = columns of A in its range) applied to the all-gathered grad_out.
+  backward (max/min): local arg-scatter into a zeroed [P*R, K] partial, then
+  reduce-scatter(sum).
+
+The block SpMM is injectable (``block_spmm``) so the partitioning / merge logic can be
+tested on CPU with gloo; the default is the CUDA C ABI (isplib_b200.capi) and there is no
+CPU fallback in the product path.
+"""
+from __future__ import annotations
+
+from dataclasses import dataclass
+from typing import Callable, Optional, Tuple
+
+import torch
+import torch.distributed as dist
+
+SUM, MAX, MIN, MEAN = 0, 1, 2, 3
+REDUCE_CODE = {"sum": SUM, "add": SUM, "max": MAX, "min": MIN, "mean": MEAN}
+FLAG_ACCUMULATE = 0x1
+
+
+@dataclass
+class CsrBlock:
+    rowptr: torch.Tensor            # int32 [R+1]
+    col: torch.Tensor               # int32 [nnz_b]  (block-local column index)
+    val: Optional[torch.Tensor]     # fp32  [nnz_b] or None
+    edge_ids: torch.Tensor          # int32 [nnz_b]  global edge id of each entry
+    plan: object = None             # capi.Plan (CUDA path only)
+
+    @property
+    def nnz(self) -> int:
+        return int(self.col.numel())
+
+
+def rows_per_rank(m: int, world: int) -> int:
+    return (m + world - 1) // world
+
+
+def split_row_block(rowptr: torch.Tensor, col: torch.Tensor, val: Optional[torch.Tensor],
+                    rank: int, world: int, n_cols: int) -> Tuple[CsrBlock, CsrBlock, torch.Tensor, int]:
+    """From the GLOBAL CSR (int64, any device) build this rank's (local, remote) blocks.
+
+    Returns (local, remote, row_degree[R] fp32 (clamped >= 1), R).  Local block columns are
+    rebased to the rank's own X slice; remote block columns index the gathered [P*Rc, K]
+    matrix (Rc = rows_per_rank(n_cols, world)), where own-slice columns never appear.
+    """
+    m = rowptr.numel() - 1
+    R = rows_per_rank(m, world)
+    Rc = rows_per_rank(n_cols, world)
+    r0, r1 = min(rank * R, m), min((rank + 1) * R, m)
+    e0, e1 = int(rowptr[r0]), int(rowptr[r1])
+    dev = col.device
+    sub_col = col[e0:e1]
+    sub_val = None if val is None else val[e0:e1]
+    eid = torch.arange(e0, e1, device=dev, dtype=torch.int64)
+    deg = (rowptr[r0 + 1:r1 + 1] - rowptr[r0:r1])
+    row = torch.repeat_interleave(torch.arange(r1 - r0, device=dev, dtype=torch.int64), deg)
+    c0, c1 = rank * Rc, (rank + 1) * Rc
+    is_local = (sub_col >= c0) & (sub_col < c1)
+
+    def make(mask, rebase):
+        cnt = torch.bincount(row[mask], minlength=R) if mask.numel() else torch.zeros(R, dtype=torch.int64, device=dev)
+        rp = torch.zeros(R + 1, dtype=torch.int64, device=dev)
+        rp[1:] = torch.cumsum(cnt, 0)
+        return CsrBlock(rp.to(torch.int32), (sub_col[mask] - rebase).to(torch.int32),
+                        None if sub_val is None else sub_val[mask].contiguous(), eid[mask].to(torch.int32))
+
+    local = make(is_local, c0)
+    remote = make(~is_local, 0)
+    full_deg = torch.zeros(R, dtype=torch.float32, device=dev)
+    full_deg[: r1 - r0] = deg.to(torch.float32)
+    full_deg.clamp_(min=1.0)
+    return local, remote, full_deg, R
+
+
+def _cuda_block_spmm(reduce_code, block: CsrBlock, x, out, arg_out, flags, row_divisor, arg_sentinel, variant=-1):
+    from . import capi
+    if block.plan is None:
+        block.plan = capi.Plan(block.rowptr, block.nnz)
+    return capi.spmm_csr(reduce_code, block.rowptr, block.col, block.val, x, block.plan, variant,
+                         out=out, arg_out=arg_out, flags=flags, row_divisor=row_divisor,
+                         edge_ids=block.edge_ids, arg_sentinel=arg_sentinel)
+
+
+class RowPartitionedSpMM:
+    """out_local = (A @ X)[own rows] with X given as this rank's row slice."""
+
+    def __init__(self, rowptr: torch.Tensor, col: torch.Tensor, value: Optional[torch.Tensor], n_cols: int,
+                 group=None, device=None, block_spmm: Optional[Callable] = None, overlap: bool = True):
+        self.group = group
+        self.world = dist.get_world_size(group) if dist.is_initialized() else 1
+        self.rank = dist.get_rank(group) if dist.is_initialized() else 0
+        self.m = rowptr.numel() - 1
+        self.n = int(n_cols)
+        self.nnz = int(col.numel())
+        self.device = torch.device(device) if device is not None else col.device
+        self.block_spmm = block_spmm or _cuda_block_spmm
+        self.overlap = overlap
+        local, remote, deg, R = split_row_block(rowptr, col, value, self.rank, self.world, self.n)
+        self.R = R
+        self.Rc = rows_per_rank(self.n, self.world)
+        mv = lambda b: CsrBlock(b.rowptr.to(self.device), b.col.to(self.device),
+                                None if b.val is None else b.val.to(self.device), b.edge_ids.to(self.device))
+        self.local, self.remote = mv(local), mv(remote)
+        self.row_degree = deg.to(self.device)
+        self.comm_stream = torch.cuda.Stream(self.device) if (self.device.type == "cuda" and overlap) else None
+        self.variant = -1
+
+    # rows this rank owns (without padding)
+    @property
+    def own_rows(self) -> int:
+        return max(0, min((self.rank + 1) * self.R, self.m) - self.rank * self.R)
+
+    def pad_x(self, x_own: torch.Tensor) -> torch.Tensor:
+        """[own_cols, K] -> [Rc, K] zero padded (the regular slice the all-gather needs)."""
+        if x_own.size(0) == self.Rc:
+            return x_own.contiguous()
+        out = torch.zeros((self.Rc, x_own.size(1)), dtype=x_own.dtype, device=x_own.device)
+        out[: x_own.size(0)] = x_own
+        return out
+
+    def _all_gather(self, x_slice: torch.Tensor) -> torch.Tensor:
+        if self.world == 1:
+            return x_slice
+        gathered = torch.empty((self.world * self.Rc, x_slice.size(1)), dtype=x_slice.dtype, device=x_slice.device)
+        dist.all_gather_into_tensor(gathered, x_slice, group=self.group)
+        return gathered
+
+    def forward(self, x_slice: torch.Tensor, reduce: str = "sum"):
+        """x_slice: [Rc, K] (use pad_x).  Returns (out [R, K], arg_out [R, K] int64 or None);
+        rows beyond own_rows are padding (zeros / init values)."""
+        code = REDUCE_CODE[reduce]
+        is_arg = code in (MAX, MIN)
+        K = x_slice.size(1)
+        out = torch.empty((self.R, K), dtype=torch.float32, device=x_slice.device)
+        arg = torch.empty((self.R, K), dtype=torch.int64, device=x_slice.device) if is_arg else None
+        inner = SUM if code == MEAN else code
+        div = self.row_degree if code == MEAN else None
+
+        if self.world == 1:
+            self.block_spmm(inner, self.local, x_slice, out, arg, 0, div, self.nnz, self.variant)
+            return out, arg
+
+        gathered = None
+        if self.comm_stream is not None:
+            cur = torch.cuda.current_stream(x_slice.device)
+            self.comm_stream.wait_stream(cur)
+            with torch.cuda.stream(self.comm_stream):
+                gathered = self._all_gather(x_slice)
+            # local block overlaps with the all-gather
+            self.block_spmm(inner, self.local, x_slice, out, arg, 0, None, self.nnz, self.variant)
+            cur.wait_stream(self.comm_stream)
+            gathered.record_stream(cur)
+        else:
+            gathered = self._all_gather(x_slice)
+            self.block_spmm(inner, self.local, x_slice, out, arg, 0, None, self.nnz, self.variant)
+        self.block_spmm(inner, self.remote, gathered, out, arg, FLAG_ACCUMULATE, div, self.nnz, self.variant)
+        return out, arg
+
+    def launches_per_forward(self) -> int:
+        """how many of OUR kernels one forward launches (for bench.py's gpu_launches)."""
+        n = 0
+        for b in ([self.local] if self.world == 1 else [self.local, self.remote]):
+            n += 1
+            if b.plan is not None and b.plan.info.num_split_rows > 0:
+                n += 1
+        return n

@@ -1,0 +1,246 @@
+"""GPU tests of the drop-in surface: torch.ops.isplib.* (same names/schemas as the
+reference registers, csrc/fusedmm.cpp:565-570), their autograd, and the plugin
+(iSpLibPlugin.patch_pyg -> torch_sparse.matmul), plus full-size property checks on the
+Reddit-shaped benchmark graph."""
+import numpy as np
+import pytest
+import torch
+
+from conftest import GOLDEN_CASES, abs_product_sum, assert_sum_close, load_golden, random_csr
+
+pytestmark = pytest.mark.gpu
+DEV = "cuda:0"
+
+
+@pytest.fixture(scope="module")
+def isplib():
+    import isplib as m   # the alias package: `from isplib import *` surface
+    return m
+
+
+def dev_graph(g):
+    rowptr = torch.from_numpy(g["rowptr"]).to(DEV)
+    col = torch.from_numpy(g["col"]).to(DEV)
+    val = None if g["value"] is None else torch.from_numpy(g["value"]).to(DEV)
+    return rowptr, col, val
+
+
+@pytest.mark.parametrize("name", GOLDEN_CASES)
+def test_ops_forward_backward_vs_reference_autograd(isplib, name):
+    g = load_golden(name)
+    rowptr, col, val = dev_graph(g)
+    go = torch.from_numpy(g["grad_out"]).to(DEV)
+    ops = torch.ops.isplib
+    x = torch.from_numpy(g["mat"]).to(DEV).requires_grad_(True)
+    o = ops.fusedmm_spmm(None, rowptr, col, val, None, None, x, None, None)
+    o.backward(go)
+    np.testing.assert_allclose(o.detach().cpu().numpy(), g["sum_out"], rtol=1e-5, atol=1e-6)
+    np.testing.assert_allclose(x.grad.cpu().numpy(), g["sum_grad_mat"], rtol=1e-5, atol=1e-6)
+
+    x = torch.from_numpy(g["mat"]).to(DEV).requires_grad_(True)
+    o = ops.fusedmm_spmm_mean(None, rowptr, col, val, None, None, None, x, None, None)
+    o.backward(go)
+    np.testing.assert_allclose(o.detach().cpu().numpy(), g["mean_out"], rtol=1e-5, atol=1e-6)
+    np.testing.assert_allclose(x.grad.cpu().numpy(), g["mean_grad_mat"], rtol=1e-5, atol=1e-6)
+
+    for red, fn in (("max", ops.fusedmm_spmm_max), ("min", ops.fusedmm_spmm_min)):
+        x = torch.from_numpy(g["mat"]).to(DEV).requires_grad_(True)
+        v = (val if val is not None else torch.ones(col.numel(), device=DEV)).clone().requires_grad_(True)
+        o, arg = fn(rowptr, col, v, x)
+        assert arg.dtype == torch.int64 and not arg.requires_grad
+        o.backward(go)
+        assert np.array_equal(o.detach().cpu().numpy(), g[f"{red}_out"])
+        assert np.array_equal(arg.cpu().numpy(), g[f"{red}_arg"])
+        np.testing.assert_allclose(x.grad.cpu().numpy(), g[f"{red}_grad_mat"], rtol=1e-5, atol=1e-6)
+        np.testing.assert_allclose(v.grad.cpu().numpy(), g[f"{red}_grad_value"], rtol=1e-5, atol=1e-6)
+
+
+def test_readme_standalone_example(isplib):
+    """README.md:95-118 verbatim (on the GPU): patch, build the 3x3 SparseTensor, matmul."""
+    from isplib import iSpLibPlugin, SparseTensor
+    import torch_sparse
+    iSpLibPlugin.patch_pyg()
+    try:
+        adj_t = SparseTensor(
+            row=torch.tensor([2, 0, 1, 0, 0], dtype=torch.int64),
+            col=torch.tensor([1, 0, 0, 2, 0], dtype=torch.int64),
+            value=torch.tensor([3, 3, 4, 2, -2], dtype=torch.float32),
+            sparse_sizes=(3, 3)).to(DEV)
+        dense = torch.tensor([[1, 0, 2], [4, 0, 0], [0, 3, 0]], dtype=torch.float32, device=DEV)
+        assert torch_sparse.matmul(adj_t, dense).tolist() == [[1, 6, 2], [4, 0, 8], [12, 0, 0]]
+        assert torch_sparse.matmul(adj_t, dense, "max").tolist() == [[3, 6, 6], [4, 0, 8], [12, 0, 0]]
+        assert torch_sparse.matmul(adj_t, dense, "min")[0].tolist() == [-2, 0, -4]
+        np.testing.assert_allclose(torch_sparse.matmul(adj_t, dense, "mean")[0].tolist(), [1 / 3, 2, 2 / 3], rtol=1e-6)
+    finally:
+        iSpLibPlugin.unpatch_pyg()
+
+
+def test_cora_shape_via_patch_pyg(isplib, oracle):
+    """BASELINE.json config 0: SpMM-sum via patch_pyg() on a Cora-shaped graph, K=64."""
+    from isplib import iSpLibPlugin
+    from isplib_b200 import synth
+    import torch_sparse
+    g = synth.make_graph("cora", values="gcn", seed=0)
+    assert g.m == 2708 and g.nnz == 10556
+    x = torch.randn(g.n, 64, generator=torch.Generator().manual_seed(0))
+    adj = g.to(DEV).sparse_tensor()
+    xd = x.to(DEV).requires_grad_(True)
+    iSpLibPlugin.patch_pyg()
+    try:
+        out = torch_sparse.matmul(adj, xd, "sum")
+        out.sum().backward()
+    finally:
+        iSpLibPlugin.unpatch_pyg()
+    ref, _ = oracle.spmm_c(g.rowptr.numpy(), g.col.numpy(), g.value.numpy(), x.numpy(), oracle.SUM)
+    assert_sum_close(out.detach().cpu().numpy(), ref, abs_product_sum(g.rowptr.numpy(), g.col.numpy(), g.value.numpy(), x.numpy()))
+    gref = oracle.spmm_backward_sum(g.rowptr.numpy(), g.col.numpy(), g.value.numpy(), np.ones((g.m, 64), np.float32), g.n)
+    np.testing.assert_allclose(xd.grad.cpu().numpy(), gref, rtol=1e-5, atol=1e-6)
+    # unpatched matmul (stock torch ops) agrees too
+    np.testing.assert_allclose(torch_sparse.matmul(adj, xd.detach(), "sum").cpu().numpy(), ref, rtol=1e-4, atol=1e-5)
+
+
+@pytest.mark.parametrize("reduce", ["sum", "mean", "max", "min"])
+def test_plugin_matches_oracle_with_autotune(isplib, oracle, reduce):
+    """Mid-size graph, big enough to trigger the on-device variant selection."""
+    from isplib import iSpLibPlugin
+    from isplib_b200 import synth
+    import torch_sparse
+    g = synth.make_graph(3000, 200_000, law="lognormal", param=1.2, values="uniform", seed=1)
+    K = 64
+    x = torch.randn(g.n, K, generator=torch.Generator().manual_seed(2))
+    adj = g.to(DEV).sparse_tensor()
+    xd = x.to(DEV).requires_grad_(True)
+    go = torch.randn(g.m, K, generator=torch.Generator().manual_seed(3))
+    iSpLibPlugin.patch_pyg()
+    try:
+        out = torch_sparse.matmul(adj, xd, reduce)
+        out2 = torch_sparse.matmul(adj, xd, reduce)      # second call: tuned variant from the cache
+        out.backward(go.to(DEV))
+    finally:
+        iSpLibPlugin.unpatch_pyg()
+    assert torch.equal(out, out2), "same inputs must give bit-identical outputs run to run"
+    rp, co, va = g.rowptr.numpy(), g.col.numpy(), g.value.numpy()
+    code = oracle.REDUCE_CODE[reduce]
+    ref, ref_arg = oracle.spmm_c(rp, co, va, x.numpy(), code)
+    if reduce in ("max", "min"):
+        assert np.array_equal(out.detach().cpu().numpy(), ref)
+        gref, _ = oracle.arg_backward(co, va, x.numpy(), ref_arg, go.numpy(), g.n)
+        np.testing.assert_allclose(xd.grad.cpu().numpy(), gref, rtol=1e-5, atol=1e-5)
+    else:
+        assert_sum_close(out.detach().cpu().numpy(), ref, abs_product_sum(rp, co, va, x.numpy(), reduce == "mean"))
+        bw = oracle.spmm_backward_sum if reduce == "sum" else oracle.spmm_backward_mean
+        gref = bw(rp, co, va, go.numpy(), g.n)
+        rpt, _, rowt = oracle.build_csc(rp, co, g.n)
+        w = va[oracle.build_csc(rp, co, g.n)[1]]
+        if reduce == "mean":
+            w = w / np.maximum(np.diff(rp), 1)[rowt]
+        assert_sum_close(xd.grad.cpu().numpy(), gref, abs_product_sum(rpt, rowt, w, go.numpy()))
+    assert torch.ops.isplib._b200_tuned_variant(adj.storage.rowptr(), adj.storage.col(), code, K, True, False) >= 0
+
+
+def test_graph_cache_eviction_and_staleness(isplib):
+    ops = torch.ops.isplib
+    ops._b200_cache_clear()
+    x = torch.ones(4, 8, device=DEV)
+    rowptr = torch.tensor([0, 1, 2], device=DEV)
+    col = torch.tensor([0, 1], device=DEV)
+    a = ops.fusedmm_spmm(None, rowptr, col, None, None, None, x, None, None)
+    assert ops._b200_cache_size() == 1 and a[1, 0] == 1
+    col[1] = 3                              # in-place edit bumps the version: entry must be rebuilt
+    x[3] = 5.0
+    b = ops.fusedmm_spmm(None, rowptr, col, None, None, None, x, None, None)
+    assert b[1, 0] == 5
+    del rowptr, col
+    rowptr2 = torch.tensor([0, 2], device=DEV)
+    col2 = torch.tensor([1, 2], device=DEV)
+    c = ops.fusedmm_spmm(None, rowptr2, col2, None, None, None, x, None, None)
+    assert c.shape == (1, 8) and ops._b200_cache_size() == 1   # dead graph evicted
+
+
+def test_ops_reject_bad_inputs(isplib):
+    ops = torch.ops.isplib
+    rowptr = torch.tensor([0, 1], device=DEV)
+    col = torch.tensor([0], device=DEV)
+    with pytest.raises(RuntimeError, match="float32"):
+        ops.fusedmm_spmm(None, rowptr, col, None, None, None, torch.ones(1, 4, device=DEV, dtype=torch.float64), None, None)
+    with pytest.raises(RuntimeError, match="2-D"):
+        ops.fusedmm_spmm(None, rowptr, col, None, None, None, torch.ones(1, 1, 4, device=DEV), None, None)
+    with pytest.raises(RuntimeError, match="CUDA"):
+        ops.fusedmm_spmm(None, rowptr.cpu(), col.cpu(), None, None, None, torch.ones(1, 4), None, None)
+
+
+# --------------------------------------------------------------------------------------
+# full benchmark size: size-independent properties (no CPU oracle at 114.6M entries)
+# --------------------------------------------------------------------------------------
+@pytest.fixture(scope="module")
+def reddit():
+    from isplib_b200 import synth, capi
+    g = synth.make_graph("reddit", values="uniform", seed=0, device=DEV)
+    assert g.m == 232_965 and g.nnz == 114_615_892
+    rp = capi.narrow_i64_to_i32(g.rowptr)
+    co = capi.narrow_i64_to_i32(g.col)
+    plan = capi.Plan(rp, g.nnz)
+    return g, rp, co, plan, capi
+
+
+def test_fullsize_properties(reddit):
+    g, rp, co, plan, capi = reddit
+    K = 128
+    gen = torch.Generator(device=DEV).manual_seed(1)
+    x1 = torch.randn(g.n, K, device=DEV, generator=gen)
+    # (1) known answer: X = ones  =>  sum row i = sum of the row's values (float64 segment sums)
+    ones = torch.ones(g.n, K, device=DEV)
+    out, _ = capi.spmm_csr("sum", rp, co, g.value, ones, plan)
+    cs = torch.zeros(g.nnz + 1, dtype=torch.float64, device=DEV)
+    torch.cumsum(g.value.double(), 0, out=cs[1:])
+    rowsum = (cs[g.rowptr[1:]] - cs[g.rowptr[:-1]])
+    abssum = torch.zeros(g.nnz + 1, dtype=torch.float64, device=DEV)
+    torch.cumsum(g.value.double().abs(), 0, out=abssum[1:])
+    scale = (abssum[g.rowptr[1:]] - abssum[g.rowptr[:-1]])
+    err = (out.double() - rowsum[:, None]).abs().max(dim=1).values
+    assert bool((err <= 1e-6 + 1e-5 * scale).all())
+    assert bool((out == out[:, :1]).all())          # every feature lane does the same work
+    # (2) linearity: A(2 x1) == 2 (A x1) exactly (scaling by 2 is exact in fp32)
+    o1, _ = capi.spmm_csr("sum", rp, co, g.value, x1, plan)
+    o2, _ = capi.spmm_csr("sum", rp, co, g.value, 2 * x1, plan)
+    assert torch.equal(o2, 2 * o1)
+    # (3) every variant gives the same max/min/arg bit for bit, and sum within tolerance
+    L = capi.lib()
+    base_max, base_arg = capi.spmm_csr("max", rp, co, g.value, x1, plan, variant=0)
+    for v in range(1, L.isplib_b200_variant_count()):
+        if L.isplib_b200_variant_supported(v, capi.MAX, K, K, K, x1.data_ptr(), x1.data_ptr()):
+            m, a = capi.spmm_csr("max", rp, co, g.value, x1, plan, variant=v)
+            assert torch.equal(m, base_max) and torch.equal(a, base_arg)
+    # (4) arg is a witness: out == val[arg] * x[col[arg]] exactly, arg inside its row, and
+    #     max >= mean >= min with no value (mean of the same terms)
+    row_lo = g.rowptr[:-1, None]
+    row_hi = g.rowptr[1:, None]
+    assert bool(((base_arg >= row_lo) & (base_arg < row_hi)).all())
+    wit = g.value[base_arg] * torch.gather(x1, 0, g.col[base_arg])
+    assert torch.equal(wit, base_max)
+    mx, _ = capi.spmm_csr("max", rp, co, None, x1, plan)
+    mn, _ = capi.spmm_csr("min", rp, co, None, x1, plan)
+    me, _ = capi.spmm_csr("mean", rp, co, None, x1, plan)
+    assert bool((mx >= me - 1e-4).all()) and bool((me >= mn - 1e-4).all())
+    # (5) idempotence / determinism: same call twice is bit-identical
+    o1b, _ = capi.spmm_csr("sum", rp, co, g.value, x1, plan)
+    assert torch.equal(o1, o1b)
+
+
+def test_fullsize_backward_adjoint(reddit):
+    """<A x, g> == <x, A^T g> at full size: checks the device-built CSC view end to end."""
+    g, rp, co, plan, capi = reddit
+    K = 32
+    gen = torch.Generator(device=DEV).manual_seed(2)
+    x = torch.randn(g.n, K, device=DEV, generator=gen)
+    go = torch.randn(g.m, K, device=DEV, generator=gen)
+    colptr, row_t, csr2csc = capi.csr_transpose(rp, co, g.n)
+    assert bool((colptr[1:] >= colptr[:-1]).all()) and int(colptr[-1]) == g.nnz
+    assert bool((torch.sort(csr2csc).values == torch.arange(g.nnz, device=DEV, dtype=torch.int32)).all())
+    plan_t = capi.Plan(colptr, g.nnz)
+    vt = capi.permute_values(g.value, csr2csc, row_t, rp, False)
+    y, _ = capi.spmm_csr("sum", rp, co, g.value, x, plan)
+    gx, _ = capi.spmm_csr("sum", colptr, row_t, vt, go, plan_t)
+    lhs = float((y.double() * go.double()).sum())
+    rhs = float((x.double() * gx.double()).sum())
+    assert abs(lhs - rhs) <= 1e-5 * max(1.0, abs(lhs), float((y.double().abs() * go.double().abs()).sum()) * 1e-2)
