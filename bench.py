@@ -266,7 +266,7 @@ def run_ours(args):
 
         def step(i):
             capi.spmm_csr(reduce, rp32, co32, g.value, xs[i & 1], plan, best, out=out, arg_out=arg)
-        launches_per_step = 1 + (1 if plan.info.num_split_rows > 0 else 0)
+        launches_per_step = 1   # one spmm_seg_kernel per SpMM (split rows are merged inside it)
         variant_name = capi.variant_names()[best]
         tune = {capi.variant_names()[v]: round(t, 3) for v, t in enumerate(times) if t >= 0}
     else:
@@ -353,12 +353,12 @@ def run_ours(args):
     peak, peak_src = peaks()
     roofline = {"bound": "hbm", "achieved": round(value / world, 2) if world > 1 else round(value, 2), "peak": peak,
                 "unit": "GB/s", "frac": round((value / world) / peak, 4), "traffic": None,
-                "kernel": "isplib::spmm_seg_kernel (+ spmm_fixup_kernel, same launch pair)",
+                "kernel": "isplib::spmm_seg_kernel",
                 "peak_source": peak_src,
                 "algorithmic_bytes_per_launch": b_alg // world,
-                "note": "achieved = B_alg per step / CUDA-event step time; a step is the segment kernel plus its "
-                        "fix-up launch. B_alg counts one K-row gather per stored entry, so it can exceed HBM "
-                        "traffic when X rows hit in L2 (ncu dram bytes in profiles/)."}
+                "note": "achieved = B_alg per step / CUDA-event step time; a step is exactly one launch of the "
+                        "segment kernel. B_alg counts one K-row gather per stored entry, so it exceeds HBM "
+                        "traffic when X rows hit in the 126 MB L2 (ncu dram bytes in profiles/)."}
     line = {
         "metric": "spmm_sum_effective_gbs", "value": round(value, 2), "unit": "GB/s", "n_gpus": world,
         "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": round(ms_step, 4),

@@ -156,7 +156,9 @@ def spmm_csr(reduce, rowptr32, col32, val, x, plan: Plan, variant: int = VARIANT
     if out is None:
         out = torch.empty((M, K), dtype=torch.float32, device=x.device)
     if is_arg and arg_out is None:
-        arg_out = torch.empty((M, K), dtype=torch.int64, device=x.device)
+        # arg_out shares out's row stride (include/isplib_b200.h: "row stride ldo")
+        ld = out.stride(0) if M > 1 else K
+        arg_out = torch.empty((M, max(ld, K)), dtype=torch.int64, device=x.device)[:, :K]
     ws_bytes = ctypes.c_size_t(0)
     check(lib().isplib_b200_spmm_workspace_bytes(ctypes.byref(plan.info), K, code, ctypes.byref(ws_bytes)),
           "spmm_workspace_bytes")

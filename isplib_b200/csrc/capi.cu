@@ -68,14 +68,19 @@ static int fill_params(SpmmParams& p, int reduce, int64_t m, int64_t n, int64_t 
     size_t need = 0;
     int st = isplib_b200_spmm_workspace_bytes(info, k, reduce, &need);
     if (st) return st;
-    const size_t part_elems = (size_t)info->num_split_items * (size_t)k;
     float* part_val = nullptr;
     int32_t* part_arg = nullptr;
-    if (part_elems > 0) {
+    int* row_ticket = nullptr;
+    int ticket_stride = 0, ticket_capacity = 0;
+    if (info->num_split_items > 0) {
         if (!workspace || workspace_bytes < need) return ISPLIB_NOT_ENOUGH_MEM;
+        const WorkspaceLayout W = workspace_layout(info->num_split_items, k, is_arg);
         char* w = (char*)align_up((size_t)(uintptr_t)workspace, 256);
-        part_val = (float*)w;
-        if (is_arg) part_arg = (int32_t*)(w + align_up(part_elems * 4, 256));
+        part_val = (float*)(w + W.off_part_val);
+        if (is_arg) part_arg = (int32_t*)(w + W.off_part_arg);
+        row_ticket = (int*)(w + W.off_ticket);
+        ticket_stride = W.ticket_stride;
+        ticket_capacity = W.ticket_capacity;
     }
 
     const PlanLayout L = plan_layout(m, nnz, info->seg_len);
@@ -92,6 +97,9 @@ static int fill_params(SpmmParams& p, int reduce, int64_t m, int64_t n, int64_t 
     p.split_rows = (const int32_t*)(base + L.off_split_rows);
     p.part_val = part_val;
     p.part_arg = part_arg;
+    p.row_ticket = row_ticket;
+    p.ticket_stride = ticket_stride;
+    p.ticket_capacity = ticket_capacity;
     p.row_div = row_divisor;
     p.edge_ids = edge_ids;
     p.ldx = ldx;

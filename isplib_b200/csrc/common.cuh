@@ -25,6 +25,27 @@ namespace isplib {
 
 constexpr int kDefaultSegLen = 256;
 constexpr int kNumSMs = 148;  // B200: 2 dies x 74 SMs
+constexpr int kMinTileW = 8;  // narrowest K tile any variant uses (sizes the ticket array)
+
+// workspace carving shared by the size query and the launcher
+struct WorkspaceLayout {
+    size_t off_part_val, off_part_arg, off_ticket, total;
+    int ticket_stride, ticket_capacity;
+};
+static inline size_t align_up_(size_t x, size_t a) { return (x + a - 1) / a * a; }
+static inline WorkspaceLayout workspace_layout(int64_t num_split_items, int64_t k, bool is_arg) {
+    WorkspaceLayout W;
+    const size_t part = align_up_((size_t)num_split_items * (size_t)k * 4, 256);
+    size_t o = 0;
+    W.off_part_val = o; o += part;
+    W.off_part_arg = o; if (is_arg) o += part;
+    W.ticket_stride = (int)(num_split_items / 2 + 1);
+    const int64_t max_tiles = (k + kMinTileW - 1) / kMinTileW;
+    W.ticket_capacity = (int)((int64_t)W.ticket_stride * (max_tiles > 0 ? max_tiles : 1));
+    W.off_ticket = o; o += align_up_((size_t)W.ticket_capacity * 4, 256);
+    W.total = o + 256;
+    return W;
+}
 
 static inline size_t align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
 
@@ -74,10 +95,12 @@ struct SpmmParams {
     const int32_t* __restrict__ split_rows;
     float* __restrict__ part_val;       // [num_split_items, k]
     int32_t* __restrict__ part_arg;     // [num_split_items, k] (max/min)
+    int* __restrict__ row_ticket;       // [ntiles, ticket_stride] arrival counters of split rows
     const float* __restrict__ row_div;  // nullable
     const int32_t* __restrict__ edge_ids;  // nullable
     long long ldx, ldo, arg_sentinel;
     int m, k, tile_w, num_items, num_split_rows, seg_len;
+    int ticket_stride, ticket_capacity;   // ints per K tile / ints available
     int flags;      // ISPLIB_FLAG_*
     int div_mode;   // 0 none, 1 by max(deg,1), 2 by row_div[]
 };

@@ -146,10 +146,11 @@ extern "C" int isplib_b200_plan_build(int64_t m, int64_t nnz, const int32_t* row
 
 extern "C" int isplib_b200_spmm_workspace_bytes(const isplib_b200_plan_info* info, int64_t k,
                                                 int reduce, size_t* bytes) {
-    if (!info || !bytes || k < 0 || reduce < 0 || reduce > 3) return ISPLIB_INVALID_ARG;
-    size_t b = align_up((size_t)info->num_split_items * (size_t)k * 4, 256);
-    if (reduce == ISPLIB_REDUCE_MAX || reduce == ISPLIB_REDUCE_MIN) b *= 2;
-    *bytes = b + 256;
+    if (reduce < 0 || reduce > 3) return ISPLIB_NO_OPT_IMPL;
+    if (!info || !bytes || k < 0) return ISPLIB_INVALID_ARG;
+    if (info->num_split_items == 0) { *bytes = 256; return ISPLIB_SUCCESS; }
+    if ((int64_t)(info->num_split_items / 2 + 1) * ((k + kMinTileW - 1) / kMinTileW) >= INT32_MAX) return ISPLIB_INVALID_ARG;
+    *bytes = workspace_layout(info->num_split_items, k, reduce == ISPLIB_REDUCE_MAX || reduce == ISPLIB_REDUCE_MIN).total;
     return ISPLIB_SUCCESS;
 }
 

@@ -14,8 +14,9 @@
 //   * fp32 accumulators (and the running arg-edge for max/min) stay in registers;
 //   * rows that fit one segment are finalised in place (mean divide, arg widening to
 //     int64, optional merge with a previous block's result); longer rows write one
-//     partial per segment and a fix-up kernel merges them in segment order, so the
-//     result is deterministic and max/min/arg stay bit-exact however a row is split;
+//     partial per segment and the last segment warp to arrive (an atomic ticket per row)
+//     merges them in segment order inside the same launch, so the result is
+//     deterministic and max/min/arg stay bit-exact however a row is split;
 //   * blockIdx.y walks K tiles slowest, so with a narrow tile the whole grid sweeps
 //     one [N, tile] column slab of X at a time and the slab stays L2-resident.
 #include "common.cuh"
@@ -28,15 +29,17 @@ namespace isplib {
 // variant table
 // ------------------------------------------------------------------------------------
 static const VariantDesc kVariants[] = {
-    {"seg/w8/u8/kfull", 0, 8, 8, 0},
     {"seg/w8/u4/kfull", 0, 8, 4, 0},
-    {"seg/w4/u8/kfull", 0, 4, 8, 0},
     {"seg/w4/u4/kfull", 0, 4, 4, 0},
-    {"seg/w8/u8/kt128", 0, 8, 8, 128},
-    {"seg/w8/u8/kt64", 0, 8, 8, 64},
-    {"seg/w8/u8/kt32", 0, 8, 8, 32},
+    {"seg/w8/u8/kfull", 0, 8, 8, 0},
+    {"seg/w4/u8/kfull", 0, 4, 8, 0},
+    {"seg/w8/u4/kt128", 0, 8, 4, 128},
+    {"seg/w4/u4/kt128", 0, 4, 4, 128},
     {"seg/w8/u4/kt64", 0, 8, 4, 64},
+    {"seg/w4/u4/kt64", 0, 4, 4, 64},
     {"seg/w8/u4/kt32", 0, 8, 4, 32},
+    {"seg/w4/u4/kt32", 0, 4, 4, 32},
+    {"seg/w8/u8/kt64", 0, 8, 8, 64},
 };
 int variant_count() { return (int)(sizeof(kVariants) / sizeof(kVariants[0])); }
 const VariantDesc* variant_desc(int v) {
@@ -158,7 +161,10 @@ __device__ __forceinline__ void finalize_store(const SpmmParams& p, int row, int
 // ------------------------------------------------------------------------------------
 // main kernel: one warp = one row segment x one K tile
 // ------------------------------------------------------------------------------------
-template <int OP, int VEC, int G, int LPL, int U>
+// PARTIAL: some lanes of the widest K tile fall outside [k0, kend) (K = 100, 200, 47 ...).
+// Those lanes gather the tile's first vector instead (same 16 bytes a valid lane reads, so
+// no extra traffic, and no predicate or zero-fill on the hot loads) and never store.
+template <int OP, int VEC, int G, int LPL, int U, bool PARTIAL>
 __global__ void __launch_bounds__(256)
 spmm_seg_kernel(const __grid_constant__ SpmmParams p) {
     constexpr int NG = 32 / G;         // lane groups per warp = entries gathered per step
@@ -191,6 +197,16 @@ spmm_seg_kernel(const __grid_constant__ SpmmParams p) {
         kok[j] = koff[j] < kend;
     }
 
+    // gather address = lane base + col * ldx_bytes: one IMAD.WIDE.U32 per gathered row
+    // instead of a 64x64-bit multiply; further vectors of the lane sit at immediate offsets
+    const char* xlane[PARTIAL ? LPL : 1];
+    xlane[0] = reinterpret_cast<const char*>(p.x + (kok[0] ? koff[0] : k0));
+    if constexpr (PARTIAL) {
+#pragma unroll
+        for (int j = 1; j < LPL; ++j) xlane[j] = reinterpret_cast<const char*>(p.x + (kok[j] ? koff[j] : k0));
+    }
+    const unsigned ldxb = (unsigned)p.ldx * 4u;
+
     float acc[LPL][VEC];
     int arg[LPL][VEC];
 #pragma unroll
@@ -201,21 +217,21 @@ spmm_seg_kernel(const __grid_constant__ SpmmParams p) {
     const bool has_val = (p.val != nullptr);
 
     // one 32-entry chunk of (col, val) per lane, one chunk prefetched ahead
-    int c_next = 0;
+    unsigned c_next = 0;
     float a_next = 0.f;
     if (eb + lane < ee) {
-        c_next = __ldcs(p.col + eb + lane);
+        c_next = (unsigned)__ldcs(p.col + eb + lane);
         a_next = has_val ? __ldcs(p.val + eb + lane) : 1.f;
     }
 
     for (int e0 = eb; e0 < ee; e0 += 32) {
-        const int c = c_next;
+        const unsigned c = c_next;
         const float a = a_next;
         const int cnt = min(32, ee - e0);
         {
             const int en = e0 + 32 + lane;
             if (en < ee) {
-                c_next = __ldcs(p.col + en);
+                c_next = (unsigned)__ldcs(p.col + en);
                 a_next = has_val ? __ldcs(p.val + en) : 1.f;
             }
         }
@@ -227,16 +243,13 @@ spmm_seg_kernel(const __grid_constant__ SpmmParams p) {
 #pragma unroll
                 for (int u = 0; u < U; ++u) {
                     const int idx = t + u * NG + g;
-                    const int cc = __shfl_sync(FULL, c, idx);
+                    const unsigned cc = __shfl_sync(FULL, c, idx);
                     aa[u] = __shfl_sync(FULL, a, idx);
-                    const float* xr = p.x + (size_t)cc * (size_t)p.ldx;
+                    const unsigned long long off = (unsigned long long)cc * ldxb;
 #pragma unroll
                     for (int j = 0; j < LPL; ++j) {
-                        if (kok[j]) load_vec<VEC>(xr + koff[j], xv[u][j]);
-                        else {
-#pragma unroll
-                            for (int v = 0; v < VEC; ++v) xv[u][j][v] = 0.f;
-                        }
+                        if constexpr (PARTIAL) load_vec<VEC>(reinterpret_cast<const float*>(xlane[j] + off), xv[u][j]);
+                        else load_vec<VEC>(reinterpret_cast<const float*>(xlane[0] + off) + j * G * VEC, xv[u][j]);
                     }
                 }
 #pragma unroll
@@ -265,15 +278,14 @@ spmm_seg_kernel(const __grid_constant__ SpmmParams p) {
                 for (int u = 0; u < U; ++u) {
                     const int idx = t + u * NG + g;
                     ok[u] = idx < cnt;
-                    const int cc = __shfl_sync(FULL, c, idx & 31);
+                    const unsigned cc = __shfl_sync(FULL, c, idx & 31);
                     aa[u] = __shfl_sync(FULL, a, idx & 31);
-                    const float* xr = p.x + (size_t)cc * (size_t)p.ldx;
+                    const unsigned long long off = (unsigned long long)cc * ldxb;
+                    if (ok[u]) {
 #pragma unroll
-                    for (int j = 0; j < LPL; ++j) {
-                        if (ok[u] && kok[j]) load_vec<VEC>(xr + koff[j], xv[u][j]);
-                        else {
-#pragma unroll
-                            for (int v = 0; v < VEC; ++v) xv[u][j][v] = 0.f;
+                        for (int j = 0; j < LPL; ++j) {
+                            if constexpr (PARTIAL) load_vec<VEC>(reinterpret_cast<const float*>(xlane[j] + off), xv[u][j]);
+                            else load_vec<VEC>(reinterpret_cast<const float*>(xlane[0] + off) + j * G * VEC, xv[u][j]);
                         }
                     }
                 }
@@ -315,58 +327,85 @@ spmm_seg_kernel(const __grid_constant__ SpmmParams p) {
                     }
                 }
         }
-        if (g != 0) return;
     }
+    const bool writer = (NG == 1) || (g == 0);   // group 0 holds the merged result
 
     if (nseg == 1) {
+        if (writer) {
 #pragma unroll
-        for (int j = 0; j < LPL; ++j)
-            if (kok[j]) finalize_store<OP, VEC>(p, row, re - rb, koff[j], acc[j], arg[j]);
-    } else {
-        const size_t slot = (size_t)(__ldg(p.part_off + row) + s);
+            for (int j = 0; j < LPL; ++j)
+                if (kok[j]) finalize_store<OP, VEC>(p, row, re - rb, koff[j], acc[j], arg[j]);
+        }
+        return;
+    }
+
+    // ---- split row: publish this segment's partial; the LAST segment warp to arrive merges
+    // all of the row's partials in segment order (the threadFenceReduction pattern: nobody
+    // waits, the order of the merge is fixed, so the result is deterministic and max/min/arg
+    // stay bit-exact) and finalises the row.  No second kernel launch.
+    const int pbase = __ldg(p.part_off + row);
+    if (writer) {
+        const size_t slot = (size_t)(pbase + s);
 #pragma unroll
         for (int j = 0; j < LPL; ++j) {
             if (kok[j]) {
                 const size_t o = slot * (size_t)p.k + (size_t)koff[j];
                 if constexpr (VEC == 4) {
-                    *reinterpret_cast<float4*>(p.part_val + o) = make_float4(acc[j][0], acc[j][1], acc[j][2], acc[j][3]);
+                    __stcg(reinterpret_cast<float4*>(p.part_val + o), make_float4(acc[j][0], acc[j][1], acc[j][2], acc[j][3]));
+                    if constexpr (OP != OP_SUM)
+                        __stcg(reinterpret_cast<int4*>(p.part_arg + o), make_int4(arg[j][0], arg[j][1], arg[j][2], arg[j][3]));
                 } else {
-                    p.part_val[o] = acc[j][0];
+                    __stcg(p.part_val + o, acc[j][0]);
+                    if constexpr (OP != OP_SUM) __stcg(p.part_arg + o, arg[j][0]);
                 }
-                if constexpr (OP != OP_SUM) store_vec_i32<VEC>(p.part_arg + o, arg[j]);
             }
         }
     }
-}
-
-// ------------------------------------------------------------------------------------
-// fix-up: one warp merges the per-segment partials of one split row, in segment order
-// ------------------------------------------------------------------------------------
-template <int OP>
-__global__ void __launch_bounds__(256)
-spmm_fixup_kernel(const __grid_constant__ SpmmParams p) {
-    const int w = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
-    if (w >= p.num_split_rows) return;
-    const int lane = threadIdx.x & 31;
-    const int row = __ldg(p.split_rows + w);
-    const int nseg = __ldg(p.seg_off + row + 1) - __ldg(p.seg_off + row);
-    const size_t slot0 = (size_t)__ldg(p.part_off + row);
-    const int deg = __ldg(p.rowptr + row + 1) - __ldg(p.rowptr + row);
-    for (int kk = lane; kk < p.k; kk += 32) {
-        float acc[1] = {init_value<OP>()};
-        int arg[1] = {kNoArg};
-        for (int s = 0; s < nseg; ++s) {
-            const size_t o = (slot0 + s) * (size_t)p.k + kk;
-            const float v = p.part_val[o];
-            if constexpr (OP == OP_SUM) {
-                acc[0] += v;
+    __threadfence();
+    __syncwarp();
+    int* const ticket_ptr = p.row_ticket + (size_t)blockIdx.y * (size_t)p.ticket_stride + (pbase >> 1);
+    int ticket = 0;
+    if (lane == 0) ticket = atomicAdd(ticket_ptr, 1);
+    ticket = __shfl_sync(FULL, ticket, 0);
+    if (ticket != nseg - 1) return;
+    __threadfence();
+    if (lane == 0) *ticket_ptr = 0;   // leave the counters zeroed for the next launch
+    if (!writer) return;
+#pragma unroll
+    for (int j = 0; j < LPL; ++j) {
+        if (!kok[j]) continue;
+        float macc[VEC];
+        int marg[VEC];
+#pragma unroll
+        for (int v = 0; v < VEC; ++v) { macc[v] = init_value<OP>(); marg[v] = kNoArg; }
+        const size_t o0 = (size_t)pbase * (size_t)p.k + (size_t)koff[j];
+#pragma unroll 4
+        for (int t = 0; t < nseg; ++t) {
+            const size_t o = o0 + (size_t)t * (size_t)p.k;
+            float pv[VEC];
+            int pa[VEC];
+            if constexpr (VEC == 4) {
+                const float4 q = __ldcg(reinterpret_cast<const float4*>(p.part_val + o));
+                pv[0] = q.x; pv[1] = q.y; pv[2] = q.z; pv[3] = q.w;
+                if constexpr (OP != OP_SUM) {
+                    const int4 r = __ldcg(reinterpret_cast<const int4*>(p.part_arg + o));
+                    pa[0] = r.x; pa[1] = r.y; pa[2] = r.z; pa[3] = r.w;
+                }
             } else {
-                const int a = p.part_arg[o];
-                // segments are in increasing edge order: strict compare keeps the first
-                if (better<OP>(v, acc[0])) { acc[0] = v; arg[0] = a; }
+                pv[0] = __ldcg(p.part_val + o);
+                if constexpr (OP != OP_SUM) pa[0] = __ldcg(p.part_arg + o);
+            }
+#pragma unroll
+            for (int v = 0; v < VEC; ++v) {
+                if constexpr (OP == OP_SUM) {
+                    macc[v] += pv[v];
+                } else {
+                    // segments are in increasing edge order: strict compare keeps the first
+                    if (better<OP>(pv[v], macc[v])) { macc[v] = pv[v]; marg[v] = pa[v]; }
+                }
             }
         }
-        finalize_store<OP, 1>(p, row, deg, kk, acc, arg);
+        finalize_store<OP, VEC>(p, row, re - rb, koff[j], macc, marg);
     }
 }
 
@@ -403,27 +442,29 @@ static TileShape pick_shape(int vec, int64_t k, int kt) {
 typedef void (*SegKernel)(const SpmmParams);
 
 template <int OP, int VEC, int G, int LPL>
-static SegKernel pick_u(int u) {
+static SegKernel pick_u(int u, bool partial) {
     constexpr int NG = 32 / G;
     // keep (entries per step) * U <= 32 and at most 64 staged floats per lane
     if constexpr (LPL * VEC * 8 <= 64)
-        if (u >= 8 && NG * 8 <= 32) return spmm_seg_kernel<OP, VEC, G, LPL, 8>;
-    if (NG * 4 <= 32) return spmm_seg_kernel<OP, VEC, G, LPL, 4>;
+        if (u >= 8 && NG * 8 <= 32)
+            return partial ? spmm_seg_kernel<OP, VEC, G, LPL, 8, true> : spmm_seg_kernel<OP, VEC, G, LPL, 8, false>;
+    if (NG * 4 <= 32)
+        return partial ? spmm_seg_kernel<OP, VEC, G, LPL, 4, true> : spmm_seg_kernel<OP, VEC, G, LPL, 4, false>;
     return nullptr;
 }
 
 template <int OP>
-static SegKernel pick_kernel(const TileShape& t, int u) {
+static SegKernel pick_kernel(const TileShape& t, int u, bool partial) {
     if (t.vec == 4) {
-        if (t.g == 8 && t.lpl == 1) return pick_u<OP, 4, 8, 1>(u);
-        if (t.g == 16 && t.lpl == 1) return pick_u<OP, 4, 16, 1>(u);
-        if (t.g == 32 && t.lpl == 1) return pick_u<OP, 4, 32, 1>(u);
-        if (t.g == 32 && t.lpl == 2) return pick_u<OP, 4, 32, 2>(u);
-        if (t.g == 32 && t.lpl == 4) return pick_u<OP, 4, 32, 4>(u);
+        if (t.g == 8 && t.lpl == 1) return pick_u<OP, 4, 8, 1>(u, partial);
+        if (t.g == 16 && t.lpl == 1) return pick_u<OP, 4, 16, 1>(u, partial);
+        if (t.g == 32 && t.lpl == 1) return pick_u<OP, 4, 32, 1>(u, partial);
+        if (t.g == 32 && t.lpl == 2) return pick_u<OP, 4, 32, 2>(u, partial);
+        if (t.g == 32 && t.lpl == 4) return pick_u<OP, 4, 32, 4>(u, partial);
     } else {
-        if (t.lpl == 1) return pick_u<OP, 1, 32, 1>(u);
-        if (t.lpl == 2) return pick_u<OP, 1, 32, 2>(u);
-        if (t.lpl == 4) return pick_u<OP, 1, 32, 4>(u);
+        if (t.lpl == 1) return pick_u<OP, 1, 32, 1>(u, partial);
+        if (t.lpl == 2) return pick_u<OP, 1, 32, 2>(u, partial);
+        if (t.lpl == 4) return pick_u<OP, 1, 32, 4>(u, partial);
     }
     return nullptr;
 }
@@ -458,27 +499,27 @@ int launch_spmm(int reduce, const SpmmParams& base, int64_t nnz, int variant, cu
     p.tile_w = t.tile_w;
     const int op = (reduce == ISPLIB_REDUCE_MAX) ? OP_MAX : (reduce == ISPLIB_REDUCE_MIN ? OP_MIN : OP_SUM);
 
+    // every tile (incl. the last one) fills all G*LPL vector slots of a lane group?
+    const bool partial = (t.tile_w != t.g * t.lpl * t.vec) || (p.k % t.tile_w != 0);
     SegKernel kern = nullptr;
-    if (op == OP_SUM) kern = pick_kernel<OP_SUM>(t, d->unroll);
-    else if (op == OP_MAX) kern = pick_kernel<OP_MAX>(t, d->unroll);
-    else kern = pick_kernel<OP_MIN>(t, d->unroll);
+    if (op == OP_SUM) kern = pick_kernel<OP_SUM>(t, d->unroll, partial);
+    else if (op == OP_MAX) kern = pick_kernel<OP_MAX>(t, d->unroll, partial);
+    else kern = pick_kernel<OP_MIN>(t, d->unroll, partial);
     if (!kern) return ISPLIB_NO_OPT_IMPL;
 
     const int warps = d->warps;
     const dim3 block(warps * 32);
     const dim3 grid((unsigned)((p.num_items + warps - 1) / warps), (unsigned)t.ntiles);
     if (t.ntiles > 65535) return ISPLIB_NO_OPT_IMPL;
+    if (p.num_split_rows > 0) {
+        // arrival counters of the split rows, one set per K tile (self-resetting, cleared
+        // anyway so an aborted launch cannot poison the next one)
+        if ((size_t)t.ntiles * (size_t)p.ticket_stride > (size_t)p.ticket_capacity) return ISPLIB_NOT_ENOUGH_MEM;
+        ISPLIB_CUDA_TRY(cudaMemsetAsync(p.row_ticket, 0, (size_t)t.ntiles * (size_t)p.ticket_stride * sizeof(int), stream));
+    }
     kern<<<grid, block, 0, stream>>>(p);
     ISPLIB_LAUNCH_CHECK();
 
-    if (p.num_split_rows > 0) {
-        const int fw = 8;
-        const dim3 fgrid((unsigned)((p.num_split_rows + fw - 1) / fw));
-        if (op == OP_SUM) spmm_fixup_kernel<OP_SUM><<<fgrid, fw * 32, 0, stream>>>(p);
-        else if (op == OP_MAX) spmm_fixup_kernel<OP_MAX><<<fgrid, fw * 32, 0, stream>>>(p);
-        else spmm_fixup_kernel<OP_MIN><<<fgrid, fw * 32, 0, stream>>>(p);
-        ISPLIB_LAUNCH_CHECK();
-    }
     return ISPLIB_SUCCESS;
 }
 

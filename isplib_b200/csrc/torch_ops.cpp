@@ -287,6 +287,9 @@ public:
         }
         ctx->saved_data["n"] = mat.size(0);
         ctx->saved_data["has_value"] = value.has_value();
+        // needs_input_grad() indexes tensor inputs only (a None `value` shifts it), so the
+        // flags are taken here, like any_variable_requires_grad at csrc/fusedmm.cpp:228
+        ctx->saved_data["mat_grad"] = mat.requires_grad();
         if (value.has_value()) ctx->save_for_backward({rowptr, col, value.value()});
         else ctx->save_for_backward({rowptr, col});
         return {out};
@@ -300,7 +303,7 @@ public:
         if (ctx->saved_data["has_value"].toBool()) value = saved[2];
         // grad_value is never computed by the reference for sum (csrc/fusedmm.cpp:268-272)
         Tensor grad_mat;
-        if (ctx->needs_input_grad(3)) {
+        if (ctx->saved_data["mat_grad"].toBool()) {
             c10::cuda::CUDAGuard guard(grad_out.device());
             std::lock_guard<std::mutex> lk(g->mu);
             ensure_csc(*g, n);
@@ -325,6 +328,9 @@ public:
         }
         ctx->saved_data["n"] = mat.size(0);
         ctx->saved_data["has_value"] = value.has_value();
+        // needs_input_grad() indexes tensor inputs only (a None `value` shifts it), so the
+        // flags are taken here, like any_variable_requires_grad at csrc/fusedmm.cpp:228
+        ctx->saved_data["mat_grad"] = mat.requires_grad();
         if (value.has_value()) ctx->save_for_backward({rowptr, col, value.value()});
         else ctx->save_for_backward({rowptr, col});
         return {out};
@@ -337,7 +343,7 @@ public:
         c10::optional<Tensor> value = c10::nullopt;
         if (ctx->saved_data["has_value"].toBool()) value = saved[2];
         Tensor grad_mat;
-        if (ctx->needs_input_grad(3)) {
+        if (ctx->saved_data["mat_grad"].toBool()) {
             c10::cuda::CUDAGuard guard(grad_out.device());
             std::lock_guard<std::mutex> lk(g->mu);
             ensure_csc(*g, n);
@@ -365,6 +371,8 @@ public:
             arg_out = std::get<1>(r).value();
         }
         ctx->saved_data["has_value"] = value.has_value();
+        ctx->saved_data["mat_grad"] = mat.requires_grad();
+        ctx->saved_data["value_grad"] = value.has_value() && value->requires_grad();
         if (value.has_value()) ctx->save_for_backward({rowptr, col, mat, arg_out, value.value()});
         else ctx->save_for_backward({rowptr, col, mat, arg_out});
         ctx->mark_non_differentiable({arg_out});  // csrc/fusedmm.cpp:403
@@ -378,8 +386,8 @@ public:
         Tensor mat = saved[2].contiguous(), arg_out = saved[3];
         Tensor value = has_value ? saved[4].contiguous() : Tensor();
         const int64_t M = arg_out.size(0), K = arg_out.size(1), N = mat.size(0), nnz = g->fwd.nnz;
-        const bool need_val = has_value && ctx->needs_input_grad(2);
-        const bool need_mat = ctx->needs_input_grad(3);
+        const bool need_val = has_value && ctx->saved_data["value_grad"].toBool();
+        const bool need_mat = ctx->saved_data["mat_grad"].toBool();
         Tensor grad_value, grad_mat;
         if (need_val || need_mat) {
             c10::cuda::CUDAGuard guard(grad_out.device());

@@ -176,9 +176,5 @@ class RowPartitionedSpMM:
 
     def launches_per_forward(self) -> int:
         """how many of OUR kernels one forward launches (for bench.py's gpu_launches)."""
-        n = 0
-        for b in ([self.local] if self.world == 1 else [self.local, self.remote]):
-            n += 1
-            if b.plan is not None and b.plan.info.num_split_rows > 0:
-                n += 1
+        n = 1 if self.world == 1 else 2   # one spmm_seg_kernel per column block
         return n

@@ -55,7 +55,7 @@ def test_host_side_argument_validation():
     sum_bytes = n.value
     assert lib.isplib_b200_spmm_workspace_bytes(ctypes.byref(info), 128, capi.MAX, ctypes.byref(n)) == 0
     assert n.value > sum_bytes >= 3 * 128 * 4
-    assert lib.isplib_b200_spmm_workspace_bytes(ctypes.byref(info), 128, 9, ctypes.byref(n)) == 256
+    assert lib.isplib_b200_spmm_workspace_bytes(ctypes.byref(info), 128, 9, ctypes.byref(n)) == 128
     # unknown FusedMM message -> FUSEDMM_NO_OPT_IMPL (csrc/fusedMM.h:114)
     assert lib.isplib_b200_fusedmm_csr_host(0x11101, 1, 1, 1, 1.0, 0, 1, 1, None, None, None, None, None, 1,
                                             None, 1, 0.0, None, 1, None) == 128

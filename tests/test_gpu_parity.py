@@ -293,10 +293,25 @@ def test_bad_arguments_return_status(capi):
     with pytest.raises(capi.IsplibError) as e:
         capi.spmm_csr("sum", rp, co, None, x, plan, variant=999)
     assert e.value.status == 128
-    other = capi.Plan(torch.tensor([0, 1, 2], dtype=torch.int32, device=DEV), 2)
-    with pytest.raises(capi.IsplibError) as e:
-        capi.spmm_csr("sum", rp, co, None, x, other)        # plan of another graph
-    assert e.value.status == 1
+    import ctypes
+    out = torch.empty((1, 4), device=DEV)
+    L = capi.lib()
+    P = lambda t: ctypes.c_void_p(t.data_ptr())
+    # plan built for m=1 used with m=2: FUSEDMM_FAIL_RETURN, nothing launched
+    st = L.isplib_b200_spmm_csr(capi.SUM, 2, 1, 4, 1, P(rp), P(co), None, P(x), 4, P(out), 4, None,
+                                ctypes.byref(plan.info), plan.ptr, None, 0, -1, None)
+    assert st == 1
+    # max without arg_out
+    st = L.isplib_b200_spmm_csr(capi.MAX, 1, 1, 4, 1, P(rp), P(co), None, P(x), 4, P(out), 4, None,
+                                ctypes.byref(plan.info), plan.ptr, None, 0, -1, None)
+    assert st == 256
+    # a split row needs workspace: none given -> FUSEDMM_NOT_ENOUGH_MEM
+    rp2 = torch.tensor([0, 600], dtype=torch.int32, device=DEV)
+    co2 = torch.zeros(600, dtype=torch.int32, device=DEV)
+    plan2 = capi.Plan(rp2, 600)
+    st = L.isplib_b200_spmm_csr(capi.SUM, 1, 1, 4, 600, P(rp2), P(co2), None, P(x), 4, P(out), 4, None,
+                                ctypes.byref(plan2.info), plan2.ptr, None, 0, -1, None)
+    assert st == -1
 
 
 # ----------------------------------------------------------------- arg backward

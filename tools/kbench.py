@@ -1,0 +1,54 @@
+#!/usr/bin/env python
+"""Kernel iteration tool (GPU box): times every supported variant of the forward SpMM
+through the C ABI on one synthetic shape and prints ms / effective GB/s per variant.
+
+    python tools/kbench.py --shape reddit --k 128 --reduce sum [--novalue] [--iters 5]
+"""
+import argparse
+import json
+import os
+import sys
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import torch  # noqa: E402
+from isplib_b200 import capi, synth  # noqa: E402
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--shape", default="reddit")
+    ap.add_argument("--k", type=int, nargs="+", default=[128])
+    ap.add_argument("--reduce", nargs="+", default=["sum"])
+    ap.add_argument("--novalue", action="store_true")
+    ap.add_argument("--iters", type=int, default=5)
+    ap.add_argument("--seg-len", type=int, nargs="+", default=[0])
+    ap.add_argument("--scale", type=float, default=1.0)
+    ap.add_argument("--json", default=None)
+    a = ap.parse_args()
+    dev = "cuda:0"
+    g = synth.make_graph(a.shape, values=None if a.novalue else "uniform", seed=0, device=dev, scale=a.scale)
+    rp, co = capi.narrow_i64_to_i32(g.rowptr), capi.narrow_i64_to_i32(g.col)
+    names = capi.variant_names()
+    results = []
+    for seg in a.seg_len:
+        plan = capi.Plan(rp, g.nnz, seg)
+        i = plan.info
+        print(f"# {a.shape} m={g.m} nnz={g.nnz} maxdeg={g.max_degree} seg_len={i.seg_len} items={i.num_items} "
+              f"split_rows={i.num_split_rows} split_items={i.num_split_items}")
+        for k in a.k:
+            x = torch.randn(g.n, k, device=dev)
+            for red in a.reduce:
+                best, times = capi.spmm_autotune(red, rp, co, g.value, x, plan, iters=a.iters)
+                b = synth.algorithmic_bytes(g.m, g.nnz, k, g.value is not None, red)
+                for v, t in enumerate(times):
+                    if t >= 0:
+                        mark = " <== best" if v == best else ""
+                        print(f"K={k:4d} {red:4s} seg={i.seg_len:4d} {names[v]:24s} {t:8.3f} ms  {b / t / 1e6:9.1f} GB/s{mark}")
+                        results.append(dict(k=k, reduce=red, seg_len=i.seg_len, variant=names[v], ms=t, gbs=b / t / 1e6))
+    if a.json:
+        with open(a.json, "w") as f:
+            json.dump(results, f, indent=1)
+
+
+if __name__ == "__main__":
+    main()
