@@ -23,7 +23,7 @@ namespace isplib {
         if (_e != cudaSuccess) return ISPLIB_CUDA_ERROR_BASE + (int)_e;  \
     } while (0)
 
-constexpr int kDefaultSegLen = 256;
+constexpr int kDefaultSegLen = 512;  // Reddit-shape sweep (gpurun_out kbench_r1_seglen): 512-1024 best
 constexpr int kNumSMs = 148;  // B200: 2 dies x 74 SMs
 constexpr int kMinTileW = 8;  // narrowest K tile any variant uses (sizes the ticket array)
 

@@ -178,3 +178,99 @@ class RowPartitionedSpMM:
         """how many of OUR kernels one forward launches (for bench.py's gpu_launches)."""
         n = 1 if self.world == 1 else 2   # one spmm_seg_kernel per column block
         return n
+
+
+# ----------------------------------------------------------------------------------------
+# autograd over the partitioned operator
+# ----------------------------------------------------------------------------------------
+def transpose_csr(rowptr: torch.Tensor, col: torch.Tensor, value: Optional[torch.Tensor], n_cols: int,
+                  mean_weights: bool = False):
+    """A^T in CSR form (colptr, row[csr2csc], value[csr2csc]) -- isplib/__init__.py:76-99 of
+    the reference -- with plain torch ops (one-time, any device).  mean_weights divides the
+    permuted values by max(deg(row),1): the weights of the mean backward."""
+    m = rowptr.numel() - 1
+    deg = rowptr[1:] - rowptr[:-1]
+    row = torch.repeat_interleave(torch.arange(m, device=col.device, dtype=torch.int64), deg)
+    csr2csc = torch.argsort(col * m + row, stable=True)
+    colptr = torch.zeros(n_cols + 1, dtype=torch.int64, device=col.device)
+    colptr[1:] = torch.cumsum(torch.bincount(col, minlength=n_cols), 0)
+    row_t = row[csr2csc]
+    val_t = None if value is None else value[csr2csc]
+    if mean_weights:
+        w = deg.clamp(min=1).to(torch.float32)[row_t]
+        val_t = (1.0 / w) if val_t is None else val_t / w
+    return colptr, row_t, val_t
+
+
+def _cuda_arg_backward(col32, val, arg, grad_out, n_rows_out, arg_sentinel):
+    from . import capi
+    gx, _ = capi.spmm_arg_backward(col32, val, None, arg, grad_out, n_rows_out, True, False, arg_sentinel)
+    return gx
+
+
+class DistSpMM:
+    """Autograd-aware row-partitioned ``matmul``: ``out_slice = dist_spmm(x_slice, reduce)``.
+
+    x_slice / out_slice are this rank's padded row slices ([Rc, K] / [R, K]).  Gradients flow
+    to x_slice: sum/mean through the partitioned A^T (all-gather of grad_out + SpMM, the same
+    machinery as the forward), max/min through a local arg-scatter + reduce-scatter."""
+
+    def __init__(self, rowptr, col, value, n_cols, group=None, device=None, block_spmm=None,
+                 arg_backward=None, overlap=True):
+        self.rowptr, self.col, self.value = rowptr, col, value
+        self.m, self.n = rowptr.numel() - 1, int(n_cols)
+        self.group, self.device = group, device
+        self._kw = dict(group=group, device=device, block_spmm=block_spmm, overlap=overlap)
+        self.fwd = RowPartitionedSpMM(rowptr, col, value, n_cols, **self._kw)
+        self._bwd = {}
+        self._arg_backward = arg_backward or _cuda_arg_backward
+        self._col32 = None
+
+    def bwd_op(self, mean: bool) -> RowPartitionedSpMM:
+        if mean not in self._bwd:
+            colptr, row_t, val_t = transpose_csr(self.rowptr, self.col, self.value, self.n, mean_weights=mean)
+            self._bwd[mean] = RowPartitionedSpMM(colptr, row_t, val_t, self.m, **self._kw)
+        return self._bwd[mean]
+
+    def __call__(self, x_slice: torch.Tensor, reduce: str = "sum") -> torch.Tensor:
+        return _DistSpMMFn.apply(x_slice, self, reduce)
+
+
+class _DistSpMMFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x_slice, op: DistSpMM, reduce: str):
+        out, arg = op.fwd.forward(x_slice.contiguous(), reduce)
+        ctx.op, ctx.reduce = op, reduce
+        if arg is not None:
+            ctx.save_for_backward(arg)
+        return out
+
+    @staticmethod
+    def backward(ctx, grad_out):
+        op, reduce = ctx.op, ctx.reduce
+        code = REDUCE_CODE[reduce]
+        grad_out = grad_out.contiguous()
+        if code in (SUM, MEAN):
+            t = op.bwd_op(code == MEAN)
+            g = grad_out
+            if g.size(0) != t.Rc:                      # pad the row slice of grad_out like X
+                g = t.pad_x(g[: t.Rc])
+            gx, _ = t.forward(g, "sum")                # csrc/fusedmm.cpp:285 / :375 of the reference
+            return gx, None, None
+        # max / min: scatter through the global edge ids, then sum the partials of all ranks
+        (arg,) = ctx.saved_tensors
+        f = op.fwd
+        dev = grad_out.device
+        if op._col32 is None:
+            op._col32 = op.col.to(dev).to(torch.int32)
+            op._val_dev = None if op.value is None else op.value.to(dev)
+        partial = op._arg_backward(op._col32, op._val_dev, arg, grad_out, f.world * f.Rc, f.nnz)
+        if f.world == 1:
+            return partial, None, None
+        out = torch.empty((f.Rc, partial.size(1)), dtype=partial.dtype, device=dev)
+        if dist.get_backend(f.group) == "nccl":
+            dist.reduce_scatter_tensor(out, partial, group=f.group)
+        else:                                          # gloo (CPU tests) has no reduce-scatter
+            dist.all_reduce(partial, group=f.group)
+            out.copy_(partial[f.rank * f.Rc:(f.rank + 1) * f.Rc])
+        return out, None, None

@@ -1,0 +1,144 @@
+"""world_size-2 gloo tests (CPU) of the multi-GPU host logic in isplib_b200/dist.py: row
+partition, column-owner split, all-gather layout, ACCUMULATE/edge-id merge protocol,
+transposed operator for the backward, reduce-scatter of the arg-scatter partials.
+
+The per-block SpMM is injected (the oracle stands in for the CUDA C ABI, honouring the same
+flags), so what is tested is everything AROUND the kernel.  Checked against the single-process
+oracle on the whole graph."""
+import os
+import sys
+
+import numpy as np
+import pytest
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+
+def oracle_block_spmm(reduce_code, block, x, out, arg_out, flags, row_divisor, arg_sentinel, variant=-1):
+    """numpy stand-in for isplib_b200_spmm_csr_ex with the same contract (edge_ids,
+    ISPLIB_FLAG_ACCUMULATE, row_divisor, arg_sentinel)."""
+    from oracle import oracle
+    rp = block.rowptr.numpy().astype(np.int64)
+    co = block.col.numpy().astype(np.int64)
+    va = None if block.val is None else block.val.numpy()
+    o, a = oracle.spmm_c(rp, co, va, x.numpy(), reduce_code)
+    nnz_b = co.shape[0]
+    if reduce_code in (1, 2):
+        gid = np.where(a == nnz_b, arg_sentinel, block.edge_ids.numpy().astype(np.int64)[np.minimum(a, max(nnz_b - 1, 0))]
+                       if nnz_b else arg_sentinel)
+        if flags & 1:
+            po, pa = out.numpy(), arg_out.numpy()
+            better = (o > po) if reduce_code == 1 else (o < po)
+            take = better | ((o == po) & (gid < pa))
+            o, gid = np.where(take, o, po), np.where(take, gid, pa)
+        out.copy_(torch.from_numpy(o))
+        arg_out.copy_(torch.from_numpy(gid))
+    else:
+        if flags & 1:
+            o = out.numpy() + o
+        if row_divisor is not None:
+            o = o / row_divisor.numpy()[:, None]
+        out.copy_(torch.from_numpy(o.astype(np.float32)))
+    return out, arg_out
+
+
+def oracle_arg_backward(col32, val, arg, grad_out, n_rows_out, arg_sentinel):
+    from oracle import oracle
+    gx, _ = oracle.arg_backward(col32.numpy().astype(np.int64), None if val is None else val.numpy(), None,
+                                arg.numpy(), grad_out.numpy(), n_rows_out)
+    return torch.from_numpy(gx)
+
+
+def make_graph(seed, M, N, with_value):
+    rng = np.random.default_rng(seed)
+    deg = rng.integers(0, 30, size=M)
+    deg[3] = 400
+    rowptr = np.zeros(M + 1, dtype=np.int64)
+    rowptr[1:] = np.cumsum(deg)
+    row = np.repeat(np.arange(M), deg)
+    col = rng.integers(0, N, size=int(rowptr[-1]))
+    order = np.lexsort((col, row))
+    col = col[order]
+    val = np.round(rng.random(col.shape[0]) * 4 - 2).astype(np.float32) if with_value else None   # ties on purpose
+    return rowptr, col, val
+
+
+def worker(rank, world, port, with_value, results):
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        from isplib_b200.dist import DistSpMM
+        from oracle import oracle
+        M = N = 101            # not divisible by world: exercises the padding
+        K = 6
+        rowptr, col, val = make_graph(5, M, N, with_value)
+        x = np.random.default_rng(1).integers(-3, 4, size=(N, K)).astype(np.float32)
+        go = np.random.default_rng(2).standard_normal((M, K)).astype(np.float32)
+        op = DistSpMM(torch.from_numpy(rowptr), torch.from_numpy(col), None if val is None else torch.from_numpy(val),
+                      N, device="cpu", block_spmm=oracle_block_spmm, arg_backward=oracle_arg_backward, overlap=False)
+        f = op.fwd
+        assert f.R == (M + world - 1) // world and f.local.nnz + f.remote.nnz == int(rowptr[min((rank + 1) * f.R, M)] - rowptr[min(rank * f.R, M)])
+        r0, r1 = rank * f.R, min((rank + 1) * f.R, M)
+        ok = {}
+        for reduce in ("sum", "mean", "max", "min"):
+            xs = f.pad_x(torch.from_numpy(x[rank * f.Rc: min((rank + 1) * f.Rc, N)])).requires_grad_(True)
+            out = op(xs, reduce)
+            gpad = torch.zeros((f.R, K))
+            gpad[: r1 - r0] = torch.from_numpy(go[r0:r1])
+            out.backward(gpad)
+            code = oracle.REDUCE_CODE[reduce]
+            ref, ref_arg = oracle.spmm_c(rowptr, col, val, x, code)
+            got = out.detach().numpy()[: r1 - r0]
+            if reduce in ("max", "min"):
+                ok[reduce + "_fwd"] = bool(np.array_equal(got, ref[r0:r1]))
+                gref, _ = oracle.arg_backward(col, val, None, ref_arg, go, N)
+            else:
+                ok[reduce + "_fwd"] = bool(np.allclose(got, ref[r0:r1], rtol=1e-5, atol=1e-5))
+                bw = oracle.spmm_backward_sum if reduce == "sum" else oracle.spmm_backward_mean
+                gref = bw(rowptr, col, val, go, N)
+            c0, c1 = rank * f.Rc, min((rank + 1) * f.Rc, N)
+            ok[reduce + "_bwd"] = bool(np.allclose(xs.grad.numpy()[: c1 - c0], gref[c0:c1], rtol=1e-4, atol=1e-4))
+        results[rank] = ok
+    finally:
+        dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("with_value", [True, False])
+def test_row_partitioned_spmm_world2_gloo(with_value):
+    world = 2
+    port = 29500 + (os.getpid() % 2000) + (1 if with_value else 0)
+    mgr = mp.Manager()
+    results = mgr.dict()
+    mp.spawn(worker, args=(world, port, with_value, results), nprocs=world, join=True)
+    assert len(results) == world
+    for rank in range(world):
+        bad = [k for k, v in results[rank].items() if not v]
+        assert not bad, f"rank {rank}: {bad}"
+
+
+def test_split_row_block_partitions_every_entry_once():
+    from isplib_b200.dist import split_row_block
+    rowptr, col, val = make_graph(9, 57, 44, True)
+    rp, co, va = torch.from_numpy(rowptr), torch.from_numpy(col), torch.from_numpy(val)
+    for world in (1, 2, 3, 8):
+        seen = []
+        for rank in range(world):
+            loc, rem, deg, R = split_row_block(rp, co, va, rank, world, 44)
+            assert loc.rowptr.numel() == R + 1 and rem.rowptr.numel() == R + 1
+            Rc = (44 + world - 1) // world
+            assert loc.col.numel() == 0 or int(loc.col.max()) < Rc
+            assert not bool(((rem.col >= rank * Rc) & (rem.col < (rank + 1) * Rc)).any())
+            # edge ids are increasing inside each block row (the tie-break relies on it)
+            for b in (loc, rem):
+                e = b.edge_ids.numpy().astype(np.int64)
+                for i in range(R):
+                    seg = e[int(b.rowptr[i]):int(b.rowptr[i + 1])]
+                    assert (np.diff(seg) > 0).all()
+            seen += loc.edge_ids.tolist() + rem.edge_ids.tolist()
+        assert sorted(seen) == list(range(col.shape[0]))

@@ -267,7 +267,7 @@ def test_plan_info(capi):
     deg = np.array([0, 1, 256, 257, 1000, 0, 3], dtype=np.int64)
     rowptr = np.concatenate([[0], np.cumsum(deg)])
     rp = torch.from_numpy(rowptr).to(DEV).to(torch.int32)
-    plan = capi.Plan(rp, int(rowptr[-1]))
+    plan = capi.Plan(rp, int(rowptr[-1]), 256)
     i = plan.info
     assert (i.m, i.nnz, i.seg_len) == (7, int(rowptr[-1]), 256)
     assert i.num_items == 1 + 1 + 1 + 2 + 4 + 1 + 1
@@ -308,7 +308,7 @@ def test_bad_arguments_return_status(capi):
     # a split row needs workspace: none given -> FUSEDMM_NOT_ENOUGH_MEM
     rp2 = torch.tensor([0, 600], dtype=torch.int32, device=DEV)
     co2 = torch.zeros(600, dtype=torch.int32, device=DEV)
-    plan2 = capi.Plan(rp2, 600)
+    plan2 = capi.Plan(rp2, 600, 256)
     st = L.isplib_b200_spmm_csr(capi.SUM, 1, 1, 4, 600, P(rp2), P(co2), None, P(x), 4, P(out), 4, None,
                                 ctypes.byref(plan2.info), plan2.ptr, None, 0, -1, None)
     assert st == -1
