@@ -135,8 +135,9 @@ const char* isplib_b200_variant_name(int variant);
 /* 1 if `variant` can run this problem, else 0 */
 int         isplib_b200_variant_supported(int variant, int reduce, int64_t k, int64_t ldx,
                                           int64_t ldo, const void* x, const void* out);
-/* Heuristic default for (k, reduce, average degree). */
-int         isplib_b200_variant_default(int reduce, int64_t k, int64_t ldx, int64_t ldo,
+/* Heuristic default from the shape alone (n = rows of x): narrow K tiles only when they
+ * make an [n, tile] slab of x L2-resident while the whole x is not. */
+int         isplib_b200_variant_default(int reduce, int64_t n, int64_t k, int64_t ldx, int64_t ldo,
                                         const void* x, const void* out, double avg_degree);
 /* Times every supported variant (1 warm-up + iters timed launches each, CUDA events
  * on `stream`), writes ms per launch to times_ms[variant] (negative = unsupported),

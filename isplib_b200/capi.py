@@ -73,7 +73,7 @@ def lib() -> ctypes.CDLL:
     L.isplib_b200_variant_name.restype = ctypes.c_char_p
     L.isplib_b200_variant_name.argtypes = [ctypes.c_int]
     L.isplib_b200_variant_supported.argtypes = [ctypes.c_int, ctypes.c_int, i64, i64, i64, p, p]
-    L.isplib_b200_variant_default.argtypes = [ctypes.c_int, i64, i64, i64, p, p, ctypes.c_double]
+    L.isplib_b200_variant_default.argtypes = [ctypes.c_int, i64, i64, i64, i64, p, p, ctypes.c_double]
     L.isplib_b200_spmm_autotune.argtypes = spmm_args + [ctypes.c_int, ctypes.POINTER(ctypes.c_int),
                                                         ctypes.POINTER(f32), p]
     L.isplib_b200_csr_transpose_workspace_bytes.argtypes = [i64, i64, i64, ctypes.POINTER(sz)]

@@ -42,9 +42,9 @@ extern "C" int isplib_b200_variant_supported(int variant, int reduce, int64_t k,
     return spmm_variant_supported(variant, reduce, k, ldx, ldo, x, out) ? 1 : 0;
 }
 
-extern "C" int isplib_b200_variant_default(int reduce, int64_t k, int64_t ldx, int64_t ldo,
+extern "C" int isplib_b200_variant_default(int reduce, int64_t n, int64_t k, int64_t ldx, int64_t ldo,
                                            const void* x, const void* out, double avg_degree) {
-    return spmm_variant_default(reduce, k, ldx, ldo, x, out, avg_degree);
+    return spmm_variant_default(reduce, n, k, ldx, ldo, x, out, avg_degree);
 }
 
 static int fill_params(SpmmParams& p, int reduce, int64_t m, int64_t n, int64_t k, int64_t nnz,
@@ -131,7 +131,7 @@ extern "C" int isplib_b200_spmm_csr_ex(int reduce, int64_t m, int64_t n, int64_t
     if (st) return st;
     if (m == 0 || k == 0) return ISPLIB_SUCCESS;
     if (variant == ISPLIB_VARIANT_AUTO)
-        variant = spmm_variant_default(reduce, k, ldx, ldo, x, out, m > 0 ? (double)nnz / (double)m : 0.0);
+        variant = spmm_variant_default(reduce, n, k, ldx, ldo, x, out, m > 0 ? (double)nnz / (double)m : 0.0);
     if (!spmm_variant_supported(variant, reduce, k, ldx, ldo, x, out)) return ISPLIB_NO_OPT_IMPL;
     return launch_spmm(reduce, p, nnz, variant, (cudaStream_t)stream);
 }
@@ -164,7 +164,7 @@ extern "C" int isplib_b200_spmm_autotune(int reduce, int64_t m, int64_t n, int64
                          plan_dev, workspace, workspace_bytes, 0, nullptr, nullptr, nnz);
     if (st) return st;
     const int nv = variant_count();
-    *best_variant = spmm_variant_default(reduce, k, ldx, ldo, x, out, m > 0 ? (double)nnz / (double)m : 0.0);
+    *best_variant = spmm_variant_default(reduce, n, k, ldx, ldo, x, out, m > 0 ? (double)nnz / (double)m : 0.0);
     if (times_ms) for (int v = 0; v < nv; ++v) times_ms[v] = -1.f;
     if (m == 0 || k == 0) return ISPLIB_SUCCESS;
 

@@ -122,7 +122,7 @@ const VariantDesc* variant_desc(int v);
 int launch_spmm(int reduce, const SpmmParams& base, int64_t nnz, int variant, cudaStream_t stream);
 bool spmm_variant_supported(int variant, int reduce, int64_t k, int64_t ldx, int64_t ldo,
                             const void* x, const void* out);
-int spmm_variant_default(int reduce, int64_t k, int64_t ldx, int64_t ldo, const void* x,
+int spmm_variant_default(int reduce, int64_t n, int64_t k, int64_t ldx, int64_t ldo, const void* x,
                          const void* out, double avg_degree);
 
 }  // namespace isplib

@@ -481,10 +481,31 @@ bool spmm_variant_supported(int variant, int reduce, int64_t k, int64_t ldx, int
     return true;
 }
 
-int spmm_variant_default(int reduce, int64_t k, int64_t ldx, int64_t ldo, const void* x,
-                         const void* out, double avg_degree) {
-    (void)reduce; (void)ldx; (void)ldo; (void)x; (void)out; (void)avg_degree;
+static int find_variant(int warps, int unroll, int kt) {
+    for (int v = 0; v < variant_count(); ++v)
+        if (kVariants[v].warps == warps && kVariants[v].unroll == unroll && kVariants[v].kt == kt) return v;
     return 0;
+}
+
+// Shape-only default (the op layer replaces it by the measured winner when autotuning is on).
+// Measured on B200 (profiles/r1_kbench_*.txt): 4 warps/CTA and U=4 win everywhere; a K tile
+// pays off only when it makes an [n, tile] slab of x L2-resident (126 MB L2) while x itself
+// is not (Reddit-shape K>=128 -> 64-wide); when nothing can be resident (products/amazon
+// shapes) 128-wide tiles are marginally ahead for K > 128.
+int spmm_variant_default(int reduce, int64_t n, int64_t k, int64_t ldx, int64_t ldo, const void* x,
+                         const void* out, double avg_degree) {
+    (void)reduce; (void)avg_degree;
+    const double MB = 1024.0 * 1024.0;
+    const double x_bytes = (double)n * (double)k * 4.0;
+    int kt = 0;
+    if (x_bytes > 96.0 * MB) {
+        if (k > 128 && (double)n * 128.0 * 4.0 <= 64.0 * MB) kt = 128;
+        else if (k > 64 && (double)n * 64.0 * 4.0 <= 64.0 * MB) kt = 64;
+        else if (k > 128) kt = 128;
+    }
+    int v = find_variant(4, 4, kt);
+    if (!spmm_variant_supported(v, reduce, k, ldx, ldo, x, out)) v = find_variant(4, 4, 0);
+    return v;
 }
 
 int launch_spmm(int reduce, const SpmmParams& base, int64_t nnz, int variant, cudaStream_t stream) {

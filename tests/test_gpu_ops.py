@@ -244,3 +244,48 @@ def test_fullsize_backward_adjoint(reddit):
     lhs = float((y.double() * go.double()).sum())
     rhs = float((x.double() * gx.double()).sum())
     assert abs(lhs - rhs) <= 1e-5 * max(1.0, abs(lhs), float((y.double().abs() * go.double().abs()).sum()) * 1e-2)
+
+
+# --------------------------------------------------------------------------------------
+# callers: the GNN layers of the reference's benchmark scripts, patched vs stock matmul
+# --------------------------------------------------------------------------------------
+@pytest.mark.parametrize("model_name", ["gcn", "sage-mean", "sage-sum", "gin"])
+def test_gnn_training_step_patched_equals_stock(isplib, model_name):
+    """One full training step (forward, nll_loss, backward) of the 2-layer models the reference
+    benchmarks (tests/cpu/gcn-sparse.py, graphSAGE-sparse.py, gin-sparse.py): with the plugin
+    active (CUDA kernels) vs inactive (stock torch-op matmul) -> same loss and gradients."""
+    import copy
+    import torch.nn.functional as F
+    from isplib import iSpLibPlugin
+    from isplib_b200 import nn as gnn, synth
+    torch.manual_seed(0)
+    g = synth.make_graph(1500, 40_000, law="lognormal", param=1.0, values="gcn" if model_name == "gcn" else None, seed=4)
+    adj = g.to(DEV).sparse_tensor()
+    feat, hidden, classes = 24, 32, 7
+    x = torch.randn(g.n, feat, device=DEV)
+    y = torch.randint(0, classes, (g.n,), device=DEV)
+    if model_name == "gcn":
+        model = gnn.GCN(feat, hidden, classes, dropout=0.0)
+    elif model_name.startswith("sage"):
+        model = gnn.GraphSAGE(feat, hidden, classes, aggr=model_name.split("-")[1], dropout=0.0)
+    else:
+        model = gnn.GIN(feat, hidden, classes)
+    model = model.to(DEV).eval() if model_name == "gin" else model.to(DEV)   # GIN: no dropout randomness
+    ref_model = copy.deepcopy(model)
+
+    def step(m):
+        out = m(x, adj)
+        lp = out if model_name != "gin" else F.log_softmax(out, dim=1)
+        loss = F.nll_loss(lp, y)
+        loss.backward()
+        return loss.item(), [p.grad.clone() for p in m.parameters()]
+
+    iSpLibPlugin.patch_pyg()
+    try:
+        loss_a, grads_a = step(model)
+    finally:
+        iSpLibPlugin.unpatch_pyg()
+    loss_b, grads_b = step(ref_model)
+    assert abs(loss_a - loss_b) <= 1e-4 * max(1.0, abs(loss_b))
+    for ga, gb in zip(grads_a, grads_b):
+        torch.testing.assert_close(ga, gb, rtol=2e-3, atol=2e-4)

@@ -1,0 +1,148 @@
+#!/usr/bin/env python
+"""Full-batch GNN training epoch on a synthetic graph, patched through iSpLibPlugin.
+
+Epoch definition = /root/reference/tests/cpu/gcn-sparse.py:82-93: zero_grad -> forward ->
+nll_loss(train mask) -> backward -> Adam step -> a second forward for train accuracy.
+Prints one JSON line: epoch ms with and without the accuracy forward, and the share of the
+epoch spent in isplib SpMM calls (forward + backward).
+
+    python tools/epoch_bench.py --model gcn --shape products --feat 100 --hidden 256 --classes 47
+    torchrun --nproc-per-node 2 tools/epoch_bench.py ...        (row-partitioned)
+"""
+import argparse
+import json
+import os
+import sys
+import time
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import torch  # noqa: E402
+import torch.distributed as dist  # noqa: E402
+import torch.nn.functional as F  # noqa: E402
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--model", default="gcn", choices=["gcn", "sage-mean", "sage-sum", "gin"])
+    ap.add_argument("--shape", default="products")
+    ap.add_argument("--feat", type=int, default=100)
+    ap.add_argument("--hidden", type=int, default=256)
+    ap.add_argument("--classes", type=int, default=47)
+    ap.add_argument("--epochs", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=2)
+    ap.add_argument("--scale", type=float, default=1.0)
+    ap.add_argument("--stock", action="store_true", help="do not patch: stock torch-op matmul (the 'pt1' mode)")
+    a = ap.parse_args()
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    lrank = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(lrank)
+    dev = torch.device("cuda", lrank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    import isplib_b200  # noqa: F401
+    from isplib import iSpLibPlugin
+    from isplib_b200 import nn as gnn, synth
+    from isplib_b200.dist import DistSpMM
+
+    torch.manual_seed(0)
+    values = "gcn" if a.model == "gcn" else None
+    g = synth.make_graph(a.shape, values=values, seed=0, device=dev, scale=a.scale)
+    N = g.n
+    gen = torch.Generator(device=dev).manual_seed(0)
+    x_all = torch.randn(N, a.feat, device=dev, generator=gen)
+    y_all = torch.randint(0, a.classes, (N,), device=dev, generator=gen)
+    train_all = torch.rand(N, device=dev, generator=gen) < 0.5
+
+    if a.model == "gcn":
+        model = gnn.GCN(a.feat, a.hidden, a.classes)
+    elif a.model.startswith("sage"):
+        model = gnn.GraphSAGE(a.feat, a.hidden, a.classes, aggr=a.model.split("-")[1])
+    else:
+        model = gnn.GIN(a.feat, a.hidden, a.classes)
+    model = model.to(dev)
+    opt = torch.optim.Adam(model.parameters(), lr=0.01, weight_decay=5e-4)
+
+    if world == 1:
+        adj = g.sparse_tensor()
+        spmm = None
+        x, y, train = x_all, y_all, train_all
+        n_train = int(train.sum())
+    else:
+        op = DistSpMM(g.rowptr, g.col, g.value, N, device=dev)
+        f = op.fwd
+        adj = None
+        spmm = op
+        r0, r1 = rank * f.Rc, min((rank + 1) * f.Rc, N)
+        x = f.pad_x(x_all[r0:r1])
+        y = torch.zeros(f.Rc, dtype=torch.long, device=dev)
+        y[: r1 - r0] = y_all[r0:r1]
+        train = torch.zeros(f.Rc, dtype=torch.bool, device=dev)
+        train[: r1 - r0] = train_all[r0:r1]
+        n_train = int(train_all.sum())
+        for p in model.parameters():
+            dist.broadcast(p.data, 0)
+    del x_all
+
+    if not a.stock:
+        iSpLibPlugin.patch_pyg()
+
+    def loss_fn(out):
+        lp = out if a.model != "gin" else F.log_softmax(out, dim=1)
+        return F.nll_loss(lp[train], y[train], reduction="sum") / n_train
+
+    def epoch(with_acc: bool):
+        model.train()
+        opt.zero_grad()
+        out = model(x, adj, spmm)
+        loss = loss_fn(out)
+        loss.backward()
+        if world > 1:
+            for p in model.parameters():
+                if p.grad is not None:
+                    dist.all_reduce(p.grad)
+        opt.step()
+        acc = None
+        if with_acc:                                       # gcn-sparse.py:88-90
+            pred = model(x, adj, spmm).max(dim=1)[1]
+            acc = pred[train].eq(y[train]).sum()
+        return loss, acc
+
+    def timed(with_acc, n):
+        for _ in range(a.warmup):
+            epoch(with_acc)
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(n):
+            loss, acc = epoch(with_acc)
+        e1.record()
+        torch.cuda.synchronize()
+        ms = e0.elapsed_time(e1) / n
+        if world > 1:
+            t = torch.tensor([ms], device=dev, dtype=torch.float64)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            ms = float(t.item())
+        return ms, float(loss)
+
+    ms_full, loss = timed(True, a.epochs)
+    ms_train, _ = timed(False, a.epochs)
+    if not a.stock:
+        iSpLibPlugin.unpatch_pyg()
+    if rank == 0:
+        print(json.dumps({"model": a.model, "shape": a.shape, "nodes": g.m, "nnz": g.nnz, "feat": a.feat,
+                          "hidden": a.hidden, "classes": a.classes, "n_gpus": world,
+                          "mode": "stock-torch" if a.stock else "isplib_b200",
+                          "epoch_ms_with_accuracy_forward": round(ms_full, 3),
+                          "epoch_ms_train_only": round(ms_train, 3), "final_loss": round(loss, 5),
+                          "epochs_timed": a.epochs}), flush=True)
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

@@ -24,6 +24,7 @@ def main():
     ap.add_argument("--seg-len", type=int, nargs="+", default=[0])
     ap.add_argument("--scale", type=float, default=1.0)
     ap.add_argument("--json", default=None)
+    ap.add_argument("--bwd", action="store_true", help="also time the backward (A^T SpMM / arg scatter)")
     a = ap.parse_args()
     dev = "cuda:0"
     g = synth.make_graph(a.shape, values=None if a.novalue else "uniform", seed=0, device=dev, scale=a.scale)
@@ -45,6 +46,35 @@ def main():
                         mark = " <== best" if v == best else ""
                         print(f"K={k:4d} {red:4s} seg={i.seg_len:4d} {names[v]:24s} {t:8.3f} ms  {b / t / 1e6:9.1f} GB/s{mark}")
                         results.append(dict(k=k, reduce=red, seg_len=i.seg_len, variant=names[v], ms=t, gbs=b / t / 1e6))
+    if a.bwd:
+        def ev_time(fn, n=5):
+            fn(); torch.cuda.synchronize()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            for _ in range(n):
+                fn()
+            e1.record(); torch.cuda.synchronize()
+            return e0.elapsed_time(e1) / n
+        t_tr = ev_time(lambda: capi.csr_transpose(rp, co, g.n), 2)
+        colptr, row_t, csr2csc = capi.csr_transpose(rp, co, g.n)
+        plan_t = capi.Plan(colptr, g.nnz)
+        vt = capi.permute_values(g.value, csr2csc, row_t, rp, False) if g.value is not None else None
+        print(f"# CSC view build (one-time): {t_tr:.2f} ms")
+        plan = capi.Plan(rp, g.nnz)
+        for k in a.k:
+            go = torch.randn(g.m, k, device=dev)
+            x = torch.randn(g.n, k, device=dev)
+            best, times = capi.spmm_autotune("sum", colptr, row_t, vt, go, plan_t, iters=a.iters)
+            b = synth.algorithmic_bytes(g.n, g.nnz, k, vt is not None, "sum")
+            print(f"K={k:4d} bwd(sum/mean) = A^T SpMM  {names[best]:24s} {times[best]:8.3f} ms  {b / times[best] / 1e6:9.1f} GB/s")
+            results.append(dict(k=k, reduce="bwd_sum", variant=names[best], ms=times[best], gbs=b / times[best] / 1e6))
+            for red in ("max",):
+                _, arg = capi.spmm_csr(red, rp, co, g.value, x, plan)
+                t = ev_time(lambda: capi.spmm_arg_backward(co, g.value, None, arg, go, g.n, True, False))
+                hv = g.value is not None
+                b = 8 * k * g.m + 4 * k * g.m + 4 * k * g.m + (4 * k * g.m if hv else 0) + 8 * k * g.m + 4 * k * g.n
+                print(f"K={k:4d} bwd({red}) arg scatter            {'':24s} {t:8.3f} ms  {b / t / 1e6:9.1f} GB/s")
+                results.append(dict(k=k, reduce="bwd_" + red, variant="arg_backward", ms=t, gbs=b / t / 1e6))
     if a.json:
         with open(a.json, "w") as f:
             json.dump(results, f, indent=1)
