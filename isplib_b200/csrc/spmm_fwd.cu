@@ -115,14 +115,19 @@ template <int OP, int VEC>
 __device__ __forceinline__ void finalize_store(const SpmmParams& p, int row, int deg, int kk,
                                                float (&acc)[VEC], int (&arg)[VEC]) {
     const size_t o = (size_t)row * (size_t)p.ldo + (size_t)kk;
+    // 16-byte stores need an aligned out row and the whole vector inside [0, k); otherwise
+    // (K % 4 != 0: the last vector of a row, or an unaligned out) fall back to scalars
+    const bool vec_ok = (VEC == 1) || (p.vec_store && kk + VEC <= p.k);
+    const int nvalid = min(VEC, p.k - kk);
     if constexpr (OP == OP_SUM) {
         if (p.flags & ISPLIB_FLAG_ACCUMULATE) {
             float prev[VEC];
-            if constexpr (VEC == 4) {
+            if (VEC == 4 && vec_ok) {
                 const float4 t = *reinterpret_cast<const float4*>(p.out + o);
-                prev[0] = t.x; prev[1] = t.y; prev[2] = t.z; prev[3] = t.w;
+                prev[0] = t.x; prev[1 % VEC] = t.y; prev[2 % VEC] = t.z; prev[3 % VEC] = t.w;
             } else {
-                prev[0] = p.out[o];
+#pragma unroll
+                for (int v = 0; v < VEC; ++v) prev[v] = (v < nvalid) ? p.out[o + v] : 0.f;
             }
 #pragma unroll
             for (int v = 0; v < VEC; ++v) acc[v] = prev[v] + acc[v];
@@ -132,7 +137,12 @@ __device__ __forceinline__ void finalize_store(const SpmmParams& p, int row, int
 #pragma unroll
             for (int v = 0; v < VEC; ++v) acc[v] = __fdiv_rn(acc[v], d);
         }
-        store_vec_f<VEC>(p.out + o, acc);
+        if (vec_ok) {
+            store_vec_f<VEC>(p.out + o, acc);
+        } else {
+#pragma unroll
+            for (int v = 0; v < VEC; ++v) if (v < nvalid) __stcs(p.out + o + v, acc[v]);
+        }
     } else {
         long long gid[VEC];
 #pragma unroll
@@ -143,18 +153,26 @@ __device__ __forceinline__ void finalize_store(const SpmmParams& p, int row, int
         if (p.flags & ISPLIB_FLAG_ACCUMULATE) {
 #pragma unroll
             for (int v = 0; v < VEC; ++v) {
-                const float pv = p.out[o + v];
-                const long long pa = p.arg_out[o + v];
-                // previous block wins unless ours is strictly better / equal with smaller id
-                if (!better_lex<OP, long long>(acc[v], gid[v], pv, pa)) { acc[v] = pv; gid[v] = pa; }
+                if (v < nvalid) {
+                    const float pv = p.out[o + v];
+                    const long long pa = p.arg_out[o + v];
+                    // previous block wins unless ours is strictly better / equal with smaller id
+                    if (!better_lex<OP, long long>(acc[v], gid[v], pv, pa)) { acc[v] = pv; gid[v] = pa; }
+                }
             }
         }
         if (p.flags & ISPLIB_FLAG_EMPTY_ZERO) {
 #pragma unroll
             for (int v = 0; v < VEC; ++v) if (gid[v] == p.arg_sentinel) acc[v] = 0.f;
         }
-        store_vec_f<VEC>(p.out + o, acc);
-        store_vec_i64<VEC>(p.arg_out + o, gid);
+        if (vec_ok) {
+            store_vec_f<VEC>(p.out + o, acc);
+            store_vec_i64<VEC>(p.arg_out + o, gid);
+        } else {
+#pragma unroll
+            for (int v = 0; v < VEC; ++v)
+                if (v < nvalid) { __stcs(p.out + o + v, acc[v]); __stcs(p.arg_out + o + v, gid[v]); }
+        }
     }
 }
 
@@ -187,7 +205,9 @@ spmm_seg_kernel(const __grid_constant__ SpmmParams p) {
     const int g = lane / G;
     const int lg = lane % G;
     const int k0 = blockIdx.y * p.tile_w;
-    const int kend = min(p.k, k0 + p.tile_w);
+    // VEC=4 loads may read up to 3 padding floats past K (the launcher checked ldx >= roundup4(K))
+    const int keff = (VEC == 4) ? ((p.k + 3) & ~3) : p.k;
+    const int kend = min(keff, k0 + p.tile_w);
 
     int koff[LPL];
     bool kok[LPL];
@@ -349,7 +369,7 @@ spmm_seg_kernel(const __grid_constant__ SpmmParams p) {
 #pragma unroll
         for (int j = 0; j < LPL; ++j) {
             if (kok[j]) {
-                const size_t o = slot * (size_t)p.k + (size_t)koff[j];
+                const size_t o = slot * (size_t)p.kp + (size_t)koff[j];
                 if constexpr (VEC == 4) {
                     __stcg(reinterpret_cast<float4*>(p.part_val + o), make_float4(acc[j][0], acc[j][1], acc[j][2], acc[j][3]));
                     if constexpr (OP != OP_SUM)
@@ -378,10 +398,10 @@ spmm_seg_kernel(const __grid_constant__ SpmmParams p) {
         int marg[VEC];
 #pragma unroll
         for (int v = 0; v < VEC; ++v) { macc[v] = init_value<OP>(); marg[v] = kNoArg; }
-        const size_t o0 = (size_t)pbase * (size_t)p.k + (size_t)koff[j];
+        const size_t o0 = (size_t)pbase * (size_t)p.kp + (size_t)koff[j];
 #pragma unroll 4
         for (int t = 0; t < nseg; ++t) {
-            const size_t o = o0 + (size_t)t * (size_t)p.k;
+            const size_t o = o0 + (size_t)t * (size_t)p.kp;
             float pv[VEC];
             int pa[VEC];
             if constexpr (VEC == 4) {
@@ -416,8 +436,10 @@ struct TileShape { int vec, g, lpl, tile_w, ntiles; };
 
 static bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15u) == 0; }
 
-static int pick_vec(int64_t k, int64_t ldx, int64_t ldo, const void* x, const void* out) {
-    if (k % 4 == 0 && ldx % 4 == 0 && ldo % 4 == 0 && aligned16(x) && aligned16(out)) return 4;
+// 16-byte gathers need 16-byte aligned x rows that own their padding up to roundup4(K); the
+// OUTPUT side does not matter (stores fall back to scalars per vector, finalize_store)
+static int pick_vec(int64_t k, int64_t ldx, const void* x) {
+    if (ldx % 4 == 0 && ldx >= ((k + 3) & ~(int64_t)3) && aligned16(x)) return 4;
     return 1;
 }
 
@@ -425,6 +447,7 @@ static TileShape pick_shape(int vec, int64_t k, int kt) {
     TileShape t;
     t.vec = vec;
     const int max_tile = vec * 32 * 4;  // G=32, LPL=4
+    if (vec == 4) k = (k + 3) & ~(int64_t)3;
     int64_t tw = (kt <= 0 || kt >= k) ? k : kt;
     if (tw > max_tile) tw = max_tile;
     if (vec == 4) tw = (tw + 3) / 4 * 4;
@@ -473,7 +496,8 @@ bool spmm_variant_supported(int variant, int reduce, int64_t k, int64_t ldx, int
                             const void* x, const void* out) {
     const VariantDesc* d = variant_desc(variant);
     if (!d || reduce < 0 || reduce > 3 || k <= 0) return false;
-    const int vec = pick_vec(k, ldx, ldo, x, out);
+    (void)ldo; (void)out;
+    const int vec = pick_vec(k, ldx, x);
     if (d->kt > 0) {
         if (d->kt >= k) return false;            // same as kfull: do not time it twice
         if (vec == 4 && d->kt % 4 != 0) return false;
@@ -515,13 +539,16 @@ int launch_spmm(int reduce, const SpmmParams& base, int64_t nnz, int variant, cu
     if (base.m == 0 || base.k == 0) return ISPLIB_SUCCESS;
 
     SpmmParams p = base;
-    const int vec = pick_vec(p.k, p.ldx, p.ldo, p.x, p.out);
+    const int vec = pick_vec(p.k, p.ldx, p.x);
     const TileShape t = pick_shape(vec, p.k, d->kt);
+    const int keff = vec == 4 ? ((p.k + 3) & ~3) : p.k;
+    p.kp = (p.k + 3) & ~3;
+    p.vec_store = (p.k % 4 == 0 && p.ldo % 4 == 0 && aligned16(p.out) && (!p.arg_out || aligned16(p.arg_out))) ? 1 : 0;
     p.tile_w = t.tile_w;
     const int op = (reduce == ISPLIB_REDUCE_MAX) ? OP_MAX : (reduce == ISPLIB_REDUCE_MIN ? OP_MIN : OP_SUM);
 
     // every tile (incl. the last one) fills all G*LPL vector slots of a lane group?
-    const bool partial = (t.tile_w != t.g * t.lpl * t.vec) || (p.k % t.tile_w != 0);
+    const bool partial = (t.tile_w != t.g * t.lpl * t.vec) || (keff % t.tile_w != 0);
     SegKernel kern = nullptr;
     if (op == OP_SUM) kern = pick_kernel<OP_SUM>(t, d->unroll, partial);
     else if (op == OP_MAX) kern = pick_kernel<OP_MAX>(t, d->unroll, partial);

@@ -223,6 +223,17 @@ std::tuple<Tensor, c10::optional<Tensor>> spmm_fw(CsrView& g, const c10::optiona
     TORCH_CHECK(mat_in.get_device() == g.rowptr32.get_device(), "isplib_b200: `mat` and the graph are on different devices");
     Tensor mat = mat_in.contiguous();  // csrc/fusedmm.cpp:140
     const int64_t M = g.m, N = mat.size(0), K = mat.size(1);
+    int64_t ldx = K;
+    if (K % 4 != 0 && K > 4 && env_int("ISPLIB_B200_PAD_K", 1)) {
+        // feature widths like 47 or 602: give every row 16-byte alignment and its own padding
+        // so the kernel can gather with 16-byte loads (the reference pads features to multiples
+        // of 16 for its SIMD kernels, tests/cpu/dataset_loader.py:145-160); out stays [M, K]
+        const int64_t Kp = (K + 3) / 4 * 4;
+        Tensor padded = torch::zeros({N, Kp}, mat.options());
+        padded.narrow(1, 0, K).copy_(mat);
+        mat = padded;
+        ldx = Kp;
+    }
     const float* val_ptr = nullptr;
     Tensor val;
     if (value.has_value()) {
@@ -258,14 +269,14 @@ std::tuple<Tensor, c10::optional<Tensor>> spmm_fw(CsrView& g, const c10::optiona
             int best = 0;
             ISPLIB_CHECK_STATUS(isplib_b200_spmm_autotune(
                 reduction, M, N, K, g.nnz, g.rowptr32.data_ptr<int32_t>(), g.col32.data_ptr<int32_t>(), val_ptr,
-                mat.data_ptr<float>(), K, out.data_ptr<float>(), K, arg_ptr, &g.info, g.plan_ptr(), wst.data_ptr(), ws,
+                mat.data_ptr<float>(), ldx, out.data_ptr<float>(), K, arg_ptr, &g.info, g.plan_ptr(), wst.data_ptr(), ws,
                 env_int("ISPLIB_B200_AUTOTUNE_ITERS", 3), &best, nullptr, stream.stream()));
             g.tuned[tkey] = best;
             variant = best;
         }
     }
     ISPLIB_CHECK_STATUS(isplib_b200_spmm_csr(reduction, M, N, K, g.nnz, g.rowptr32.data_ptr<int32_t>(),
-                                             g.col32.data_ptr<int32_t>(), val_ptr, mat.data_ptr<float>(), K,
+                                             g.col32.data_ptr<int32_t>(), val_ptr, mat.data_ptr<float>(), ldx,
                                              out.data_ptr<float>(), K, arg_ptr, &g.info, g.plan_ptr(),
                                              wst.data_ptr(), ws, variant, stream.stream()));
     return std::make_tuple(out, arg_out);

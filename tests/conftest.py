@@ -82,3 +82,13 @@ def assert_sum_close(actual, desired, cond=None):
     bad = err > ATOL + RTOL * scale
     assert not bad.any(), (f"{int(bad.sum())} / {bad.size} elements out of tolerance; "
                            f"max err {err.max():.3e}, worst ratio {(err / (ATOL + RTOL * scale)).max():.2f}")
+
+
+def grad_cond(oracle, rowptr, col, val, grad_out, N, mean=False):
+    """abs_product_sum for the sum/mean BACKWARD (A^T with the backward's weights)."""
+    colptr, csr2csc, row_t = oracle.build_csc(rowptr, col, N)
+    w = np.ones(col.shape[0], np.float32) if val is None else np.asarray(val, np.float32)
+    w = w[csr2csc]
+    if mean:
+        w = w / np.maximum(np.diff(rowptr), 1)[row_t]
+    return abs_product_sum(colptr, row_t, w, grad_out)

@@ -39,21 +39,21 @@ for name in names:
     x = mat.clone().requires_grad_(True)
     o = ops.fusedmm_spmm(row, rowptr, col, value, colptr, csr2csc, x, value[csr2csc], row[csr2csc])
     o.backward(go)
-    ok["sum_out"] = bool(np.allclose(o.detach().numpy(), z["sum_out"], rtol=1e-5, atol=1e-6))
-    ok["sum_grad"] = bool(np.allclose(x.grad.numpy(), z["sum_grad_mat"], rtol=1e-5, atol=1e-6))
+    ok["sum_out"] = bool(np.allclose(o.detach().numpy(), z["sum_out"], rtol=1e-4, atol=1e-5))
+    ok["sum_grad"] = bool(np.allclose(x.grad.numpy(), z["sum_grad_mat"], rtol=1e-4, atol=1e-5))
     x = mat.clone().requires_grad_(True)
     w = value[csr2csc] / rowcount[row][csr2csc].float().clamp(min=1)
     o = ops.fusedmm_spmm_mean(row, rowptr, col, value, rowcount, colptr, csr2csc, x, row[csr2csc], w)
     o.backward(go)
-    ok["mean_out"] = bool(np.allclose(o.detach().numpy(), z["mean_out"], rtol=1e-5, atol=1e-6))
-    ok["mean_grad"] = bool(np.allclose(x.grad.numpy(), z["mean_grad_mat"], rtol=1e-5, atol=1e-6))
+    ok["mean_out"] = bool(np.allclose(o.detach().numpy(), z["mean_out"], rtol=1e-4, atol=1e-5))
+    ok["mean_grad"] = bool(np.allclose(x.grad.numpy(), z["mean_grad_mat"], rtol=1e-4, atol=1e-5))
     for red, fn in (("max", ops.fusedmm_spmm_max), ("min", ops.fusedmm_spmm_min)):
         x = mat.clone().requires_grad_(True)
         o, arg = fn(rowptr, col, value, x)
         o.backward(go)
         ok[red + "_out"] = bool(np.array_equal(o.detach().numpy(), z[red + "_out"]))
         ok[red + "_arg"] = bool(np.array_equal(arg.numpy(), z[red + "_arg"]))
-        ok[red + "_grad"] = bool(np.allclose(x.grad.numpy(), z[red + "_grad_mat"], rtol=1e-5, atol=1e-6))
+        ok[red + "_grad"] = bool(np.allclose(x.grad.numpy(), z[red + "_grad_mat"], rtol=1e-4, atol=1e-5))
     res[name] = ok
 print("RESULT " + json.dumps(res))
 '''

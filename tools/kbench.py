@@ -37,7 +37,8 @@ def main():
         print(f"# {a.shape} m={g.m} nnz={g.nnz} maxdeg={g.max_degree} seg_len={i.seg_len} items={i.num_items} "
               f"split_rows={i.num_split_rows} split_items={i.num_split_items}")
         for k in a.k:
-            x = torch.randn(g.n, k, device=dev)
+            kp = (k + 3) // 4 * 4                      # rows padded like the op layer does for odd K
+            x = torch.randn(g.n, kp, device=dev)[:, :k]
             for red in a.reduce:
                 best, times = capi.spmm_autotune(red, rp, co, g.value, x, plan, iters=a.iters)
                 b = synth.algorithmic_bytes(g.m, g.nnz, k, g.value is not None, red)
