@@ -11,31 +11,50 @@
 
 namespace isplib {
 
-// One thread per (row, feature).  arg / grad_out are read coalesced along the feature
-// axis; the scatter target row differs per element (that is the operation), so the
-// adds are fp32 RED atomics into L2.  HBM-bound: 8+4 bytes read, one 4-byte RMW, plus
-// the dependent 4-byte col (and val) gathers per element.
+// arg / grad_out are read coalesced along the feature axis (4 features per thread as 2x16 B
+// + 16 B when the rows allow it); the scatter target row differs per element (that is the
+// operation), so the adds are fp32 RED atomics into L2.  All dependent gathers of a thread's
+// 4 elements (col[e], val[e], x[col[e]]) are issued together before the first atomic.
+template <int V>
 __global__ void __launch_bounds__(256)
 arg_backward_kernel(long long m, int k, const int32_t* __restrict__ col,
                     const float* __restrict__ val, const float* __restrict__ x, long long ldx,
                     const long long* __restrict__ arg, long long ld_arg, long long sentinel,
                     const float* __restrict__ grad_out, long long ldgo,
                     float* __restrict__ grad_x, long long ldgx, float* __restrict__ grad_val) {
-    const long long total = m * (long long)k;
+    const int kv = (k + V - 1) / V;                       // V-wide groups per row
+    const long long total = m * (long long)kv;
     for (long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x; t < total;
          t += (long long)gridDim.x * blockDim.x) {
-        const long long i = t / k;
-        const int kk = (int)(t - i * k);
-        const long long e = __ldcs(arg + i * ld_arg + kk);
-        if (e == sentinel) continue;
-        const float g = __ldcs(grad_out + i * ldgo + kk);
-        const int c = __ldg(col + e);
-        if (grad_x) {
-            const float v = val ? __fmul_rn(__ldg(val + e), g) : g;
-            atomicAdd(grad_x + (long long)c * ldgx + kk, v);
+        const long long i = t / kv;
+        const int kk = (int)(t - i * kv) * V;
+        long long e[V];
+        float g[V];
+        if constexpr (V == 4) {
+            const longlong2 a0 = __ldcs(reinterpret_cast<const longlong2*>(arg + i * ld_arg + kk));
+            const longlong2 a1 = __ldcs(reinterpret_cast<const longlong2*>(arg + i * ld_arg + kk) + 1);
+            const float4 gg = __ldcs(reinterpret_cast<const float4*>(grad_out + i * ldgo + kk));
+            e[0] = a0.x; e[1] = a0.y; e[2] = a1.x; e[3] = a1.y;
+            g[0] = gg.x; g[1] = gg.y; g[2] = gg.z; g[3] = gg.w;
+        } else {
+            e[0] = __ldcs(arg + i * ld_arg + kk);
+            g[0] = __ldcs(grad_out + i * ldgo + kk);
         }
-        if (grad_val) {
-            atomicAdd(grad_val + e, __fmul_rn(__ldg(x + (long long)c * ldx + kk), g));
+        int c[V];
+        float a[V];
+        bool ok[V];
+#pragma unroll
+        for (int v = 0; v < V; ++v) {
+            ok[v] = (e[v] != sentinel);
+            c[v] = ok[v] ? __ldg(col + e[v]) : 0;
+        }
+#pragma unroll
+        for (int v = 0; v < V; ++v) a[v] = (val && ok[v]) ? __ldg(val + e[v]) : 1.f;
+#pragma unroll
+        for (int v = 0; v < V; ++v) {
+            if (!ok[v]) continue;
+            if (grad_x) atomicAdd(grad_x + (long long)c[v] * ldgx + kk + v, val ? __fmul_rn(a[v], g[v]) : g[v]);
+            if (grad_val) atomicAdd(grad_val + e[v], __fmul_rn(__ldg(x + (long long)c[v] * ldx + kk + v), g[v]));
         }
     }
 }
@@ -68,13 +87,20 @@ extern "C" int isplib_b200_spmm_arg_backward(int64_t m, int64_t n, int64_t k, in
         if (grad_val && nnz > 0) ISPLIB_CUDA_TRY(cudaMemsetAsync(grad_val, 0, (size_t)nnz * 4, stream));
     }
     if (m == 0 || k == 0 || nnz == 0) return ISPLIB_SUCCESS;
-    const long long total = (long long)m * k;
+    const bool v4 = (k % 4 == 0) && (ld_arg % 2 == 0) && (ldgo % 4 == 0) &&
+                    ((reinterpret_cast<uintptr_t>(arg) & 15u) == 0) && ((reinterpret_cast<uintptr_t>(grad_out) & 15u) == 0);
+    const long long total = (long long)m * (v4 ? k / 4 : k);
     long long blocks = (total + 255) / 256;
-    const long long cap = (long long)kNumSMs * 8 * 16;  // grid-stride beyond 16 waves of 8 CTAs/SM
+    const long long cap = (long long)kNumSMs * 8 * 32;  // grid-stride beyond 32 waves of 8 CTAs/SM
     if (blocks > cap) blocks = cap;
-    arg_backward_kernel<<<(unsigned)blocks, 256, 0, stream>>>(
-        (long long)m, (int)k, col, val, x, (long long)ldx, (const long long*)arg, (long long)ld_arg,
-        (long long)arg_sentinel, grad_out, (long long)ldgo, grad_x, (long long)ldgx, grad_val);
+    if (v4)
+        arg_backward_kernel<4><<<(unsigned)blocks, 256, 0, stream>>>(
+            (long long)m, (int)k, col, val, x, (long long)ldx, (const long long*)arg, (long long)ld_arg,
+            (long long)arg_sentinel, grad_out, (long long)ldgo, grad_x, (long long)ldgx, grad_val);
+    else
+        arg_backward_kernel<1><<<(unsigned)blocks, 256, 0, stream>>>(
+            (long long)m, (int)k, col, val, x, (long long)ldx, (const long long*)arg, (long long)ld_arg,
+            (long long)arg_sentinel, grad_out, (long long)ldgo, grad_x, (long long)ldgx, grad_val);
     ISPLIB_LAUNCH_CHECK();
     return ISPLIB_SUCCESS;
 }

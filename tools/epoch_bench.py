@@ -122,10 +122,12 @@ def main():
         e1.record()
         torch.cuda.synchronize()
         ms = e0.elapsed_time(e1) / n
+        loss = loss.detach().clone()
         if world > 1:
             t = torch.tensor([ms], device=dev, dtype=torch.float64)
             dist.all_reduce(t, op=dist.ReduceOp.MAX)
             ms = float(t.item())
+            dist.all_reduce(loss)        # local partial sums / global count -> global mean
         return ms, float(loss)
 
     ms_full, loss = timed(True, a.epochs)
