@@ -46,6 +46,7 @@ def parse_args():
     ap.add_argument("--reduce", default=REDUCE)
     ap.add_argument("--variant", type=int, default=None, help="force a kernel variant (default: on-device autotune)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-gcn", action="store_true", help="skip the secondary GCN-epoch measurement")
     ap.add_argument("--cpu-seconds", type=float, default=12.0, help="budget for the cpu_baseline leg")
     return ap.parse_args()
 
@@ -248,6 +249,7 @@ def run_ours(args):
     K, reduce = args.k, args.reduce
     g = synth.make_graph(args.shape, values="uniform", seed=0, device=dev)   # same graph on every rank
     M, N, nnz = g.m, g.n, g.nnz
+    g_max_degree, g_gini = g.max_degree, g.gini
     b_alg = synth.algorithmic_bytes(M, nnz, K, True, reduce)
     gen = torch.Generator(device=dev).manual_seed(0)
     xs = [torch.randn(N, K, device=dev, generator=gen) for _ in range(2)]   # rotated so X is never warm in L2
@@ -396,6 +398,20 @@ def run_ours(args):
                        "on the device (uploaded once per graph, as the plugin caches per graph)"}
         del adj
 
+    # --- secondary: the other half of BASELINE.json's metric, a 2-layer GCN training epoch
+    # (hidden 256) on the ogbn-products-shaped graph via patch_pyg(), same N GPUs ---------------
+    gcn = None
+    if not args.no_gcn:
+        try:
+            torch.cuda.empty_cache()
+            import types
+            sys.path.insert(0, os.path.join(ROOT, "tools"))
+            import epoch_bench
+            gcn = epoch_bench.run(types.SimpleNamespace(model="gcn", shape="products", feat=100, hidden=256, classes=47,
+                                                        epochs=3, warmup=2, scale=1.0, stock=False), init_dist=False)
+        except Exception as ex:   # never lose the headline number to the secondary one
+            gcn = {"error": repr(ex)[:200]}
+
     if rank != 0:
         if world > 1:
             dist.barrier()
@@ -417,8 +433,8 @@ def run_ours(args):
         "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
         "config": {"workload": f"{args.shape}-shape SpMM-{reduce} K={K} fp32, int32 CSR, {M} nodes, {nnz} nnz "
                                f"(synthetic log-normal degrees, uniform columns, seed 0)",
-                   "reduce": reduce, "K": K, "variant": variant_name, "max_degree": g.max_degree,
-                   "degree_gini": round(g.gini, 3),
+                   "reduce": reduce, "K": K, "variant": variant_name, "max_degree": g_max_degree,
+                   "degree_gini": round(g_gini, 3),
                    "l2": "inputs 1.04 GB (col+val+X) > 126 MB L2 and two X buffers rotated between steps; no flush",
                    "parallelism": "single GPU" if world == 1 else f"1-D row partition x{world}, X all-gathered per step "
                                                                    f"over NCCL with local-block overlap"},
@@ -431,6 +447,8 @@ def run_ours(args):
         line["autotune_ms"] = tune
     if e2e is not None:
         line["e2e"] = e2e
+    if gcn is not None:
+        line["gcn_epoch"] = gcn
     if world == 1 and not args.no_cpu_baseline:
         try:
             line["cpu_baseline"] = cpu_baseline_leg(args, args.cpu_seconds)

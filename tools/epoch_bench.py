@@ -21,25 +21,15 @@ import torch.distributed as dist  # noqa: E402
 import torch.nn.functional as F  # noqa: E402
 
 
-def main():
-    ap = argparse.ArgumentParser()
-    ap.add_argument("--model", default="gcn", choices=["gcn", "sage-mean", "sage-sum", "gin"])
-    ap.add_argument("--shape", default="products")
-    ap.add_argument("--feat", type=int, default=100)
-    ap.add_argument("--hidden", type=int, default=256)
-    ap.add_argument("--classes", type=int, default=47)
-    ap.add_argument("--epochs", type=int, default=5)
-    ap.add_argument("--warmup", type=int, default=2)
-    ap.add_argument("--scale", type=float, default=1.0)
-    ap.add_argument("--stock", action="store_true", help="do not patch: stock torch-op matmul (the 'pt1' mode)")
-    a = ap.parse_args()
-
+def run(a, init_dist=True):
+    """a: namespace with model, shape, feat, hidden, classes, epochs, warmup, scale, stock.
+    Returns the result dict on rank 0 (None elsewhere)."""
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
     lrank = int(os.environ.get("LOCAL_RANK", "0"))
     torch.cuda.set_device(lrank)
     dev = torch.device("cuda", lrank)
-    if world > 1:
+    if world > 1 and init_dist and not dist.is_initialized():
         dist.init_process_group("nccl", device_id=dev)
     import isplib_b200  # noqa: F401
     from isplib import iSpLibPlugin
@@ -134,14 +124,33 @@ def main():
     ms_train, _ = timed(False, a.epochs)
     if not a.stock:
         iSpLibPlugin.unpatch_pyg()
+    res = None
     if rank == 0:
-        print(json.dumps({"model": a.model, "shape": a.shape, "nodes": g.m, "nnz": g.nnz, "feat": a.feat,
-                          "hidden": a.hidden, "classes": a.classes, "n_gpus": world,
-                          "mode": "stock-torch" if a.stock else "isplib_b200",
-                          "epoch_ms_with_accuracy_forward": round(ms_full, 3),
-                          "epoch_ms_train_only": round(ms_train, 3), "final_loss": round(loss, 5),
-                          "epochs_timed": a.epochs}), flush=True)
-    if world > 1:
+        res = {"model": a.model, "shape": a.shape, "nodes": g.m, "nnz": g.nnz, "feat": a.feat,
+               "hidden": a.hidden, "classes": a.classes, "n_gpus": world,
+               "mode": "stock-torch" if a.stock else "isplib_b200",
+               "epoch_ms_with_accuracy_forward": round(ms_full, 3),
+               "epoch_ms_train_only": round(ms_train, 3), "final_loss": round(loss, 5),
+               "epochs_timed": a.epochs}
+    return res
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--model", default="gcn", choices=["gcn", "sage-mean", "sage-sum", "gin"])
+    ap.add_argument("--shape", default="products")
+    ap.add_argument("--feat", type=int, default=100)
+    ap.add_argument("--hidden", type=int, default=256)
+    ap.add_argument("--classes", type=int, default=47)
+    ap.add_argument("--epochs", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=2)
+    ap.add_argument("--scale", type=float, default=1.0)
+    ap.add_argument("--stock", action="store_true", help="do not patch: stock torch-op matmul (the 'pt1' mode)")
+    a = ap.parse_args()
+    res = run(a)
+    if res is not None:
+        print(json.dumps(res), flush=True)
+    if dist.is_initialized():
         dist.barrier()
         dist.destroy_process_group()
 
