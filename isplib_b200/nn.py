@@ -25,16 +25,27 @@ def _matmul(adj_t, x, reduce):
 
 
 class GCNConv(nn.Module):
-    """out = A @ (x W) + b   (PyG GCNConv with normalize=False: linear first, then propagate)."""
+    """out = A @ (x W) + b  (PyG GCNConv with normalize=False propagates AFTER the linear
+    layer, at width out_channels).
 
-    def __init__(self, in_channels: int, out_channels: int, bias: bool = True):
+    ``order``: 'linear_first' is PyG's order; 'aggregate_first' computes (A @ x) W, which is
+    the same function but runs the SpMM at width in_channels and -- when x does not require
+    grad, i.e. in the first layer -- needs no backward SpMM at all; 'auto' (default) picks
+    aggregate_first iff in_channels < out_channels."""
+
+    def __init__(self, in_channels: int, out_channels: int, bias: bool = True, order: str = "auto"):
         super().__init__()
+        assert order in ("auto", "linear_first", "aggregate_first")
         self.lin = nn.Linear(in_channels, out_channels, bias=False)
         self.bias = nn.Parameter(torch.zeros(out_channels)) if bias else None
+        self.aggregate_first = (order == "aggregate_first") or (order == "auto" and in_channels < out_channels)
 
     def forward(self, x, adj_t, spmm: Optional[Callable] = None):
-        x = self.lin(x)
-        out = spmm(x, "sum") if spmm is not None else _matmul(adj_t, x, "sum")
+        agg = (lambda t: spmm(t, "sum")) if spmm is not None else (lambda t: _matmul(adj_t, t, "sum"))
+        if self.aggregate_first:
+            out = self.lin(agg(x))
+        else:
+            out = agg(self.lin(x))
         return out if self.bias is None else out + self.bias
 
 
@@ -72,10 +83,10 @@ class GINConv(nn.Module):
 
 
 class GCN(nn.Module):
-    def __init__(self, in_channels, hidden, num_classes, dropout: float = 0.5):
+    def __init__(self, in_channels, hidden, num_classes, dropout: float = 0.5, order: str = "auto"):
         super().__init__()
-        self.conv1 = GCNConv(in_channels, hidden)
-        self.conv2 = GCNConv(hidden, num_classes)
+        self.conv1 = GCNConv(in_channels, hidden, order=order)
+        self.conv2 = GCNConv(hidden, num_classes, order=order)
         self.dropout = dropout
 
     def forward(self, x, adj_t, spmm=None):

@@ -130,3 +130,20 @@ def test_synth_generators():
     assert small.m == 233 and abs(small.nnz - 114_616) <= 1
     b = synth.algorithmic_bytes(232_965, 114_615_892, 128, True)
     assert abs(b / 1e9 - 59.72) < 0.01
+
+
+def test_gcn_layer_orders_are_the_same_function():
+    """(A x) W == A (x W): the aggregate-first order of isplib_b200.nn.GCNConv is PyG's
+    GCNConv up to fp32 reassociation (stock CPU matmul, plugin not active)."""
+    import isplib_b200  # noqa: F401
+    from isplib_b200 import nn as gnn, synth
+    torch.manual_seed(0)
+    g = synth.make_graph(300, 4000, values="gcn", seed=2)
+    adj = g.sparse_tensor()
+    x = torch.randn(g.n, 12)
+    a = gnn.GCNConv(12, 20, order="linear_first")
+    b = gnn.GCNConv(12, 20, order="aggregate_first")
+    b.load_state_dict(a.state_dict())
+    assert not a.aggregate_first and b.aggregate_first and gnn.GCNConv(12, 20).aggregate_first
+    assert not gnn.GCNConv(20, 12).aggregate_first
+    torch.testing.assert_close(a(x, adj), b(x, adj), rtol=1e-4, atol=1e-5)

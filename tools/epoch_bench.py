@@ -46,7 +46,7 @@ def run(a, init_dist=True):
     train_all = torch.rand(N, device=dev, generator=gen) < 0.5
 
     if a.model == "gcn":
-        model = gnn.GCN(a.feat, a.hidden, a.classes)
+        model = gnn.GCN(a.feat, a.hidden, a.classes, order=getattr(a, "order", "linear_first"))
     elif a.model.startswith("sage"):
         model = gnn.GraphSAGE(a.feat, a.hidden, a.classes, aggr=a.model.split("-")[1])
     else:
@@ -128,7 +128,7 @@ def run(a, init_dist=True):
     if rank == 0:
         res = {"model": a.model, "shape": a.shape, "nodes": g.m, "nnz": g.nnz, "feat": a.feat,
                "hidden": a.hidden, "classes": a.classes, "n_gpus": world,
-               "mode": "stock-torch" if a.stock else "isplib_b200",
+               "mode": "stock-torch" if a.stock else "isplib_b200", "gcn_order": getattr(a, "order", "linear_first"),
                "epoch_ms_with_accuracy_forward": round(ms_full, 3),
                "epoch_ms_train_only": round(ms_train, 3), "final_loss": round(loss, 5),
                "epochs_timed": a.epochs}
@@ -146,6 +146,8 @@ def main():
     ap.add_argument("--warmup", type=int, default=2)
     ap.add_argument("--scale", type=float, default=1.0)
     ap.add_argument("--stock", action="store_true", help="do not patch: stock torch-op matmul (the 'pt1' mode)")
+    ap.add_argument("--order", default="linear_first", choices=["linear_first", "aggregate_first", "auto"],
+                    help="GCN only: PyG's order (linear then propagate) or the cheaper equivalent")
     a = ap.parse_args()
     res = run(a)
     if res is not None:
