@@ -183,6 +183,19 @@ int isplib_b200_spmm_arg_backward(int64_t m, int64_t n, int64_t k, int64_t nnz,
                                   float* grad_x, int64_t ldgx, float* grad_val,
                                   int zero_init, isplib_stream_t stream);
 
+/* Gradient w.r.t. the stored values of the sum / mean SpMM (SDDMM on the CSR pattern):
+ *     out_val[e] = < a[row(e),:], x[col[e],:] >   (mean_scale != 0: / max(deg(row(e)),1))
+ * with a = grad_out.  The reference never computes it (csrc/fusedmm.cpp:268-272,349-353
+ * return an undefined gradient) though its header has the ROP_DOT stage (csrc/fusedMM.h:34);
+ * provided as the next op on the same access pattern.  Uses the
+ * forward plan of the same graph.  a: [m,k] stride lda, x: [n,k] stride ldx.             */
+int isplib_b200_sddmm_csr(int64_t m, int64_t n, int64_t k, int64_t nnz,
+                          const int32_t* rowptr, const int32_t* col,
+                          const float* a, int64_t lda, const float* x, int64_t ldx,
+                          int mean_scale, float* out_val,
+                          const isplib_b200_plan_info* info, const void* plan_dev,
+                          isplib_stream_t stream);
+
 /* ---- index helpers ------------------------------------------------------------- */
 /* int64 -> int32 narrowing of rowptr/col as the ops receive them
  * (csrc/fusedmm.cpp:128-129 reads int64).  *overflow_flag_dev (device int, may be

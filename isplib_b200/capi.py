@@ -32,7 +32,7 @@ EXPORTS = [
     "isplib_b200_variant_default", "isplib_b200_spmm_autotune",
     "isplib_b200_csr_transpose_workspace_bytes", "isplib_b200_csr_transpose",
     "isplib_b200_permute_values", "isplib_b200_spmm_arg_backward",
-    "isplib_b200_narrow_i64_to_i32", "isplib_b200_fusedmm_csr_host",
+    "isplib_b200_narrow_i64_to_i32", "isplib_b200_fusedmm_csr_host", "isplib_b200_sddmm_csr",
 ]
 
 
@@ -82,6 +82,7 @@ def lib() -> ctypes.CDLL:
     L.isplib_b200_spmm_arg_backward.argtypes = [i64, i64, i64, i64, p, p, p, i64, p, i64, i64, p, i64,
                                                 p, i64, p, ctypes.c_int, p]
     L.isplib_b200_narrow_i64_to_i32.argtypes = [i64, p, p, p, p]
+    L.isplib_b200_sddmm_csr.argtypes = [i64, i64, i64, i64, p, p, p, i64, p, i64, ctypes.c_int, p, pinfo, p, p]
     L.isplib_b200_fusedmm_csr_host.argtypes = [i32, i64, i64, i64, f32, i64, i64, i64, p, p, p, p, p, i64,
                                                p, i64, f32, p, i64, p]
     for name in EXPORTS:
@@ -245,3 +246,16 @@ def narrow_i64_to_i32(src: torch.Tensor) -> torch.Tensor:
     if int(flag.item()) != 0:
         raise IsplibError(256, "narrow_i64_to_i32 (value out of int32 range)")
     return dst
+
+
+def sddmm_csr(rowptr32, col32, a, x, plan: Plan, mean_scale: bool = False) -> torch.Tensor:
+    """out_val[e] = <a[row(e)], x[col[e]]> (/ max(deg,1)) -- isplib_b200_sddmm_csr."""
+    assert a.is_cuda and x.is_cuda and a.dtype == torch.float32 and x.dtype == torch.float32
+    assert a.stride(1) == 1 and x.stride(1) == 1 and a.shape[1] == x.shape[1]
+    M, K = a.shape
+    N = x.shape[0]
+    out = torch.empty(plan.nnz, dtype=torch.float32, device=x.device)
+    check(lib().isplib_b200_sddmm_csr(M, N, K, plan.nnz, _p(rowptr32), _p(col32), _p(a), max(a.stride(0), K), _p(x),
+                                      max(x.stride(0), K), 1 if mean_scale else 0, _p(out), ctypes.byref(plan.info),
+                                      plan.ptr, _stream(x.device)), "sddmm_csr")
+    return out

@@ -1,0 +1,188 @@
+// sddmm.cu -- sampled dense-dense product on the CSR pattern, sm_100a:
+//     out_val[e] = < a[row(e), :], x[col[e], :] >      (optionally / max(deg(row(e)), 1))
+//
+// This is d(loss)/d(value[e]) of the sum (resp. mean) SpMM with a = grad_out.  The reference
+// leaves that gradient undefined (/root/reference/csrc/fusedmm.cpp:268-272, :349-353) although
+// its message header already has the ROP_DOT stage for it (csrc/fusedMM.h:34); SURVEY.md
+// section 8f ranks it as the next op after the hot path.  Same access pattern and roofline as
+// the forward SpMM: one K-row gather of x per stored entry.
+//
+// One warp owns one plan segment (same plan as the forward).  The a-row lives in registers;
+// x rows are gathered exactly like in spmm_seg_kernel (coalesced index chunk, shuffles,
+// 16-byte loads, U gathers in flight).  Each lane accumulates, for every entry of the chunk
+// that its lane group handles, the partial dot product over its own K slice; a halving
+// butterfly (G-1 shuffles per group for G entries, i.e. ~1 shuffle per entry) then leaves
+// lane (group g, lane lg) with the full dot product of entry lg*NG+g, which is stored
+// coalesced.  Deterministic: fixed reduction tree, no atomics.
+#include "common.cuh"
+
+namespace isplib {
+
+struct SddmmParams {
+    const int32_t* __restrict__ rowptr;
+    const int32_t* __restrict__ col;
+    const float* __restrict__ a;      // [m, k]
+    const float* __restrict__ x;      // [n, k]
+    float* __restrict__ out;          // [nnz]
+    const int32_t* __restrict__ seg_off;
+    const int32_t* __restrict__ item_row;
+    long long lda, ldx;
+    int k, num_items, seg_len, mean_scale;
+};
+
+template <int VEC>
+__device__ __forceinline__ void ld_vec(const float* __restrict__ p, float (&v)[VEC]) {
+    if constexpr (VEC == 4) {
+        const float4 t = __ldg(reinterpret_cast<const float4*>(p));
+        v[0] = t.x; v[1] = t.y; v[2] = t.z; v[3] = t.w;
+    } else {
+        v[0] = __ldg(p);
+    }
+}
+
+// G lanes per entry, 32/G entries per step; each lane covers LPL vectors of VEC floats per pass
+template <int VEC, int G, int LPL>
+__global__ void __launch_bounds__(128)
+sddmm_seg_kernel(const __grid_constant__ SddmmParams p) {
+    constexpr int NG = 32 / G;
+    constexpr int P = G;                 // entries per lane group per 32-entry chunk
+    constexpr int U = (P >= 4) ? 4 : P;  // gathers in flight
+    constexpr int PASS_W = G * LPL * VEC;
+    constexpr unsigned FULL = 0xffffffffu;
+
+    const int lane = threadIdx.x & 31;
+    const int item = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    if (item >= p.num_items) return;
+    const int row = __ldg(p.item_row + item);
+    const int s = item - __ldg(p.seg_off + row);
+    const int rb = __ldg(p.rowptr + row), re = __ldg(p.rowptr + row + 1);
+    const int eb = rb + s * p.seg_len;
+    const int ee = min(re, eb + p.seg_len);
+    if (eb >= ee) return;
+    const int g = lane / G, lg = lane % G;
+    const float inv = p.mean_scale ? __fdiv_rn(1.f, (float)max(re - rb, 1)) : 1.f;
+    const unsigned ldxb = (unsigned)p.ldx * 4u;
+    const int keff = (VEC == 4) ? ((p.k + 3) & ~3) : p.k;
+    const float* arow = p.a + (size_t)row * (size_t)p.lda;
+
+    for (int e0 = eb; e0 < ee; e0 += 32) {
+        const int cnt = min(32, ee - e0);
+        const unsigned c = (lane < cnt) ? (unsigned)__ldcs(p.col + e0 + lane) : 0u;
+        float part[P];
+#pragma unroll
+        for (int v = 0; v < P; ++v) part[v] = 0.f;
+
+        for (int kp = 0; kp < keff; kp += PASS_W) {
+            // this lane's slice of the a-row for this pass (zero outside K: a's padding is not ours)
+            float av[LPL][VEC];
+            int ko[LPL];
+            bool ok[LPL];
+#pragma unroll
+            for (int j = 0; j < LPL; ++j) {
+                ko[j] = kp + (lg + j * G) * VEC;
+                ok[j] = ko[j] < keff;
+#pragma unroll
+                for (int q = 0; q < VEC; ++q) av[j][q] = 0.f;
+                if (ok[j]) {
+                    if (VEC == 1 || ko[j] + VEC <= p.k) ld_vec<VEC>(arow + ko[j], av[j]);
+                    else {
+#pragma unroll
+                        for (int q = 0; q < VEC; ++q) if (ko[j] + q < p.k) av[j][q] = __ldg(arow + ko[j] + q);
+                    }
+                }
+            }
+#pragma unroll
+            for (int v0 = 0; v0 < P; v0 += U) {
+                float xv[U][LPL][VEC];
+#pragma unroll
+                for (int u = 0; u < U; ++u) {
+                    const int idx = (v0 + u) * NG + g;            // entry of the chunk this group handles
+                    const unsigned cc = __shfl_sync(FULL, c, idx);
+                    const char* xr = reinterpret_cast<const char*>(p.x) + (unsigned long long)cc * ldxb;
+#pragma unroll
+                    for (int j = 0; j < LPL; ++j) {
+                        // out-of-range lanes re-read the row's first vector (valid memory, product with 0)
+                        const int off = ok[j] ? ko[j] : 0;
+                        if (idx < cnt) {
+                            ld_vec<VEC>(reinterpret_cast<const float*>(xr) + off, xv[u][j]);
+                            if (VEC == 4 && ko[j] + VEC > p.k) {      // x's own padding may hold anything
+#pragma unroll
+                                for (int q = 0; q < VEC; ++q) if (ko[j] + q >= p.k) xv[u][j][q] = 0.f;
+                            }
+                        } else {
+#pragma unroll
+                            for (int q = 0; q < VEC; ++q) xv[u][j][q] = 0.f;
+                        }
+                    }
+                }
+#pragma unroll
+                for (int u = 0; u < U; ++u)
+#pragma unroll
+                    for (int j = 0; j < LPL; ++j)
+#pragma unroll
+                        for (int q = 0; q < VEC; ++q) part[v0 + u] = fmaf(av[j][q], xv[u][j][q], part[v0 + u]);
+            }
+        }
+
+        // halving butterfly inside each lane group: P values on G lanes -> 1 value per lane;
+        // lane lg ends with the total of value index lg
+#pragma unroll
+        for (int o = P / 2; o >= 1; o >>= 1) {
+            const bool hi = (lg & o) != 0;
+#pragma unroll
+            for (int h = 0; h < o; ++h) {
+                const float keep = hi ? part[h + o] : part[h];
+                const float send = hi ? part[h] : part[h + o];
+                part[h] = keep + __shfl_xor_sync(FULL, send, o);
+            }
+        }
+        const int idx = lg * NG + g;
+        if (idx < cnt) p.out[e0 + idx] = part[0] * inv;
+    }
+}
+
+}  // namespace isplib
+
+using namespace isplib;
+
+extern "C" int isplib_b200_sddmm_csr(int64_t m, int64_t n, int64_t k, int64_t nnz,
+                                     const int32_t* rowptr, const int32_t* col,
+                                     const float* a, int64_t lda, const float* x, int64_t ldx,
+                                     int mean_scale, float* out_val,
+                                     const isplib_b200_plan_info* info, const void* plan_dev,
+                                     isplib_stream_t stream_) {
+    cudaStream_t stream = (cudaStream_t)stream_;
+    if (m < 0 || n < 0 || k < 0 || nnz < 0 || m >= INT32_MAX - 1 || nnz >= INT32_MAX || k >= INT32_MAX) return ISPLIB_INVALID_ARG;
+    if (nnz == 0 || m == 0) return ISPLIB_SUCCESS;
+    if (!rowptr || !col || !out_val || !info || !plan_dev) return ISPLIB_INVALID_ARG;
+    if (info->m != m || info->nnz != nnz) return ISPLIB_FAIL;
+    if (k == 0) { ISPLIB_CUDA_TRY(cudaMemsetAsync(out_val, 0, (size_t)nnz * 4, stream)); return ISPLIB_SUCCESS; }
+    if (!a || !x || lda < k || ldx < k) return ISPLIB_INVALID_ARG;
+
+    const PlanLayout L = plan_layout(m, nnz, info->seg_len);
+    const char* base = (const char*)plan_dev;
+    SddmmParams p;
+    p.rowptr = rowptr; p.col = col; p.a = a; p.x = x; p.out = out_val;
+    p.seg_off = (const int32_t*)(base + L.off_seg_off);
+    p.item_row = (const int32_t*)(base + L.off_item_row);
+    p.lda = lda; p.ldx = ldx; p.k = (int)k; p.num_items = (int)info->num_items;
+    p.seg_len = info->seg_len; p.mean_scale = mean_scale;
+
+    const int64_t k4 = (k + 3) & ~(int64_t)3;
+    const bool vec4 = (ldx % 4 == 0) && (ldx >= k4) && (lda % 4 == 0) &&
+                      ((reinterpret_cast<uintptr_t>(x) & 15u) == 0) && ((reinterpret_cast<uintptr_t>(a) & 15u) == 0);
+    const int warps = 4;
+    const dim3 grid((unsigned)((p.num_items + warps - 1) / warps)), block(warps * 32);
+    if (vec4) {
+        const int64_t tv = k4 / 4;
+        if (tv <= 8) sddmm_seg_kernel<4, 8, 1><<<grid, block, 0, stream>>>(p);
+        else if (tv <= 16) sddmm_seg_kernel<4, 16, 1><<<grid, block, 0, stream>>>(p);
+        else if (tv <= 32) sddmm_seg_kernel<4, 32, 1><<<grid, block, 0, stream>>>(p);
+        else sddmm_seg_kernel<4, 32, 2><<<grid, block, 0, stream>>>(p);   // 256 floats per pass, loops for wider K
+    } else {
+        if (k <= 32) sddmm_seg_kernel<1, 32, 1><<<grid, block, 0, stream>>>(p);
+        else sddmm_seg_kernel<1, 32, 2><<<grid, block, 0, stream>>>(p);
+    }
+    ISPLIB_LAUNCH_CHECK();
+    return ISPLIB_SUCCESS;
+}

@@ -285,6 +285,23 @@ std::tuple<Tensor, c10::optional<Tensor>> spmm_fw(CsrView& g, const c10::optiona
 // ---------------------------------------------------------------------------------------
 // autograd Functions -- FusedMM_SPMMSum / Mean / Max / Min of the reference
 // ---------------------------------------------------------------------------------------
+// d(loss)/d(value) of sum / mean: one SDDMM over the CSR pattern (isplib_b200_sddmm_csr)
+Tensor value_gradient(AutogradContext* ctx, GraphEntry& g, const variable_list& saved, const Tensor& grad_out_in,
+                      bool mean) {
+    if (!ctx->saved_data["value_grad"].toBool()) return Tensor();
+    c10::cuda::CUDAGuard guard(grad_out_in.device());
+    Tensor grad_out = grad_out_in.contiguous();
+    Tensor value = saved[2], mat = saved[3].contiguous();
+    Tensor grad_value = torch::empty_like(value, value.options().memory_format(c10::MemoryFormat::Contiguous));
+    auto stream = at::cuda::getCurrentCUDAStream();
+    std::lock_guard<std::mutex> lk(g.mu);
+    ISPLIB_CHECK_STATUS(isplib_b200_sddmm_csr(g.fwd.m, mat.size(0), mat.size(1), g.fwd.nnz, g.fwd.rowptr32.data_ptr<int32_t>(),
+                                              g.fwd.col32.data_ptr<int32_t>(), grad_out.data_ptr<float>(), grad_out.size(1),
+                                              mat.data_ptr<float>(), mat.size(1), mean ? 1 : 0, grad_value.data_ptr<float>(),
+                                              &g.fwd.info, g.fwd.plan_ptr(), stream.stream()));
+    return grad_value;
+}
+
 class SPMMSum : public torch::autograd::Function<SPMMSum> {
 public:
     static variable_list forward(AutogradContext* ctx, Variable rowptr, Variable col,
@@ -301,7 +318,10 @@ public:
         // needs_input_grad() indexes tensor inputs only (a None `value` shifts it), so the
         // flags are taken here, like any_variable_requires_grad at csrc/fusedmm.cpp:228
         ctx->saved_data["mat_grad"] = mat.requires_grad();
-        if (value.has_value()) ctx->save_for_backward({rowptr, col, value.value()});
+        const bool value_grad = value.has_value() && value->requires_grad();
+        ctx->saved_data["value_grad"] = value_grad;
+        if (value_grad) ctx->save_for_backward({rowptr, col, value.value(), mat});
+        else if (value.has_value()) ctx->save_for_backward({rowptr, col, value.value()});
         else ctx->save_for_backward({rowptr, col});
         return {out};
     }
@@ -312,7 +332,9 @@ public:
         const int64_t n = ctx->saved_data["n"].toInt();
         c10::optional<Tensor> value = c10::nullopt;
         if (ctx->saved_data["has_value"].toBool()) value = saved[2];
-        // grad_value is never computed by the reference for sum (csrc/fusedmm.cpp:268-272)
+        // the reference never computes grad_value for sum (csrc/fusedmm.cpp:268-272 returns an
+        // undefined gradient); here it is the SDDMM <grad_out[row(e)], mat[col[e]]>
+        Tensor grad_value = value_gradient(ctx, *g, saved, grad_out, /*mean=*/false);
         Tensor grad_mat;
         if (ctx->saved_data["mat_grad"].toBool()) {
             c10::cuda::CUDAGuard guard(grad_out.device());
@@ -322,7 +344,7 @@ public:
             c10::optional<Tensor> ovt = vt.defined() ? c10::optional<Tensor>(vt) : c10::nullopt;
             grad_mat = std::get<0>(spmm_fw(g->bwd, ovt, grad_out, ISPLIB_REDUCE_SUM));  // csrc/fusedmm.cpp:285
         }
-        return {Variable(), Variable(), Variable(), grad_mat};
+        return {Variable(), Variable(), grad_value, grad_mat};
     }
 };
 
@@ -342,7 +364,10 @@ public:
         // needs_input_grad() indexes tensor inputs only (a None `value` shifts it), so the
         // flags are taken here, like any_variable_requires_grad at csrc/fusedmm.cpp:228
         ctx->saved_data["mat_grad"] = mat.requires_grad();
-        if (value.has_value()) ctx->save_for_backward({rowptr, col, value.value()});
+        const bool value_grad = value.has_value() && value->requires_grad();
+        ctx->saved_data["value_grad"] = value_grad;
+        if (value_grad) ctx->save_for_backward({rowptr, col, value.value(), mat});
+        else if (value.has_value()) ctx->save_for_backward({rowptr, col, value.value()});
         else ctx->save_for_backward({rowptr, col});
         return {out};
     }
@@ -353,6 +378,7 @@ public:
         const int64_t n = ctx->saved_data["n"].toInt();
         c10::optional<Tensor> value = c10::nullopt;
         if (ctx->saved_data["has_value"].toBool()) value = saved[2];
+        Tensor grad_value = value_gradient(ctx, *g, saved, grad_out, /*mean=*/true);   // csrc/fusedmm.cpp:349-353: undefined there
         Tensor grad_mat;
         if (ctx->saved_data["mat_grad"].toBool()) {
             c10::cuda::CUDAGuard guard(grad_out.device());
@@ -363,7 +389,7 @@ public:
             Tensor w = permuted_values(*g, value, true);
             grad_mat = std::get<0>(spmm_fw(g->bwd, w, grad_out, ISPLIB_REDUCE_SUM));
         }
-        return {Variable(), Variable(), Variable(), grad_mat};
+        return {Variable(), Variable(), grad_value, grad_mat};
     }
 };
 

@@ -216,6 +216,27 @@ int oracle_build_csc(const INDEXTYPE m, const INDEXTYPE n, const INDEXTYPE nnz,
     return O_SUCCESS;
 }
 
+/* d(loss)/d(value[e]) of the sum / mean SpMM: the SDDMM  <grad_out[row(e)], mat[col[e]]>
+ * (/ max(deg,1) for mean).  NOT computed by the reference (csrc/fusedmm.cpp:268-272,349-353
+ * leave grad_value undefined); it is the derivative of fusedMM_csr's own recurrence
+ * z[i] += val[e] * y[indx[e]] with respect to val[e], restated here as the checker of the
+ * extension isplib_b200_sddmm_csr. */
+int oracle_sddmm(const INDEXTYPE m, const INDEXTYPE k, const INDEXTYPE *rowptr, const INDEXTYPE *col,
+                 const VALUETYPE *a, const VALUETYPE *x, const int mean_scale, VALUETYPE *out)
+{
+#pragma omp parallel for schedule(dynamic, 16)
+    for (INDEXTYPE i = 0; i < m; ++i) {
+        INDEXTYPE deg = rowptr[i + 1] - rowptr[i];
+        if (deg < 1) deg = 1;
+        for (INDEXTYPE e = rowptr[i]; e < rowptr[i + 1]; ++e) {
+            double s = 0.0;
+            for (INDEXTYPE kk = 0; kk < k; ++kk) s += (double)a[i * k + kk] * (double)x[col[e] * k + kk];
+            out[e] = (VALUETYPE)(mean_scale ? s / (double)deg : s);
+        }
+    }
+    return O_SUCCESS;
+}
+
 int oracle_num_threads(void)
 {
 #ifdef _OPENMP

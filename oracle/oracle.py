@@ -72,6 +72,8 @@ def load_c() -> ctypes.CDLL:
         lib.oracle_arg_backward.argtypes = [i64, i64, i64, p, p, p, p, p, p, p]
         lib.oracle_build_csc.restype = ctypes.c_int
         lib.oracle_build_csc.argtypes = [i64, i64, i64, p, p, p, p, p, p]
+        lib.oracle_sddmm.restype = ctypes.c_int
+        lib.oracle_sddmm.argtypes = [i64, i64, p, p, p, p, ctypes.c_int, p]
         lib.oracle_num_threads.restype = ctypes.c_int
         _lib = lib
     return _lib
@@ -242,3 +244,17 @@ def arg_backward(col, value, mat, arg, grad_out, N: int, need_grad_value: bool =
 
 def num_threads() -> int:
     return int(load_c().oracle_num_threads())
+
+
+def sddmm(rowptr, col, a, x, mean_scale: bool = False) -> np.ndarray:
+    """grad_value of sum/mean: <a[row(e)], x[col[e]]> (/ max(deg,1)), float64 accumulation."""
+    rowptr = np.ascontiguousarray(rowptr, dtype=np.int64)
+    col = np.ascontiguousarray(col, dtype=np.int64)
+    a = np.ascontiguousarray(a, dtype=np.float32)
+    x = np.ascontiguousarray(x, dtype=np.float32)
+    out = np.zeros(col.shape[0], dtype=np.float32)
+    st = load_c().oracle_sddmm(rowptr.shape[0] - 1, a.shape[1], _ptr(rowptr), _ptr(col), _ptr(a), _ptr(x),
+                               1 if mean_scale else 0, _ptr(out))
+    if st != 0:
+        raise RuntimeError(f"oracle_sddmm status {st}")
+    return out

@@ -291,3 +291,29 @@ def test_gnn_training_step_patched_equals_stock(isplib, model_name):
     assert abs(loss_a - loss_b) <= 1e-4 * max(1.0, abs(loss_b))
     for ga, gb in zip(grads_a, grads_b):
         torch.testing.assert_close(ga, gb, rtol=2e-3, atol=2e-4)
+
+
+@pytest.mark.parametrize("reduce", ["sum", "mean"])
+def test_value_gradient_of_sum_and_mean(isplib, oracle, reduce):
+    """grad w.r.t. the adjacency values (learnable edge weights): undefined in the reference
+    (csrc/fusedmm.cpp:268-272, 349-353), provided here as an SDDMM; checked against the
+    analytic derivative <grad_out[row(e)], X[col(e)]> (/deg) and against grad_mat's oracle."""
+    from isplib_b200 import synth
+    g = synth.make_graph(900, 30_000, law="lognormal", param=1.2, values="uniform", seed=8)
+    K = 48
+    x = torch.randn(g.n, K, generator=torch.Generator().manual_seed(1))
+    go = torch.randn(g.m, K, generator=torch.Generator().manual_seed(2))
+    rowptr, col = g.rowptr.to(DEV), g.col.to(DEV)
+    val = g.value.to(DEV).requires_grad_(True)
+    xd = x.to(DEV).requires_grad_(True)
+    ops = torch.ops.isplib
+    if reduce == "sum":
+        out = ops.fusedmm_spmm(None, rowptr, col, val, None, None, xd, None, None)
+    else:
+        out = ops.fusedmm_spmm_mean(None, rowptr, col, val, None, None, None, xd, None, None)
+    out.backward(go.to(DEV))
+    ref = oracle.sddmm(g.rowptr.numpy(), g.col.numpy(), go.numpy(), x.numpy(), reduce == "mean")
+    np.testing.assert_allclose(val.grad.cpu().numpy(), ref, rtol=1e-4, atol=1e-4)
+    bw = oracle.spmm_backward_sum if reduce == "sum" else oracle.spmm_backward_mean
+    gref = bw(g.rowptr.numpy(), g.col.numpy(), g.value.numpy(), go.numpy(), g.n)
+    np.testing.assert_allclose(xd.grad.cpu().numpy(), gref, rtol=1e-4, atol=1e-4)
