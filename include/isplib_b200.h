@@ -196,6 +196,18 @@ int isplib_b200_sddmm_csr(int64_t m, int64_t n, int64_t k, int64_t nnz,
                           const isplib_b200_plan_info* info, const void* plan_dev,
                           isplib_stream_t stream);
 
+/* ---- graph ingest: COO (e.g. a PyG edge_index, or a Matrix Market file) -> CSR ----------
+ * Replaces the host-side argsort of torch_sparse's SparseTensor constructor that every
+ * loader of the reference goes through (tests/cpu/dataset_loader.py:10, T.ToSparseTensor()).
+ * Stable sort by (row, col): duplicates keep their input order (the README fixture has one).
+ * Outputs: rowptr[m+1], col_out[nnz], perm[nnz] (CSR position -> input position) and, if
+ * val != NULL, val_out[nnz].  All int32 / fp32, device pointers.                            */
+int isplib_b200_coo_to_csr_workspace_bytes(int64_t m, int64_t n, int64_t nnz, size_t* bytes);
+int isplib_b200_coo_to_csr(int64_t m, int64_t n, int64_t nnz,
+                           const int32_t* row, const int32_t* col, const float* val,
+                           int32_t* rowptr, int32_t* col_out, float* val_out, int32_t* perm,
+                           void* workspace, size_t workspace_bytes, isplib_stream_t stream);
+
 /* ---- index helpers ------------------------------------------------------------- */
 /* int64 -> int32 narrowing of rowptr/col as the ops receive them
  * (csrc/fusedmm.cpp:128-129 reads int64).  *overflow_flag_dev (device int, may be

@@ -33,6 +33,7 @@ EXPORTS = [
     "isplib_b200_csr_transpose_workspace_bytes", "isplib_b200_csr_transpose",
     "isplib_b200_permute_values", "isplib_b200_spmm_arg_backward",
     "isplib_b200_narrow_i64_to_i32", "isplib_b200_fusedmm_csr_host", "isplib_b200_sddmm_csr",
+    "isplib_b200_coo_to_csr_workspace_bytes", "isplib_b200_coo_to_csr",
 ]
 
 
@@ -82,6 +83,8 @@ def lib() -> ctypes.CDLL:
     L.isplib_b200_spmm_arg_backward.argtypes = [i64, i64, i64, i64, p, p, p, i64, p, i64, i64, p, i64,
                                                 p, i64, p, ctypes.c_int, p]
     L.isplib_b200_narrow_i64_to_i32.argtypes = [i64, p, p, p, p]
+    L.isplib_b200_coo_to_csr_workspace_bytes.argtypes = [i64, i64, i64, ctypes.POINTER(sz)]
+    L.isplib_b200_coo_to_csr.argtypes = [i64, i64, i64, p, p, p, p, p, p, p, p, sz, p]
     L.isplib_b200_sddmm_csr.argtypes = [i64, i64, i64, i64, p, p, p, i64, p, i64, ctypes.c_int, p, pinfo, p, p]
     L.isplib_b200_fusedmm_csr_host.argtypes = [i32, i64, i64, i64, f32, i64, i64, i64, p, p, p, p, p, i64,
                                                p, i64, f32, p, i64, p]
@@ -259,3 +262,19 @@ def sddmm_csr(rowptr32, col32, a, x, plan: Plan, mean_scale: bool = False) -> to
                                       max(x.stride(0), K), 1 if mean_scale else 0, _p(out), ctypes.byref(plan.info),
                                       plan.ptr, _stream(x.device)), "sddmm_csr")
     return out
+
+
+def coo_to_csr(row32, col32, val, m: int, n: int):
+    """(rowptr, col, val, perm) int32/fp32 on the device, stable by (row, col) -- isplib_b200_coo_to_csr."""
+    nnz = row32.numel()
+    dev = row32.device
+    rowptr = torch.empty(m + 1, dtype=torch.int32, device=dev)
+    col_out = torch.empty(nnz, dtype=torch.int32, device=dev)
+    perm = torch.empty(nnz, dtype=torch.int32, device=dev)
+    val_out = None if val is None else torch.empty(nnz, dtype=torch.float32, device=dev)
+    ws_bytes = ctypes.c_size_t(0)
+    check(lib().isplib_b200_coo_to_csr_workspace_bytes(m, n, nnz, ctypes.byref(ws_bytes)), "coo_to_csr_ws")
+    ws = _dev_bytes(ws_bytes.value, dev)
+    check(lib().isplib_b200_coo_to_csr(m, n, nnz, _p(row32), _p(col32), _p(val), _p(rowptr), _p(col_out), _p(val_out),
+                                       _p(perm), _aligned_ptr(ws), ws_bytes.value, _stream(dev)), "coo_to_csr")
+    return rowptr, col_out, val_out, perm

@@ -294,3 +294,96 @@ extern "C" int isplib_b200_narrow_i64_to_i32(int64_t count, const int64_t* src, 
     ISPLIB_LAUNCH_CHECK();
     return ISPLIB_SUCCESS;
 }
+
+
+// ---------------------------------------------------------------------------------
+// COO -> CSR (graph ingest)
+// ---------------------------------------------------------------------------------
+namespace isplib {
+
+__global__ void coo_keys_kernel(int nnz, long long n, const int32_t* __restrict__ row,
+                                const int32_t* __restrict__ col, unsigned long long* __restrict__ keys,
+                                int32_t* __restrict__ idx, int32_t* __restrict__ bad, int m) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= nnz) return;
+    const int r = row[i], c = col[i];
+    if (r < 0 || r >= m || c < 0 || c >= n) *bad = 1;
+    keys[i] = (unsigned long long)r * (unsigned long long)n + (unsigned long long)c;
+    idx[i] = i;
+}
+
+__global__ void coo_scatter_kernel(int nnz, long long n, const unsigned long long* __restrict__ keys,
+                                   const int32_t* __restrict__ perm, const float* __restrict__ val,
+                                   int32_t* __restrict__ row_sorted, int32_t* __restrict__ col_out,
+                                   float* __restrict__ val_out) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= nnz) return;
+    const unsigned long long k = keys[i];
+    const unsigned long long r = k / (unsigned long long)n;
+    row_sorted[i] = (int32_t)r;
+    col_out[i] = (int32_t)(k - r * (unsigned long long)n);
+    if (val) val_out[i] = val[perm[i]];
+}
+
+}  // namespace isplib
+
+static int key_bits64(int64_t m, int64_t n) {
+    const unsigned long long mx = (unsigned long long)(m > 0 ? m : 1) * (unsigned long long)(n > 0 ? n : 1);
+    int b = 1;
+    while (b < 64 && (1ull << b) < mx) ++b;
+    return b;
+}
+
+extern "C" int isplib_b200_coo_to_csr_workspace_bytes(int64_t m, int64_t n, int64_t nnz, size_t* bytes) {
+    if (!bytes || m < 0 || n < 0 || nnz < 0 || nnz >= INT32_MAX || m >= INT32_MAX - 1 || n >= INT32_MAX) return ISPLIB_INVALID_ARG;
+    size_t sort_tmp = 0;
+    cub::DeviceRadixSort::SortPairs(nullptr, sort_tmp, (const unsigned long long*)nullptr, (unsigned long long*)nullptr,
+                                    (const int32_t*)nullptr, (int32_t*)nullptr, (int)nnz, 0, key_bits64(m, n));
+    size_t o = 0;
+    o = align_up(o + (size_t)nnz * 8, 256);   // keys in
+    o = align_up(o + (size_t)nnz * 8, 256);   // keys sorted
+    o = align_up(o + (size_t)nnz * 4, 256);   // iota
+    o = align_up(o + (size_t)nnz * 4, 256);   // sorted rows
+    o = align_up(o + 256, 256);               // error flag
+    o = align_up(o + sort_tmp, 256);
+    *bytes = o + 256;
+    return ISPLIB_SUCCESS;
+}
+
+extern "C" int isplib_b200_coo_to_csr(int64_t m, int64_t n, int64_t nnz,
+                                      const int32_t* row, const int32_t* col, const float* val,
+                                      int32_t* rowptr, int32_t* col_out, float* val_out, int32_t* perm,
+                                      void* workspace, size_t workspace_bytes, isplib_stream_t stream_) {
+    cudaStream_t stream = (cudaStream_t)stream_;
+    size_t need = 0;
+    int st = isplib_b200_coo_to_csr_workspace_bytes(m, n, nnz, &need);
+    if (st) return st;
+    if (!rowptr || (nnz > 0 && (!row || !col || !col_out || !perm)) || (val && !val_out)) return ISPLIB_INVALID_ARG;
+    if (!workspace || workspace_bytes < need) return ISPLIB_NOT_ENOUGH_MEM;
+    char* base = (char*)align_up((size_t)(uintptr_t)workspace, 256);
+    size_t o = 0;
+    unsigned long long* keys = (unsigned long long*)(base + o);        o = align_up(o + (size_t)nnz * 8, 256);
+    unsigned long long* keys_sorted = (unsigned long long*)(base + o); o = align_up(o + (size_t)nnz * 8, 256);
+    int32_t* iota = (int32_t*)(base + o);                              o = align_up(o + (size_t)nnz * 4, 256);
+    int32_t* row_sorted = (int32_t*)(base + o);                        o = align_up(o + (size_t)nnz * 4, 256);
+    int32_t* bad = (int32_t*)(base + o);                               o = align_up(o + 256, 256);
+    void* sort_tmp = base + o;
+    size_t sort_bytes = workspace_bytes - o - 256;
+    ISPLIB_CUDA_TRY(cudaMemsetAsync(bad, 0, 4, stream));
+    if (nnz > 0) {
+        const int blocks = (int)((nnz + 255) / 256);
+        coo_keys_kernel<<<blocks, 256, 0, stream>>>((int)nnz, (long long)n, row, col, keys, iota, bad, (int)m);
+        ISPLIB_LAUNCH_CHECK();
+        ISPLIB_CUDA_TRY(cub::DeviceRadixSort::SortPairs(sort_tmp, sort_bytes, keys, keys_sorted, iota, perm, (int)nnz, 0,
+                                                        key_bits64(m, n), stream));
+        coo_scatter_kernel<<<blocks, 256, 0, stream>>>((int)nnz, (long long)n, keys_sorted, perm, val, row_sorted, col_out, val_out);
+        ISPLIB_LAUNCH_CHECK();
+    }
+    // rowptr from the sorted rows: same routine as colptr from sorted columns
+    colptr_from_sorted_kernel<<<(int)((nnz + 1 + 255) / 256), 256, 0, stream>>>((int)nnz, (int)m, row_sorted, rowptr);
+    ISPLIB_LAUNCH_CHECK();
+    int32_t h_bad = 0;
+    ISPLIB_CUDA_TRY(cudaMemcpyAsync(&h_bad, bad, 4, cudaMemcpyDeviceToHost, stream));
+    ISPLIB_CUDA_TRY(cudaStreamSynchronize(stream));
+    return h_bad ? ISPLIB_INVALID_ARG : ISPLIB_SUCCESS;
+}

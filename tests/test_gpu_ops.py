@@ -317,3 +317,59 @@ def test_value_gradient_of_sum_and_mean(isplib, oracle, reduce):
     bw = oracle.spmm_backward_sum if reduce == "sum" else oracle.spmm_backward_mean
     gref = bw(g.rowptr.numpy(), g.col.numpy(), g.value.numpy(), go.numpy(), g.n)
     np.testing.assert_allclose(xd.grad.cpu().numpy(), gref, rtol=1e-4, atol=1e-4)
+
+
+# --------------------------------------------------------------------------------------
+# ingest formats: edge_index -> CSR on the device, Matrix Market round trip
+# --------------------------------------------------------------------------------------
+def test_from_edge_index_matches_host_sparse_tensor(isplib):
+    from isplib import SparseTensor
+    from isplib_b200 import io
+    gen = torch.Generator().manual_seed(5)
+    M, N, E = 300, 200, 5000
+    ei = torch.stack([torch.randint(0, M, (E,), generator=gen), torch.randint(0, N, (E,), generator=gen)])
+    ei[:, 10] = ei[:, 3]                      # a duplicate entry: input order must be kept (stable)
+    w = torch.randn(E, generator=gen)
+    ref = SparseTensor(row=ei[0], col=ei[1], value=w, sparse_sizes=(M, N))          # host: stable argsort
+    got = io.from_edge_index(ei, w, M, N, device=DEV)
+    for a, b in zip(got.csr(), ref.csr()):
+        assert torch.equal(a.cpu(), b)
+    assert got.sparse_sizes() == (M, N)
+    nov = io.from_edge_index(ei, None, M, N, device=DEV)
+    assert nov.storage.value() is None and torch.equal(nov.storage.col().cpu(), ref.storage.col())
+    # README.md:105-110 fixture through the device builder
+    adj = io.from_edge_index(torch.tensor([[2, 0, 1, 0, 0], [1, 0, 0, 2, 0]]), torch.tensor([3., 3., 4., 2., -2.]), 3, 3, DEV)
+    assert adj.csr()[0].tolist() == [0, 3, 4, 5] and adj.csr()[2].tolist() == [3, -2, 2, 4, 3]
+    with pytest.raises(Exception):
+        io.from_edge_index(torch.tensor([[0, 5], [0, 1]]), None, 3, 3, DEV)         # row 5 out of range
+
+
+def test_matrix_market_round_trip_and_spmm(isplib, oracle, tmp_path):
+    from isplib import iSpLibPlugin
+    from isplib_b200 import io, synth
+    import torch_sparse
+    g = synth.make_graph(400, 6000, law="lognormal", param=1.0, values="uniform", seed=6)
+    # Matrix Market sums duplicates; make the graph duplicate-free so the round trip is exact
+    row = torch.repeat_interleave(torch.arange(g.m), g.rowptr[1:] - g.rowptr[:-1])
+    key = torch.unique(row * g.n + g.col)
+    row, col = key // g.n, key % g.n
+    val = torch.rand(key.numel(), generator=torch.Generator().manual_seed(1)) + 0.5
+    from isplib import SparseTensor
+    adj = SparseTensor(row=row, col=col, value=val, sparse_sizes=(g.m, g.n))
+    path = str(tmp_path / "graph.mtx")
+    io.write_mtx(adj, path)
+    back = io.read_mtx(path, device=DEV)
+    for a, b in zip(back.csr(), adj.csr()):
+        if a.dtype.is_floating_point:
+            torch.testing.assert_close(a.cpu(), b, rtol=1e-6, atol=0)
+        else:
+            assert torch.equal(a.cpu(), b)
+    x = torch.randn(g.n, 32, generator=torch.Generator().manual_seed(2))
+    iSpLibPlugin.patch_pyg()
+    try:
+        out = torch_sparse.matmul(back, x.to(DEV), "sum")
+    finally:
+        iSpLibPlugin.unpatch_pyg()
+    rp, co, va = [t.numpy() for t in adj.csr()]
+    ref, _ = oracle.spmm_c(rp, co, back.storage.value().cpu().numpy(), x.numpy(), oracle.SUM)
+    assert_sum_close(out.cpu().numpy(), ref, abs_product_sum(rp, co, va, x.numpy()))
