@@ -73,8 +73,19 @@ class iSpLibPlugin:
     is_cached = False
     value_cached = False
     # 'reference': max/min leave lowest()/max() in rows without entries, as
-    # csrc/fusedmm.cpp:147-150 does; nothing else is configurable here.
+    # csrc/fusedmm.cpp:147-150 does; 'zero': torch_sparse's convention (what PyG's aggr='max'
+    # expects for isolated nodes).  arg_out is the nnz sentinel in both.
     empty_row_mode = "reference"
+
+    @classmethod
+    def set_empty_row_mode(cls, mode: str):
+        if mode not in ("reference", "zero"):
+            raise ValueError("empty_row_mode must be 'reference' or 'zero'")
+        cls.empty_row_mode = mode
+        if mode == "zero":
+            os.environ["ISPLIB_B200_EMPTY_ROWS"] = "zero"
+        else:
+            os.environ.pop("ISPLIB_B200_EMPTY_ROWS", None)
 
     @staticmethod
     def spmm(src, other, reduce: str = "sum"):

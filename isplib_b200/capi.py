@@ -15,7 +15,7 @@ from typing import Optional, Tuple
 import torch
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libisplib_b200.so")
+LIB_PATH = os.environ.get("ISPLIB_B200_LIB") or os.path.join(_HERE, "libisplib_b200.so")   # env: A/B builds in tools/
 
 SUM, MAX, MIN, MEAN = 0, 1, 2, 3
 REDUCE_CODE = {"sum": SUM, "add": SUM, "max": MAX, "min": MIN, "mean": MEAN}

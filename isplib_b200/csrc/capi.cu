@@ -55,7 +55,7 @@ static int fill_params(SpmmParams& p, int reduce, int64_t m, int64_t n, int64_t 
                        const float* row_divisor, const int32_t* edge_ids, int64_t arg_sentinel) {
     if (reduce < 0 || reduce > 3) return ISPLIB_NO_OPT_IMPL;
     if (m < 0 || n < 0 || k < 0 || nnz < 0) return ISPLIB_INVALID_ARG;
-    if (m >= INT32_MAX - 1 || nnz >= INT32_MAX || k >= INT32_MAX || n >= INT32_MAX) return ISPLIB_INVALID_ARG;
+    if (m >= INT32_MAX - 1 || nnz >= INT32_MAX - 64 || k >= INT32_MAX || n >= INT32_MAX) return ISPLIB_INVALID_ARG;
     if (m == 0 || k == 0) { memset(&p, 0, sizeof(p)); return ISPLIB_SUCCESS; }
     if (!rowptr || !out || !info || !plan_dev) return ISPLIB_INVALID_ARG;
     if (nnz > 0 && (!col || !x)) return ISPLIB_INVALID_ARG;
@@ -94,6 +94,7 @@ static int fill_params(SpmmParams& p, int reduce, int64_t m, int64_t n, int64_t 
     p.seg_off = (const int32_t*)(base + L.off_seg_off);
     p.part_off = (const int32_t*)(base + L.off_part_off);
     p.item_row = (const int32_t*)(base + L.off_item_row);
+    p.item_desc = (const int4*)(base + L.off_item_desc);
     p.split_rows = (const int32_t*)(base + L.off_split_rows);
     p.part_val = part_val;
     p.part_arg = part_arg;

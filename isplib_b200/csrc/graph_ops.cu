@@ -46,16 +46,25 @@ __global__ void plan_count_kernel(int m, int seg_len, const int32_t* __restrict_
 }
 
 // one warp per row: write the row id into each of its item slots, collect split rows
-__global__ void plan_fill_kernel(int m, const int32_t* __restrict__ seg_off,
+__global__ void plan_fill_kernel(int m, int seg_len, const int32_t* __restrict__ rowptr,
+                                 const int32_t* __restrict__ seg_off,
                                  const int32_t* __restrict__ part_off,
-                                 int32_t* __restrict__ item_row, int32_t* __restrict__ split_rows,
+                                 int32_t* __restrict__ item_row, int4* __restrict__ item_desc,
+                                 int32_t* __restrict__ split_rows,
                                  unsigned long long* __restrict__ counters,
                                  int32_t* __restrict__ split_cursor) {
     const int row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
     const int lane = threadIdx.x & 31;
     if (row >= m) return;
     const int b = seg_off[row], e = seg_off[row + 1];
-    for (int w = b + lane; w < e; w += 32) item_row[w] = row;
+    const int rb = rowptr[row], re = rowptr[row + 1];
+    const int pb = part_off[row];
+    for (int w = b + lane; w < e; w += 32) {
+        const int s = w - b;
+        item_row[w] = row;
+        const int eb = rb + s * seg_len;
+        item_desc[w] = make_int4(row, eb, min(re, eb + seg_len), (e - b > 1) ? pb + s : -1);
+    }
     if (lane == 0) {
         if (e - b > 1) split_rows[atomicAdd(split_cursor, 1)] = row;
         if (row == m - 1) {
@@ -71,7 +80,7 @@ using namespace isplib;
 
 extern "C" int isplib_b200_plan_bytes(int64_t m, int64_t nnz, int32_t seg_len, size_t* bytes) {
     if (!bytes || m < 0 || nnz < 0) return ISPLIB_INVALID_ARG;
-    if (m >= INT32_MAX - 1 || nnz >= INT32_MAX) return ISPLIB_INVALID_ARG;
+    if (m >= INT32_MAX - 1 || nnz >= INT32_MAX - 64) return ISPLIB_INVALID_ARG;   // kernels index e0 + 63
     const PlanLayout L = plan_layout(m, nnz, seg_len);
     size_t scan_tmp = 0;
     cub::DeviceScan::ExclusiveSum(nullptr, scan_tmp, (const int32_t*)nullptr, (int32_t*)nullptr, (int)(m + 1));
@@ -103,6 +112,7 @@ extern "C" int isplib_b200_plan_build(int64_t m, int64_t nnz, const int32_t* row
     int32_t* seg_off = (int32_t*)(base + L.off_seg_off);
     int32_t* part_off = (int32_t*)(base + L.off_part_off);
     int32_t* item_row = (int32_t*)(base + L.off_item_row);
+    int4* item_desc = (int4*)(base + L.off_item_desc);
     int32_t* split_rows = (int32_t*)(base + L.off_split_rows);
     size_t o = L.off_temp;
     int32_t* seg_cnt = (int32_t*)(base + o);  o = align_up(o + (size_t)(m + 1) * 4, 256);
@@ -123,7 +133,7 @@ extern "C" int isplib_b200_plan_build(int64_t m, int64_t nnz, const int32_t* row
     if (m > 0) {
         const int wpb = 8;
         plan_fill_kernel<<<(int)((m + wpb - 1) / wpb), wpb * 32, 0, stream>>>(
-            (int)m, seg_off, part_off, item_row, split_rows, counters, cursor);
+            (int)m, S, rowptr, seg_off, part_off, item_row, item_desc, split_rows, counters, cursor);
         ISPLIB_LAUNCH_CHECK();
     }
     unsigned long long h[8] = {0};

@@ -40,6 +40,9 @@ static const VariantDesc kVariants[] = {
     {"seg/w8/u4/kt32", 0, 8, 4, 32},
     {"seg/w4/u4/kt32", 0, 4, 4, 32},
     {"seg/w8/u8/kt64", 0, 8, 8, 64},
+    {"seg/w4/u2/kfull", 0, 4, 2, 0},
+    {"seg/w4/u2/kt64", 0, 4, 2, 64},
+    {"seg/w8/u2/kt64", 0, 8, 2, 64},
 };
 int variant_count() { return (int)(sizeof(kVariants) / sizeof(kVariants[0])); }
 const VariantDesc* variant_desc(int v) {
@@ -53,14 +56,44 @@ template <int VEC> struct VecT;
 template <> struct VecT<4> { using type = float4; };
 template <> struct VecT<1> { using type = float; };
 
+#ifndef ISPLIB_X_EVICT_LAST
+#define ISPLIB_X_EVICT_LAST 0
+#endif
+
+#if ISPLIB_X_EVICT_LAST
+// L2 cache policy for the gathered X rows: keep them (evict_last) while the index stream and
+// the output go through with evict-first hints, so a K slab of X survives in L2.
+__device__ __forceinline__ unsigned long long x_policy() {
+    unsigned long long pol;
+    asm volatile("createpolicy.fractional.L2::evict_last.b64 %0, 1.0;" : "=l"(pol));
+    return pol;
+}
+#define ISPLIB_XPOL_DECL const unsigned long long xpol = x_policy();
+#define ISPLIB_XPOL_ARG , xpol
+#define ISPLIB_XPOL_PARAM , unsigned long long xpol
+#else
+#define ISPLIB_XPOL_DECL
+#define ISPLIB_XPOL_ARG
+#define ISPLIB_XPOL_PARAM
+#endif
+
 template <int VEC>
-__device__ __forceinline__ void load_vec(const float* __restrict__ p, float (&v)[VEC]) {
+__device__ __forceinline__ void load_vec(const float* __restrict__ p, float (&v)[VEC] ISPLIB_XPOL_PARAM) {
+#if ISPLIB_X_EVICT_LAST
+    if constexpr (VEC == 4) {
+        asm volatile("ld.global.nc.L2::cache_hint.v4.f32 {%0,%1,%2,%3}, [%4], %5;"
+                     : "=f"(v[0]), "=f"(v[1]), "=f"(v[2]), "=f"(v[3]) : "l"(p), "l"(xpol));
+    } else {
+        asm volatile("ld.global.nc.L2::cache_hint.f32 %0, [%1], %2;" : "=f"(v[0]) : "l"(p), "l"(xpol));
+    }
+#else
     if constexpr (VEC == 4) {
         const float4 t = __ldg(reinterpret_cast<const float4*>(p));
         v[0] = t.x; v[1] = t.y; v[2] = t.z; v[3] = t.w;
     } else {
         v[0] = __ldg(p);
     }
+#endif
 }
 
 template <int VEC>
@@ -193,14 +226,11 @@ spmm_seg_kernel(const __grid_constant__ SpmmParams p) {
     const int item = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
     if (item >= p.num_items) return;
 
-    const int row = __ldg(p.item_row + item);
-    const int so = __ldg(p.seg_off + row);
-    const int nseg = __ldg(p.seg_off + row + 1) - so;
-    const int s = item - so;
-    const int rb = __ldg(p.rowptr + row);
-    const int re = __ldg(p.rowptr + row + 1);
-    const int eb = rb + s * p.seg_len;
-    const int ee = min(re, eb + p.seg_len);
+    // one 16-byte descriptor per work item {row, first entry, end entry, partial slot or -1}:
+    // a single load instead of the item_row -> seg_off -> rowptr chain, which matters for
+    // short rows (products-shape: ~50 entries per row, the chain was ~1/3 of a warp's life)
+    const int4 desc = __ldg(p.item_desc + item);
+    const int row = desc.x, eb = desc.y, ee = desc.z, slot_id = desc.w;
 
     const int g = lane / G;
     const int lg = lane % G;
@@ -235,6 +265,7 @@ spmm_seg_kernel(const __grid_constant__ SpmmParams p) {
         for (int v = 0; v < VEC; ++v) { acc[j][v] = init_value<OP>(); arg[j][v] = kNoArg; }
 
     const bool has_val = (p.val != nullptr);
+    ISPLIB_XPOL_DECL
 
     // one 32-entry chunk of (col, val) per lane, one chunk prefetched ahead
     unsigned c_next = 0;
@@ -268,8 +299,8 @@ spmm_seg_kernel(const __grid_constant__ SpmmParams p) {
                     const unsigned long long off = (unsigned long long)cc * ldxb;
 #pragma unroll
                     for (int j = 0; j < LPL; ++j) {
-                        if constexpr (PARTIAL) load_vec<VEC>(reinterpret_cast<const float*>(xlane[j] + off), xv[u][j]);
-                        else load_vec<VEC>(reinterpret_cast<const float*>(xlane[0] + off) + j * G * VEC, xv[u][j]);
+                        if constexpr (PARTIAL) load_vec<VEC>(reinterpret_cast<const float*>(xlane[j] + off), xv[u][j] ISPLIB_XPOL_ARG);
+                        else load_vec<VEC>(reinterpret_cast<const float*>(xlane[0] + off) + j * G * VEC, xv[u][j] ISPLIB_XPOL_ARG);
                     }
                 }
 #pragma unroll
@@ -304,8 +335,8 @@ spmm_seg_kernel(const __grid_constant__ SpmmParams p) {
                     if (ok[u]) {
 #pragma unroll
                         for (int j = 0; j < LPL; ++j) {
-                            if constexpr (PARTIAL) load_vec<VEC>(reinterpret_cast<const float*>(xlane[j] + off), xv[u][j]);
-                            else load_vec<VEC>(reinterpret_cast<const float*>(xlane[0] + off) + j * G * VEC, xv[u][j]);
+                            if constexpr (PARTIAL) load_vec<VEC>(reinterpret_cast<const float*>(xlane[j] + off), xv[u][j] ISPLIB_XPOL_ARG);
+                            else load_vec<VEC>(reinterpret_cast<const float*>(xlane[0] + off) + j * G * VEC, xv[u][j] ISPLIB_XPOL_ARG);
                         }
                     }
                 }
@@ -350,11 +381,11 @@ spmm_seg_kernel(const __grid_constant__ SpmmParams p) {
     }
     const bool writer = (NG == 1) || (g == 0);   // group 0 holds the merged result
 
-    if (nseg == 1) {
+    if (slot_id < 0) {   // the row fits this one segment: its degree is ee - eb
         if (writer) {
 #pragma unroll
             for (int j = 0; j < LPL; ++j)
-                if (kok[j]) finalize_store<OP, VEC>(p, row, re - rb, koff[j], acc[j], arg[j]);
+                if (kok[j]) finalize_store<OP, VEC>(p, row, ee - eb, koff[j], acc[j], arg[j]);
         }
         return;
     }
@@ -364,8 +395,10 @@ spmm_seg_kernel(const __grid_constant__ SpmmParams p) {
     // waits, the order of the merge is fixed, so the result is deterministic and max/min/arg
     // stay bit-exact) and finalises the row.  No second kernel launch.
     const int pbase = __ldg(p.part_off + row);
+    const int nseg = __ldg(p.seg_off + row + 1) - __ldg(p.seg_off + row);
+    const int rb = __ldg(p.rowptr + row), re = __ldg(p.rowptr + row + 1);
     if (writer) {
-        const size_t slot = (size_t)(pbase + s);
+        const size_t slot = (size_t)slot_id;
 #pragma unroll
         for (int j = 0; j < LPL; ++j) {
             if (kok[j]) {
@@ -471,6 +504,8 @@ static SegKernel pick_u(int u, bool partial) {
     if constexpr (LPL * VEC * 8 <= 64)
         if (u >= 8 && NG * 8 <= 32)
             return partial ? spmm_seg_kernel<OP, VEC, G, LPL, 8, true> : spmm_seg_kernel<OP, VEC, G, LPL, 8, false>;
+    if (u <= 2)
+        return partial ? spmm_seg_kernel<OP, VEC, G, LPL, 2, true> : spmm_seg_kernel<OP, VEC, G, LPL, 2, false>;
     if (NG * 4 <= 32)
         return partial ? spmm_seg_kernel<OP, VEC, G, LPL, 4, true> : spmm_seg_kernel<OP, VEC, G, LPL, 4, false>;
     return nullptr;

@@ -22,6 +22,7 @@
 #include <torch/torch.h>
 
 #include <cstdlib>
+#include <string>
 #include <map>
 #include <memory>
 #include <mutex>
@@ -275,10 +276,15 @@ std::tuple<Tensor, c10::optional<Tensor>> spmm_fw(CsrView& g, const c10::optiona
             variant = best;
         }
     }
-    ISPLIB_CHECK_STATUS(isplib_b200_spmm_csr(reduction, M, N, K, g.nnz, g.rowptr32.data_ptr<int32_t>(),
-                                             g.col32.data_ptr<int32_t>(), val_ptr, mat.data_ptr<float>(), ldx,
-                                             out.data_ptr<float>(), K, arg_ptr, &g.info, g.plan_ptr(),
-                                             wst.data_ptr(), ws, variant, stream.stream()));
+    // ISPLIB_B200_EMPTY_ROWS=zero: torch_sparse's convention for max/min rows without entries
+    // (0) instead of what csrc/fusedmm.cpp:147-150 leaves behind (lowest()/max())
+    const char* er = std::getenv("ISPLIB_B200_EMPTY_ROWS");
+    const int flags = (is_arg && er && std::string(er) == "zero") ? ISPLIB_FLAG_EMPTY_ZERO : 0;
+    ISPLIB_CHECK_STATUS(isplib_b200_spmm_csr_ex(reduction, M, N, K, g.nnz, g.rowptr32.data_ptr<int32_t>(),
+                                                g.col32.data_ptr<int32_t>(), val_ptr, mat.data_ptr<float>(), ldx,
+                                                out.data_ptr<float>(), K, arg_ptr, &g.info, g.plan_ptr(),
+                                                wst.data_ptr(), ws, variant, flags, nullptr, nullptr, g.nnz,
+                                                stream.stream()));
     return std::make_tuple(out, arg_out);
 }
 

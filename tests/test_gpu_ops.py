@@ -373,3 +373,26 @@ def test_matrix_market_round_trip_and_spmm(isplib, oracle, tmp_path):
     rp, co, va = [t.numpy() for t in adj.csr()]
     ref, _ = oracle.spmm_c(rp, co, back.storage.value().cpu().numpy(), x.numpy(), oracle.SUM)
     assert_sum_close(out.cpu().numpy(), ref, abs_product_sum(rp, co, va, x.numpy()))
+
+
+def test_empty_row_mode_zero_via_plugin(isplib):
+    """PyG's aggr='max' expects 0 for isolated nodes (torch_sparse); the reference wrapper leaves
+    lowest(); both are available, the reference behaviour is the default."""
+    from isplib import iSpLibPlugin, SparseTensor
+    import torch_sparse
+    adj = SparseTensor(row=torch.tensor([0, 0, 2]), col=torch.tensor([0, 1, 1]), value=torch.tensor([1., -2., 3.]),
+                       sparse_sizes=(4, 2)).to(DEV)
+    x = torch.tensor([[1., -1.], [2., 5.]], device=DEV)
+    iSpLibPlugin.patch_pyg()
+    try:
+        ref_mode = torch_sparse.matmul(adj, x, "max")
+        iSpLibPlugin.set_empty_row_mode("zero")
+        zero_mode = torch_sparse.matmul(adj, x, "max")
+        zmin = torch_sparse.matmul(adj, x, "min")
+    finally:
+        iSpLibPlugin.set_empty_row_mode("reference")
+        iSpLibPlugin.unpatch_pyg()
+    lowest = torch.finfo(torch.float32).min
+    assert ref_mode.tolist() == [[1., -1.], [lowest, lowest], [6., 15.], [lowest, lowest]]
+    assert zero_mode.tolist() == [[1., -1.], [0., 0.], [6., 15.], [0., 0.]]
+    assert zmin.tolist() == [[-4., -10.], [0., 0.], [6., 15.], [0., 0.]]
