@@ -4,6 +4,7 @@
 #include "common.cuh"
 #include <float.h>
 #include <stdio.h>
+#include <stdlib.h>
 #include <string.h>
 #include <vector>
 
@@ -174,8 +175,11 @@ extern "C" int isplib_b200_spmm_autotune(int reduce, int64_t m, int64_t n, int64
     ISPLIB_CUDA_TRY(cudaEventCreate(&e1));
     float best = FLT_MAX;
     int rc = ISPLIB_SUCCESS;
+    const char* tb = getenv("ISPLIB_B200_TUNE_BULK");
+    const bool tune_bulk = tb && tb[0] == '1';
     for (int v = 0; v < nv && rc == ISPLIB_SUCCESS; ++v) {
         if (!spmm_variant_supported(v, reduce, k, ldx, ldo, x, out)) continue;
+        if (variant_desc(v)->method == 1 && !tune_bulk) continue;   // see the variant table
         rc = launch_spmm(reduce, p, nnz, v, stream);  // warm-up
         if (rc) break;
         cudaEventRecord(e0, stream);

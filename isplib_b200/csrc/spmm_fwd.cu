@@ -43,6 +43,13 @@ static const VariantDesc kVariants[] = {
     {"seg/w4/u2/kfull", 0, 4, 2, 0},
     {"seg/w4/u2/kt64", 0, 4, 2, 64},
     {"seg/w8/u2/kt64", 0, 8, 2, 64},
+    // method 1: TMA bulk-copy gather through a per-warp shared-memory ring; `unroll` = stages
+    // (measured 3x slower than the LDG gather for 256-512 B rows -- profiles/r1_kbench_bulk.txt:
+    // the copy engine retires one small bulk request per ~14-30 cycles per SM -- so the on-device
+    // selection skips these unless ISPLIB_B200_TUNE_BULK=1; they stay selectable by id)
+    {"bulk/w4/s3/kfull", 1, 4, 3, 0},
+    {"bulk/w4/s3/kt64", 1, 4, 3, 64},
+    {"bulk/w8/s3/kt64", 1, 8, 3, 64},
 };
 int variant_count() { return (int)(sizeof(kVariants) / sizeof(kVariants[0])); }
 const VariantDesc* variant_desc(int v) {
@@ -210,6 +217,118 @@ __device__ __forceinline__ void finalize_store(const SpmmParams& p, int row, int
 }
 
 // ------------------------------------------------------------------------------------
+// what every gather strategy ends with: merge the lane groups, then finalise the row (single
+// segment) or publish a partial and let the last-arriving segment warp merge the row
+// ------------------------------------------------------------------------------------
+template <int OP, int VEC, int G, int LPL>
+__device__ __forceinline__ void finish_item(const SpmmParams& p, const int lane, const int row, const int eb,
+                                            const int ee, const int slot_id, const int (&koff)[LPL],
+                                            const bool (&kok)[LPL], float (&acc)[LPL][VEC], int (&arg)[LPL][VEC]) {
+    constexpr int NG = 32 / G;
+    constexpr unsigned FULL = 0xffffffffu;
+    const int g = lane / G;
+    // merge the NG lane groups (they hold interleaved entries of the same segment)
+    if constexpr (NG > 1) {
+#pragma unroll
+        for (int off = G; off < 32; off <<= 1) {
+#pragma unroll
+            for (int j = 0; j < LPL; ++j)
+#pragma unroll
+                for (int v = 0; v < VEC; ++v) {
+                    const float ov = __shfl_xor_sync(FULL, acc[j][v], off);
+                    if constexpr (OP == OP_SUM) {
+                        acc[j][v] += ov;
+                    } else {
+                        const int oa = __shfl_xor_sync(FULL, arg[j][v], off);
+                        if (better_lex<OP, int>(ov, oa, acc[j][v], arg[j][v])) { acc[j][v] = ov; arg[j][v] = oa; }
+                    }
+                }
+        }
+    }
+    const bool writer = (NG == 1) || (g == 0);   // group 0 holds the merged result
+
+    if (slot_id < 0) {   // the row fits this one segment: its degree is ee - eb
+        if (writer) {
+#pragma unroll
+            for (int j = 0; j < LPL; ++j)
+                if (kok[j]) finalize_store<OP, VEC>(p, row, ee - eb, koff[j], acc[j], arg[j]);
+        }
+        return;
+    }
+
+    // ---- split row: publish this segment's partial; the LAST segment warp to arrive merges
+    // all of the row's partials in segment order (the threadFenceReduction pattern: nobody
+    // waits, the order of the merge is fixed, so the result is deterministic and max/min/arg
+    // stay bit-exact) and finalises the row.  No second kernel launch.
+    const int pbase = __ldg(p.part_off + row);
+    const int nseg = __ldg(p.seg_off + row + 1) - __ldg(p.seg_off + row);
+    const int rb = __ldg(p.rowptr + row), re = __ldg(p.rowptr + row + 1);
+    if (writer) {
+        const size_t slot = (size_t)slot_id;
+#pragma unroll
+        for (int j = 0; j < LPL; ++j) {
+            if (kok[j]) {
+                const size_t o = slot * (size_t)p.kp + (size_t)koff[j];
+                if constexpr (VEC == 4) {
+                    __stcg(reinterpret_cast<float4*>(p.part_val + o), make_float4(acc[j][0], acc[j][1], acc[j][2], acc[j][3]));
+                    if constexpr (OP != OP_SUM)
+                        __stcg(reinterpret_cast<int4*>(p.part_arg + o), make_int4(arg[j][0], arg[j][1], arg[j][2], arg[j][3]));
+                } else {
+                    __stcg(p.part_val + o, acc[j][0]);
+                    if constexpr (OP != OP_SUM) __stcg(p.part_arg + o, arg[j][0]);
+                }
+            }
+        }
+    }
+    __threadfence();
+    __syncwarp();
+    int* const ticket_ptr = p.row_ticket + (size_t)blockIdx.y * (size_t)p.ticket_stride + (pbase >> 1);
+    int ticket = 0;
+    if (lane == 0) ticket = atomicAdd(ticket_ptr, 1);
+    ticket = __shfl_sync(FULL, ticket, 0);
+    if (ticket != nseg - 1) return;
+    __threadfence();
+    if (lane == 0) *ticket_ptr = 0;   // leave the counters zeroed for the next launch
+    if (!writer) return;
+#pragma unroll
+    for (int j = 0; j < LPL; ++j) {
+        if (!kok[j]) continue;
+        float macc[VEC];
+        int marg[VEC];
+#pragma unroll
+        for (int v = 0; v < VEC; ++v) { macc[v] = init_value<OP>(); marg[v] = kNoArg; }
+        const size_t o0 = (size_t)pbase * (size_t)p.kp + (size_t)koff[j];
+#pragma unroll 4
+        for (int t = 0; t < nseg; ++t) {
+            const size_t o = o0 + (size_t)t * (size_t)p.kp;
+            float pv[VEC];
+            int pa[VEC];
+            if constexpr (VEC == 4) {
+                const float4 q = __ldcg(reinterpret_cast<const float4*>(p.part_val + o));
+                pv[0] = q.x; pv[1] = q.y; pv[2] = q.z; pv[3] = q.w;
+                if constexpr (OP != OP_SUM) {
+                    const int4 r = __ldcg(reinterpret_cast<const int4*>(p.part_arg + o));
+                    pa[0] = r.x; pa[1] = r.y; pa[2] = r.z; pa[3] = r.w;
+                }
+            } else {
+                pv[0] = __ldcg(p.part_val + o);
+                if constexpr (OP != OP_SUM) pa[0] = __ldcg(p.part_arg + o);
+            }
+#pragma unroll
+            for (int v = 0; v < VEC; ++v) {
+                if constexpr (OP == OP_SUM) {
+                    macc[v] += pv[v];
+                } else {
+                    // segments are in increasing edge order: strict compare keeps the first
+                    if (better<OP>(pv[v], macc[v])) { macc[v] = pv[v]; marg[v] = pa[v]; }
+                }
+            }
+        }
+        finalize_store<OP, VEC>(p, row, re - rb, koff[j], macc, marg);
+    }
+}
+
+// ------------------------------------------------------------------------------------
 // main kernel: one warp = one row segment x one K tile
 // ------------------------------------------------------------------------------------
 // PARTIAL: some lanes of the widest K tile fall outside [k0, kend) (K = 100, 200, 47 ...).
@@ -361,105 +480,154 @@ spmm_seg_kernel(const __grid_constant__ SpmmParams p) {
         }
     }
 
-    // merge the NG lane groups (they hold interleaved entries of the same segment)
-    if constexpr (NG > 1) {
+    finish_item<OP, VEC, G, LPL>(p, lane, row, eb, ee, slot_id, koff, kok, acc, arg);
+}
+
+// ------------------------------------------------------------------------------------
+// bulk-copy gather variant: the dense rows are fetched by the TMA engine
+// (cp.async.bulk global -> shared, completion on an mbarrier) instead of by LDG into registers.
+// Every lane issues the bulk copy of ONE row (no address math or data registers per 16 bytes),
+// SE rows per stage and STAGES stages per warp are in flight -- bytes in flight are bounded by
+// shared memory (24-48 KB per warp), not by registers -- and the FMA / compare loop reads the
+// rows back with conflict-free LDS.128.  Warp-private ring: no __syncthreads, each warp owns
+// its stage buffers and its mbarriers.  Same work items, same finish_item as the LDG kernel.
+// ------------------------------------------------------------------------------------
+__device__ __forceinline__ unsigned smem_u32(const void* ptr) { return (unsigned)__cvta_generic_to_shared(ptr); }
+__device__ __forceinline__ void mbar_init(unsigned bar, unsigned count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive_expect_tx(unsigned bar, unsigned bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ bool mbar_try_wait(unsigned bar, unsigned parity) {
+    unsigned ok;
+    asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
+                 : "=r"(ok) : "r"(bar), "r"(parity) : "memory");
+    return ok != 0;
+}
+__device__ __forceinline__ void bulk_g2s(unsigned dst, const void* src, unsigned bytes, unsigned bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                 ::"r"(dst), "l"(src), "r"(bytes), "r"(bar) : "memory");
+}
+
+constexpr int kBulkSE = 16;   // rows (entries) per stage
+
+template <int OP, int G, int LPL, int STAGES>
+__global__ void __launch_bounds__(256)
+spmm_bulk_kernel(const __grid_constant__ SpmmParams p) {
+    constexpr int VEC = 4;
+    constexpr int NG = 32 / G;
+    constexpr int SE = kBulkSE;
+    constexpr int ROW_STRIDE = G * LPL * 16;          // bytes of one staged row slot
+    constexpr int STAGE_BYTES = SE * ROW_STRIDE;
+    constexpr unsigned FULL = 0xffffffffu;
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+
+    const int lane = threadIdx.x & 31;
+    const int wib = threadIdx.x >> 5;
+    const int nwarps = blockDim.x >> 5;
+    const int item = blockIdx.x * nwarps + wib;
+    if (item >= p.num_items) return;
+
+    unsigned char* my = smem_raw + (size_t)wib * (STAGES * STAGE_BYTES);
+    unsigned long long* bars = reinterpret_cast<unsigned long long*>(smem_raw + (size_t)nwarps * (STAGES * STAGE_BYTES)) + wib * STAGES;
+    const unsigned buf0 = smem_u32(my);
+    const unsigned bar0 = smem_u32(bars);
+    if (lane == 0) {
 #pragma unroll
-        for (int off = G; off < 32; off <<= 1) {
+        for (int i = 0; i < STAGES; ++i) mbar_init(bar0 + 8u * i, 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncwarp();
+
+    const int4 desc = __ldg(p.item_desc + item);
+    const int row = desc.x, eb = desc.y, ee = desc.z, slot_id = desc.w;
+    const int g = lane / G, lg = lane % G;
+    const int k0 = blockIdx.y * p.tile_w;
+    const int keff = (p.k + 3) & ~3;
+    const int kend = min(keff, k0 + p.tile_w);
+    const unsigned row_bytes = (unsigned)(kend - k0) * 4u;
+
+    int koff[LPL];
+    bool kok[LPL];
 #pragma unroll
-            for (int j = 0; j < LPL; ++j)
+    for (int j = 0; j < LPL; ++j) { koff[j] = k0 + (lg + j * G) * VEC; kok[j] = koff[j] < kend; }
+    float acc[LPL][VEC];
+    int arg[LPL][VEC];
 #pragma unroll
-                for (int v = 0; v < VEC; ++v) {
-                    const float ov = __shfl_xor_sync(FULL, acc[j][v], off);
-                    if constexpr (OP == OP_SUM) {
-                        acc[j][v] += ov;
-                    } else {
-                        const int oa = __shfl_xor_sync(FULL, arg[j][v], off);
-                        if (better_lex<OP, int>(ov, oa, acc[j][v], arg[j][v])) { acc[j][v] = ov; arg[j][v] = oa; }
+    for (int j = 0; j < LPL; ++j)
+#pragma unroll
+        for (int v = 0; v < VEC; ++v) { acc[j][v] = init_value<OP>(); arg[j][v] = kNoArg; }
+
+    const bool has_val = (p.val != nullptr);
+    const char* const xbase = reinterpret_cast<const char*>(p.x + k0);
+    const unsigned ldxb = (unsigned)p.ldx * 4u;
+    const int nstages = (ee - eb + SE - 1) / SE;
+    float a_reg[STAGES];
+
+    auto issue = [&](int s, int i) {
+        if (s >= nstages) return;
+        const int e0 = eb + s * SE;
+        const int cnt = min(SE, ee - e0);
+        unsigned c = 0;
+        a_reg[i] = 0.f;
+        if (lane < cnt) {
+            c = (unsigned)__ldcs(p.col + e0 + lane);
+            a_reg[i] = has_val ? __ldcs(p.val + e0 + lane) : 1.f;
+        }
+        if (lane == 0) mbar_arrive_expect_tx(bar0 + 8u * i, (unsigned)cnt * row_bytes);
+        __syncwarp();
+        if (lane < cnt)
+            bulk_g2s(buf0 + (unsigned)(i * STAGE_BYTES + lane * ROW_STRIDE), xbase + (unsigned long long)c * ldxb,
+                     row_bytes, bar0 + 8u * i);
+    };
+
+    // prologue: fill the ring
+#pragma unroll
+    for (int i = 0; i < STAGES; ++i) issue(i, i);
+
+    for (int base = 0; base < nstages; base += STAGES) {
+        const unsigned parity = (unsigned)((base / STAGES) & 1);
+#pragma unroll
+        for (int i = 0; i < STAGES; ++i) {
+            const int s = base + i;
+            if (s < nstages) {                      // warp-uniform
+                const int e0 = eb + s * SE;
+                const int cnt = min(SE, ee - e0);
+                while (!mbar_try_wait(bar0 + 8u * i, parity)) { }
+                const unsigned char* stage = my + i * STAGE_BYTES;
+#pragma unroll
+                for (int t = 0; t < SE; t += NG) {
+                    const int idx = t + g;
+                    const float a = __shfl_sync(FULL, a_reg[i], idx);
+                    if (idx < cnt) {
+                        const int e = e0 + idx;
+#pragma unroll
+                        for (int j = 0; j < LPL; ++j) {
+                            if (kok[j]) {
+                                const float4 q = *reinterpret_cast<const float4*>(stage + idx * ROW_STRIDE + (lg + j * G) * 16);
+                                const float xv[4] = {q.x, q.y, q.z, q.w};
+#pragma unroll
+                                for (int v = 0; v < VEC; ++v) {
+                                    if constexpr (OP == OP_SUM) {
+                                        acc[j][v] = fmaf(a, xv[v], acc[j][v]);
+                                    } else {
+                                        const float tt = __fmul_rn(a, xv[v]);
+                                        if (better<OP>(tt, acc[j][v])) { acc[j][v] = tt; arg[j][v] = e; }
+                                    }
+                                }
+                            }
+                        }
                     }
                 }
-        }
-    }
-    const bool writer = (NG == 1) || (g == 0);   // group 0 holds the merged result
-
-    if (slot_id < 0) {   // the row fits this one segment: its degree is ee - eb
-        if (writer) {
-#pragma unroll
-            for (int j = 0; j < LPL; ++j)
-                if (kok[j]) finalize_store<OP, VEC>(p, row, ee - eb, koff[j], acc[j], arg[j]);
-        }
-        return;
-    }
-
-    // ---- split row: publish this segment's partial; the LAST segment warp to arrive merges
-    // all of the row's partials in segment order (the threadFenceReduction pattern: nobody
-    // waits, the order of the merge is fixed, so the result is deterministic and max/min/arg
-    // stay bit-exact) and finalises the row.  No second kernel launch.
-    const int pbase = __ldg(p.part_off + row);
-    const int nseg = __ldg(p.seg_off + row + 1) - __ldg(p.seg_off + row);
-    const int rb = __ldg(p.rowptr + row), re = __ldg(p.rowptr + row + 1);
-    if (writer) {
-        const size_t slot = (size_t)slot_id;
-#pragma unroll
-        for (int j = 0; j < LPL; ++j) {
-            if (kok[j]) {
-                const size_t o = slot * (size_t)p.kp + (size_t)koff[j];
-                if constexpr (VEC == 4) {
-                    __stcg(reinterpret_cast<float4*>(p.part_val + o), make_float4(acc[j][0], acc[j][1], acc[j][2], acc[j][3]));
-                    if constexpr (OP != OP_SUM)
-                        __stcg(reinterpret_cast<int4*>(p.part_arg + o), make_int4(arg[j][0], arg[j][1], arg[j][2], arg[j][3]));
-                } else {
-                    __stcg(p.part_val + o, acc[j][0]);
-                    if constexpr (OP != OP_SUM) __stcg(p.part_arg + o, arg[j][0]);
-                }
+                // every lane is done reading this stage before the TMA engine may overwrite it
+                __syncwarp();
+                asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+                issue(s + STAGES, i);
             }
         }
     }
-    __threadfence();
-    __syncwarp();
-    int* const ticket_ptr = p.row_ticket + (size_t)blockIdx.y * (size_t)p.ticket_stride + (pbase >> 1);
-    int ticket = 0;
-    if (lane == 0) ticket = atomicAdd(ticket_ptr, 1);
-    ticket = __shfl_sync(FULL, ticket, 0);
-    if (ticket != nseg - 1) return;
-    __threadfence();
-    if (lane == 0) *ticket_ptr = 0;   // leave the counters zeroed for the next launch
-    if (!writer) return;
-#pragma unroll
-    for (int j = 0; j < LPL; ++j) {
-        if (!kok[j]) continue;
-        float macc[VEC];
-        int marg[VEC];
-#pragma unroll
-        for (int v = 0; v < VEC; ++v) { macc[v] = init_value<OP>(); marg[v] = kNoArg; }
-        const size_t o0 = (size_t)pbase * (size_t)p.kp + (size_t)koff[j];
-#pragma unroll 4
-        for (int t = 0; t < nseg; ++t) {
-            const size_t o = o0 + (size_t)t * (size_t)p.kp;
-            float pv[VEC];
-            int pa[VEC];
-            if constexpr (VEC == 4) {
-                const float4 q = __ldcg(reinterpret_cast<const float4*>(p.part_val + o));
-                pv[0] = q.x; pv[1] = q.y; pv[2] = q.z; pv[3] = q.w;
-                if constexpr (OP != OP_SUM) {
-                    const int4 r = __ldcg(reinterpret_cast<const int4*>(p.part_arg + o));
-                    pa[0] = r.x; pa[1] = r.y; pa[2] = r.z; pa[3] = r.w;
-                }
-            } else {
-                pv[0] = __ldcg(p.part_val + o);
-                if constexpr (OP != OP_SUM) pa[0] = __ldcg(p.part_arg + o);
-            }
-#pragma unroll
-            for (int v = 0; v < VEC; ++v) {
-                if constexpr (OP == OP_SUM) {
-                    macc[v] += pv[v];
-                } else {
-                    // segments are in increasing edge order: strict compare keeps the first
-                    if (better<OP>(pv[v], macc[v])) { macc[v] = pv[v]; marg[v] = pa[v]; }
-                }
-            }
-        }
-        finalize_store<OP, VEC>(p, row, re - rb, koff[j], macc, marg);
-    }
+    finish_item<OP, VEC, G, LPL>(p, lane, row, eb, ee, slot_id, koff, kok, acc, arg);
 }
 
 // ------------------------------------------------------------------------------------
@@ -527,12 +695,40 @@ static SegKernel pick_kernel(const TileShape& t, int u, bool partial) {
     return nullptr;
 }
 
+template <int OP, int G, int LPL>
+static SegKernel pick_bulk_stages(int stages) {
+    (void)stages;
+    return spmm_bulk_kernel<OP, G, LPL, 3>;
+}
+
+template <int OP>
+static SegKernel pick_bulk_kernel(const TileShape& t, int stages) {
+    if (t.vec != 4) return nullptr;
+    if (t.g == 8 && t.lpl == 1) return pick_bulk_stages<OP, 8, 1>(stages);
+    if (t.g == 16 && t.lpl == 1) return pick_bulk_stages<OP, 16, 1>(stages);
+    if (t.g == 32 && t.lpl == 1) return pick_bulk_stages<OP, 32, 1>(stages);
+    if (t.g == 32 && t.lpl == 2) return pick_bulk_stages<OP, 32, 2>(stages);
+    if (t.g == 32 && t.lpl == 4) return pick_bulk_stages<OP, 32, 4>(stages);
+    return nullptr;
+}
+
+static size_t bulk_smem_bytes(const TileShape& t, int warps, int stages) {
+    return (size_t)warps * stages * kBulkSE * (size_t)(t.g * t.lpl * 16) + (size_t)warps * stages * 8 + 16;
+}
+constexpr size_t kMaxDynSmem = 227 * 1024;
+
 bool spmm_variant_supported(int variant, int reduce, int64_t k, int64_t ldx, int64_t ldo,
                             const void* x, const void* out) {
     const VariantDesc* d = variant_desc(variant);
     if (!d || reduce < 0 || reduce > 3 || k <= 0) return false;
     (void)ldo; (void)out;
     const int vec = pick_vec(k, ldx, x);
+    if (d->method == 1) {
+        // bulk copies need 16-byte aligned rows and sizes, and the ring must fit shared memory
+        if (vec != 4) return false;
+        const TileShape t = pick_shape(vec, k, d->kt);
+        if (bulk_smem_bytes(t, d->warps, d->unroll) > kMaxDynSmem) return false;
+    }
     if (d->kt > 0) {
         if (d->kt >= k) return false;            // same as kfull: do not time it twice
         if (vec == 4 && d->kt % 4 != 0) return false;
@@ -585,9 +781,21 @@ int launch_spmm(int reduce, const SpmmParams& base, int64_t nnz, int variant, cu
     // every tile (incl. the last one) fills all G*LPL vector slots of a lane group?
     const bool partial = (t.tile_w != t.g * t.lpl * t.vec) || (keff % t.tile_w != 0);
     SegKernel kern = nullptr;
-    if (op == OP_SUM) kern = pick_kernel<OP_SUM>(t, d->unroll, partial);
-    else if (op == OP_MAX) kern = pick_kernel<OP_MAX>(t, d->unroll, partial);
-    else kern = pick_kernel<OP_MIN>(t, d->unroll, partial);
+    size_t smem = 0;
+    if (d->method == 1) {
+        if (op == OP_SUM) kern = pick_bulk_kernel<OP_SUM>(t, d->unroll);
+        else if (op == OP_MAX) kern = pick_bulk_kernel<OP_MAX>(t, d->unroll);
+        else kern = pick_bulk_kernel<OP_MIN>(t, d->unroll);
+        if (!kern) return ISPLIB_NO_OPT_IMPL;
+        smem = bulk_smem_bytes(t, d->warps, d->unroll);
+        if (smem > kMaxDynSmem) return ISPLIB_NO_OPT_IMPL;
+        if (smem > 48 * 1024)
+            ISPLIB_CUDA_TRY(cudaFuncSetAttribute((const void*)kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    } else {
+        if (op == OP_SUM) kern = pick_kernel<OP_SUM>(t, d->unroll, partial);
+        else if (op == OP_MAX) kern = pick_kernel<OP_MAX>(t, d->unroll, partial);
+        else kern = pick_kernel<OP_MIN>(t, d->unroll, partial);
+    }
     if (!kern) return ISPLIB_NO_OPT_IMPL;
 
     const int warps = d->warps;
@@ -600,7 +808,7 @@ int launch_spmm(int reduce, const SpmmParams& base, int64_t nnz, int variant, cu
         if ((size_t)t.ntiles * (size_t)p.ticket_stride > (size_t)p.ticket_capacity) return ISPLIB_NOT_ENOUGH_MEM;
         ISPLIB_CUDA_TRY(cudaMemsetAsync(p.row_ticket, 0, (size_t)t.ntiles * (size_t)p.ticket_stride * sizeof(int), stream));
     }
-    kern<<<grid, block, 0, stream>>>(p);
+    kern<<<grid, block, smem, stream>>>(p);
     ISPLIB_LAUNCH_CHECK();
 
     return ISPLIB_SUCCESS;
