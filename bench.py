@@ -51,6 +51,14 @@ def parse_args():
     return ap.parse_args()
 
 
+def workload_name(shape, reduce, k):
+    """Identical in both arms (ours / --impl reference)."""
+    from isplib_b200 import synth
+    m, nnz, law, param = synth.SHAPES[shape]
+    return (f"{shape}-shape SpMM-{reduce} forward, K={k}, fp32 values, {m} nodes, {nnz} nnz "
+            f"(synthetic {law} degrees, uniform columns, seed 0)")
+
+
 def peaks():
     """(hbm_gbs, source) -- MEASURED_PEAKS.json if the driver wrote it, else the recipe's fallback."""
     p = os.path.join(ROOT, "MEASURED_PEAKS.json")
@@ -181,8 +189,8 @@ def run_reference(args):
         "impl": "reference", "metric": "spmm_sum_effective_gbs", "value": round(val, 3), "unit": "GB/s",
         "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": round(dt * 1e3, 3),
         "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": f"{args.shape}-shape SpMM-{args.reduce} K={K} fp32 (int64 CSR, CPU)", "sample": sample,
-                   "impl": impl_desc},
+        "config": {"workload": workload_name(args.shape, args.reduce, K), "sample": sample, "impl": impl_desc,
+                   "index_dtype": "int64 (the reference's)"},
         "cpu_baseline": {"value": round(val, 3), "unit": "GB/s", "cores": cores, "kind": kind, "sample": sample},
         "e2e": {"value": round(val, 3), "unit": "GB/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gflops": round(2.0 * g.nnz * K / dt / 1e9, 2),
@@ -397,6 +405,37 @@ def run_ours(args):
                        "separate streams (prefetching loop), `serial_*` is the same on one stream; adjacency resident "
                        "on the device (uploaded once per graph, as the plugin caches per graph)"}
         del adj
+    else:
+        # N > 1: every rank copies ITS row slice of X from pinned host memory, runs the
+        # row-partitioned forward (all-gather + SpMM) and copies its slice of the result back
+        from isplib_b200.dist import DistSpMM  # noqa: F401  (same operator as the timed loop)
+        x_host = [s_.cpu().pin_memory() for s_ in slices]
+        out_host = torch.empty((op.R, K), dtype=torch.float32).pin_memory()
+
+        def e2e_step(i):
+            xd = x_host[i & 1].to(dev, non_blocking=True)
+            o, _ = op.forward(xd, reduce)
+            out_host.copy_(o, non_blocking=True)
+        for i in range(3):
+            e2e_step(i)
+        barrier()
+        n_e2e = max(4, min(args.steps, 20))
+        a0, a1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a0.record()
+        for i in range(n_e2e):
+            e2e_step(i)
+        a1.record()
+        barrier()
+        ms_e2e = a0.elapsed_time(a1) / n_e2e
+        t = torch.tensor([ms_e2e], device=dev, dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms_e2e = float(t.item())
+        e2e = {"value": round(b_alg / (ms_e2e * 1e-3) / 1e9, 2), "unit": "GB/s",
+               "h2d_bytes_per_step": world * op.Rc * K * 4, "d2h_bytes_per_step": world * op.R * K * 4,
+               "ms_per_step": round(ms_e2e, 3),
+               "path": "isplib_b200.dist.RowPartitionedSpMM.forward per rank: X row slice from pinned host memory -> "
+                       "NCCL all-gather + local/remote block SpMM -> result slice back to pinned host memory, every "
+                       "step, one stream per rank; max over ranks"}
 
     # --- secondary: the other half of BASELINE.json's metric, a 2-layer GCN training epoch
     # (hidden 256) on the ogbn-products-shaped graph via patch_pyg(), same N GPUs ---------------
@@ -435,8 +474,7 @@ def run_ours(args):
         "metric": "spmm_sum_effective_gbs", "value": round(value, 2), "unit": "GB/s", "n_gpus": world,
         "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": round(ms_step, 4),
         "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": f"{args.shape}-shape SpMM-{reduce} K={K} fp32, int32 CSR, {M} nodes, {nnz} nnz "
-                               f"(synthetic log-normal degrees, uniform columns, seed 0)",
+        "config": {"workload": workload_name(args.shape, reduce, K), "index_dtype": "int32 (narrowed once per graph)",
                    "reduce": reduce, "K": K, "variant": variant_name, "max_degree": g_max_degree,
                    "degree_gini": round(g_gini, 3),
                    "l2": "inputs 1.04 GB (col+val+X) > 126 MB L2 and two X buffers rotated between steps; no flush",
