@@ -435,3 +435,43 @@ def test_ops_are_cuda_graph_capturable(isplib):
     torch.cuda.synchronize()
     assert torch.equal(out, ref_out) and torch.equal(mx, ref_mx)
     torch.testing.assert_close(x.grad, ref_grad, rtol=1e-5, atol=1e-6)
+
+
+def test_ops_from_concurrent_threads_and_streams(isplib, oracle):
+    """The op layer is called from the Python thread (forward) and from autograd worker
+    threads (backward) in real training (SURVEY 8b 'Threading'): hammer it from 4 threads, each
+    on its own CUDA stream, two graphs shared between them."""
+    import threading
+    from isplib_b200 import synth
+    graphs = [synth.make_graph(700, 25_000, law="lognormal", param=1.1, values="uniform", seed=s).to(DEV) for s in (1, 2)]
+    K = 32
+    x = torch.randn(700, K, device=DEV)
+    refs = []
+    for g in graphs:
+        r, _ = oracle.spmm_c(g.rowptr.cpu().numpy(), g.col.cpu().numpy(), g.value.cpu().numpy(), x.cpu().numpy(), oracle.MAX)
+        refs.append(torch.from_numpy(r).to(DEV))
+    errors = []
+
+    def worker(tid):
+        try:
+            stream = torch.cuda.Stream()
+            with torch.cuda.stream(stream):
+                for it in range(20):
+                    g = graphs[(tid + it) % 2]
+                    xr = x.clone().requires_grad_(True)
+                    out, _ = torch.ops.isplib.fusedmm_spmm_max(g.rowptr, g.col, g.value, xr)
+                    s = torch.ops.isplib.fusedmm_spmm(None, g.rowptr, g.col, g.value, None, None, xr, None, None)
+                    (out.sum() + s.sum()).backward()
+                    if not torch.equal(out.detach(), refs[(tid + it) % 2]):
+                        errors.append((tid, it, "mismatch"))
+            stream.synchronize()
+        except Exception as ex:   # noqa: BLE001
+            errors.append((tid, repr(ex)))
+
+    threads = [threading.Thread(target=worker, args=(t,)) for t in range(4)]
+    for t in threads:
+        t.start()
+    for t in threads:
+        t.join()
+    torch.cuda.synchronize()
+    assert not errors, errors[:3]
