@@ -289,7 +289,7 @@ def run_ours(args):
         def step(i):
             op.forward(slices[i & 1], reduce)
         step(0)
-        launches_per_step = op.launches_per_forward()
+        launches_per_step = op.launches_per_forward() * len(op._k_chunks(K))
         variant_name = "auto" if args.variant is None else capi.variant_names()[args.variant]
         tune = {}
 
@@ -507,9 +507,31 @@ def run_ours(args):
 
 def main():
     args = parse_args()
-    if args.impl == "reference":
-        return run_reference(args)
-    return run_ours(args)
+    # Native libraries (NCCL's version banner) write to fd 1; the contract is ONE JSON line on
+    # stdout, so fd 1 points at stderr while the benchmark runs and is restored for the line.
+    sys.stdout.flush()
+    real_stdout = os.dup(1)
+    os.dup2(2, 1)
+    lines = []
+    orig_print = print
+
+    def capture(*a, **k):
+        if k.get("file") in (None, sys.stdout) and a and isinstance(a[0], str) and a[0].startswith("{"):
+            lines.append(a[0])
+        else:
+            orig_print(*a, **k)
+    import builtins
+    builtins.print = capture
+    try:
+        rc = run_reference(args) if args.impl == "reference" else run_ours(args)
+    finally:
+        builtins.print = orig_print
+        sys.stdout.flush()
+        os.dup2(real_stdout, 1)
+        os.close(real_stdout)
+    for l in lines:
+        print(l, flush=True)
+    return rc
 
 
 if __name__ == "__main__":
