@@ -1,0 +1,60 @@
+"""Locality reordering of the graph around the hot path.
+
+The reference's "autotuner" exists to pick a CPU-friendly feature width
+(/root/reference/autotuner/findbestk.py) and its loaders pad features to multiples of 16
+(/root/reference/tests/cpu/dataset_loader.py:145-160).  On B200 the K side is handled inside
+the op layer (rows padded to 16 bytes, on-device variant selection); what is left to the data
+side is the ORDER of the nodes: the SpMM is bound by gathers of X rows, and a node order that
+keeps a row's neighbours close together turns L2 misses into L2/L1 hits.
+
+    perm = reverse_cuthill_mckee(adj)            # or degree_order(adj), or any permutation
+    adj_p = permute(adj, perm)                   # P A P^T
+    out_p = torch_sparse.matmul(adj_p, x[perm])  # == (A x)[perm]
+
+Symmetric permutations commute with the SpMM, so training is unchanged up to the fixed
+relabelling of nodes (features, labels and masks are indexed with the same ``perm``).
+"""
+from __future__ import annotations
+
+import sys
+
+import numpy as np
+import torch
+
+
+def _st():
+    import isplib_b200  # noqa: F401
+    return sys.modules["torch_sparse"].SparseTensor
+
+
+def degree_order(adj, descending: bool = True) -> torch.Tensor:
+    """Nodes sorted by degree: hubs first -- the rows every other row gathers share cache lines."""
+    deg = adj.storage.rowcount()
+    return torch.argsort(deg, descending=descending, stable=True)
+
+
+def reverse_cuthill_mckee(adj) -> torch.Tensor:
+    """Bandwidth-reducing order (scipy's RCM on the symmetrised pattern; host side, one-time)."""
+    import scipy.sparse as sp
+    from scipy.sparse.csgraph import reverse_cuthill_mckee as rcm
+    rowptr, col, _ = adj.csr()
+    m, n = adj.sparse_sizes()
+    assert m == n, "symmetric reordering needs a square adjacency"
+    a = sp.csr_matrix((np.ones(col.numel(), dtype=np.int8), col.cpu().numpy(), rowptr.cpu().numpy()), shape=(m, n))
+    perm = rcm((a + a.T).tocsr(), symmetric_mode=True)
+    return torch.from_numpy(np.ascontiguousarray(perm).astype(np.int64)).to(col.device)
+
+
+def permute(adj, perm: torch.Tensor):
+    """P A P^T: new node i is old node perm[i].  Built through the device COO->CSR path when the
+    graph lives on a GPU, with torch ops otherwise."""
+    row, col, val = adj.coo()
+    m, n = adj.sparse_sizes()
+    assert m == n and perm.numel() == m
+    inv = torch.empty_like(perm)
+    inv[perm] = torch.arange(m, device=perm.device, dtype=perm.dtype)
+    new_row, new_col = inv[row], inv[col]
+    if row.is_cuda:
+        from . import io
+        return io.from_edge_index(torch.stack([new_row, new_col]), val, m, n, device=row.device)
+    return _st()(row=new_row, col=new_col, value=val, sparse_sizes=(m, n))

@@ -147,3 +147,20 @@ def test_gcn_layer_orders_are_the_same_function():
     assert not a.aggregate_first and b.aggregate_first and gnn.GCNConv(12, 20).aggregate_first
     assert not gnn.GCNConv(20, 12).aggregate_first
     torch.testing.assert_close(a(x, adj), b(x, adj), rtol=1e-4, atol=1e-5)
+
+
+def test_reordering_commutes_with_spmm():
+    """(P A P^T)(P x) == P (A x): isplib_b200.reorder on the stock CPU matmul."""
+    import isplib_b200  # noqa: F401
+    from isplib_b200 import reorder, synth
+    g = synth.make_graph(200, 3000, values="uniform", seed=3)
+    adj = g.sparse_tensor()
+    x = torch.randn(g.n, 5)
+    ref = sys.modules["torch_sparse"].matmul(adj, x, "sum")
+    for perm in (reorder.degree_order(adj), reorder.reverse_cuthill_mckee(adj), torch.randperm(g.n)):
+        assert sorted(perm.tolist()) == list(range(g.n))
+        adj_p = reorder.permute(adj, perm)
+        out_p = sys.modules["torch_sparse"].matmul(adj_p, x[perm], "sum")
+        torch.testing.assert_close(out_p, ref[perm], rtol=1e-5, atol=1e-5)
+        mx = sys.modules["torch_sparse"].matmul(adj_p, x[perm], "max")
+        torch.testing.assert_close(mx, sys.modules["torch_sparse"].matmul(adj, x, "max")[perm])
