@@ -176,10 +176,16 @@ extern "C" int isplib_b200_spmm_autotune(int reduce, int64_t m, int64_t n, int64
     float best = FLT_MAX;
     int rc = ISPLIB_SUCCESS;
     const char* tb = getenv("ISPLIB_B200_TUNE_BULK");
+    const char* ta = getenv("ISPLIB_B200_TUNE_ALL");
     const bool tune_bulk = tb && tb[0] == '1';
+    const bool tune_all = ta && ta[0] == '1';
     for (int v = 0; v < nv && rc == ISPLIB_SUCCESS; ++v) {
         if (!spmm_variant_supported(v, reduce, k, ldx, ldo, x, out)) continue;
-        if (variant_desc(v)->method == 1 && !tune_bulk) continue;   // see the variant table
+        const VariantDesc* d = variant_desc(v);
+        if (d->method == 1 && !tune_bulk) continue;   // see the variant table
+        // default candidate set = the family that wins on every measured shape (U=4; 4 warps/CTA
+        // for every K tile, 8 warps only untiled); the rest only with ISPLIB_B200_TUNE_ALL=1
+        if (d->method == 0 && !tune_all && !(d->unroll == 4 && (d->warps == 4 || d->kt == 0))) continue;
         rc = launch_spmm(reduce, p, nnz, v, stream);  // warm-up
         if (rc) break;
         cudaEventRecord(e0, stream);

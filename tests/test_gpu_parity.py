@@ -440,3 +440,39 @@ def test_sddmm_matches_oracle(capi, oracle, K, mean):
         ap[:, :K] = ad
         got2 = capi.sddmm_csr(rp, co, ap[:, :K], xp[:, :K], plan, mean).cpu().numpy()
         assert_sum_close(got2, ref, cond)
+
+
+@pytest.mark.parametrize("K", [47, 64, 100, 128])
+def test_no_out_of_bounds_writes_canaries(capi, oracle, K):
+    """compute-sanitizer is not available on this pool, so out-of-bounds WRITES are caught with
+    canaries: out / arg_out live inside larger buffers whose guard rows and guard columns must
+    be untouched after every variant has run (split rows, partial tiles, scalar-store tail)."""
+    rng = np.random.default_rng(900 + K)
+    M, N = 97, 80
+    rowptr, col, val = random_csr(rng, M, N, 40, empty_prob=0.1, long_rows=[(0, 1200), (96, 700)])
+    mat = rng.standard_normal((N, K)).astype(np.float32)
+    rp, co, va, _ = to_dev(rowptr, col, val, mat)
+    Kp = (K + 3) // 4 * 4
+    xb = torch.full((N + 2, Kp + 4), 3.0, device=DEV)
+    xb[1:N + 1, :K] = torch.from_numpy(mat).to(DEV)
+    x = xb[1:N + 1, :K]
+    plan = capi.Plan(rp, co.numel(), 256)
+    L = capi.lib()
+    for reduce in ("sum", "max"):
+        code = capi.REDUCE_CODE[reduce]
+        ref, ref_arg = oracle.spmm_c(rowptr, col, val, mat, code)
+        for v in range(L.isplib_b200_variant_count()):
+            if not L.isplib_b200_variant_supported(v, code, K, x.stride(0), Kp + 4, x.data_ptr(), x.data_ptr()):
+                continue
+            ob = torch.full((M + 2, Kp + 4), 7.0, device=DEV)
+            ab = torch.full((M + 2, Kp + 4), -5, dtype=torch.int64, device=DEV)
+            out, arg = capi.spmm_csr(reduce, rp, co, va, x, plan, v, out=ob[1:M + 1, :K],
+                                     arg_out=ab[1:M + 1, :K] if reduce == "max" else None)
+            torch.cuda.synchronize()
+            name = capi.variant_names()[v]
+            assert (ob[0] == 7).all() and (ob[M + 1] == 7).all() and (ob[:, K:] == 7).all(), name
+            if reduce == "max":
+                assert (ab[0] == -5).all() and (ab[M + 1] == -5).all() and (ab[:, K:] == -5).all(), name
+                assert np.array_equal(out.cpu().numpy(), ref) and np.array_equal(arg.cpu().numpy(), ref_arg), name
+            else:
+                assert_sum_close(out.cpu().numpy(), ref, abs_product_sum(rowptr, col, val, mat))

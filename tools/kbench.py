@@ -25,7 +25,11 @@ def main():
     ap.add_argument("--scale", type=float, default=1.0)
     ap.add_argument("--json", default=None)
     ap.add_argument("--bwd", action="store_true", help="also time the backward (A^T SpMM / arg scatter)")
+    ap.add_argument("--all", action="store_true", help="time every variant, not only the default candidate set")
     a = ap.parse_args()
+    if a.all:
+        os.environ["ISPLIB_B200_TUNE_ALL"] = "1"
+        os.environ["ISPLIB_B200_TUNE_BULK"] = "1"
     dev = "cuda:0"
     g = synth.make_graph(a.shape, values=None if a.novalue else "uniform", seed=0, device=dev, scale=a.scale)
     rp, co = capi.narrow_i64_to_i32(g.rowptr), capi.narrow_i64_to_i32(g.col)
