@@ -51,6 +51,12 @@ def parse_args():
     return ap.parse_args()
 
 
+# dram__bytes_read.sum + dram__bytes_write.sum per launch from the committed `ncu --set full`
+# capture of this very command (profiles/r1_full_spmm_seg_sum_k128_w4u4kt64.txt); null for
+# configurations that were not captured.
+NCU_TRAFFIC_BYTES = {("reddit", 128, "sum", "seg/w4/u4/kt64"): 5_251_204_000 + 263_436_800}
+
+
 def workload_name(shape, reduce, k):
     """Identical in both arms (ours / --impl reference)."""
     from isplib_b200 import synth
@@ -464,7 +470,8 @@ def run_ours(args):
 
     peak, peak_src = peaks()
     roofline = {"bound": "hbm", "achieved": round(value / world, 2) if world > 1 else round(value, 2), "peak": peak,
-                "unit": "GB/s", "frac": round((value / world) / peak, 4), "traffic": None,
+                "unit": "GB/s", "frac": round((value / world) / peak, 4),
+                "traffic": NCU_TRAFFIC_BYTES.get((args.shape, K, reduce, variant_name)) if world == 1 else None,
                 "kernel": "isplib::spmm_seg_kernel",
                 "peak_source": peak_src,
                 "algorithmic_bytes_per_launch": b_alg // world,
