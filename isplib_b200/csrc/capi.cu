@@ -94,9 +94,7 @@ static int fill_params(SpmmParams& p, int reduce, int64_t m, int64_t n, int64_t 
     p.arg_out = (long long*)arg_out;
     p.seg_off = (const int32_t*)(base + L.off_seg_off);
     p.part_off = (const int32_t*)(base + L.off_part_off);
-    p.item_row = (const int32_t*)(base + L.off_item_row);
     p.item_desc = (const int4*)(base + L.off_item_desc);
-    p.split_rows = (const int32_t*)(base + L.off_split_rows);
     p.part_val = part_val;
     p.part_arg = part_arg;
     p.row_ticket = row_ticket;

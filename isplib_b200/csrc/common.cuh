@@ -50,9 +50,9 @@ static inline WorkspaceLayout workspace_layout(int64_t num_split_items, int64_t 
 static inline size_t align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
 
 // ---- plan layout inside the caller's device buffer ---------------------------------
-// [counters: 8 x int64][seg_off: m+1][part_off: m+1][item_row: wmax][item_desc: wmax x int4][split_rows: m][temp...]
+// [counters: 8 x int64][seg_off: m+1][part_off: m+1][item_desc: wmax x int4][temp...]
 struct PlanLayout {
-    size_t off_counters, off_seg_off, off_part_off, off_item_row, off_item_desc, off_split_rows, off_temp;
+    size_t off_counters, off_seg_off, off_part_off, off_item_desc, off_temp;
     size_t persistent_bytes;  // everything the SpMM kernels read
     int64_t wmax;
 };
@@ -72,9 +72,7 @@ static inline PlanLayout plan_layout(int64_t m, int64_t nnz, int32_t seg_len) {
     L.off_counters = o;   o = align_up(o + 8 * sizeof(int64_t), 256);
     L.off_seg_off = o;    o = align_up(o + (size_t)(m + 1) * 4, 256);
     L.off_part_off = o;   o = align_up(o + (size_t)(m + 1) * 4, 256);
-    L.off_item_row = o;   o = align_up(o + (size_t)L.wmax * 4, 256);
     L.off_item_desc = o;  o = align_up(o + (size_t)L.wmax * 16, 256);
-    L.off_split_rows = o; o = align_up(o + (size_t)(m > 0 ? m : 1) * 4, 256);
     L.persistent_bytes = o;
     L.off_temp = o;
     return L;
@@ -92,9 +90,7 @@ struct SpmmParams {
     long long* __restrict__ arg_out;    // nullable
     const int32_t* __restrict__ seg_off;
     const int32_t* __restrict__ part_off;
-    const int32_t* __restrict__ item_row;
     const int4* __restrict__ item_desc;   // {row, eb, ee, partial slot | -1} per work item
-    const int32_t* __restrict__ split_rows;
     float* __restrict__ part_val;       // [num_split_items, k]
     int32_t* __restrict__ part_arg;     // [num_split_items, k] (max/min)
     int* __restrict__ row_ticket;       // [ntiles, ticket_stride] arrival counters of split rows

@@ -49,10 +49,8 @@ __global__ void plan_count_kernel(int m, int seg_len, const int32_t* __restrict_
 __global__ void plan_fill_kernel(int m, int seg_len, const int32_t* __restrict__ rowptr,
                                  const int32_t* __restrict__ seg_off,
                                  const int32_t* __restrict__ part_off,
-                                 int32_t* __restrict__ item_row, int4* __restrict__ item_desc,
-                                 int32_t* __restrict__ split_rows,
-                                 unsigned long long* __restrict__ counters,
-                                 int32_t* __restrict__ split_cursor) {
+                                 int4* __restrict__ item_desc,
+                                 unsigned long long* __restrict__ counters) {
     const int row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
     const int lane = threadIdx.x & 31;
     if (row >= m) return;
@@ -61,12 +59,10 @@ __global__ void plan_fill_kernel(int m, int seg_len, const int32_t* __restrict__
     const int pb = part_off[row];
     for (int w = b + lane; w < e; w += 32) {
         const int s = w - b;
-        item_row[w] = row;
         const int eb = rb + s * seg_len;
         item_desc[w] = make_int4(row, eb, min(re, eb + seg_len), (e - b > 1) ? pb + s : -1);
     }
     if (lane == 0) {
-        if (e - b > 1) split_rows[atomicAdd(split_cursor, 1)] = row;
         if (row == m - 1) {
             counters[PC_ITEMS] = (unsigned long long)e;
             counters[PC_SPLIT_ITEMS] = (unsigned long long)part_off[m];
@@ -84,11 +80,10 @@ extern "C" int isplib_b200_plan_bytes(int64_t m, int64_t nnz, int32_t seg_len, s
     const PlanLayout L = plan_layout(m, nnz, seg_len);
     size_t scan_tmp = 0;
     cub::DeviceScan::ExclusiveSum(nullptr, scan_tmp, (const int32_t*)nullptr, (int32_t*)nullptr, (int)(m + 1));
-    // temp: seg_cnt[m+1], part_cnt[m+1], split cursor, cub scratch
+    // temp: seg_cnt[m+1], part_cnt[m+1], cub scratch
     size_t o = L.off_temp;
     o = align_up(o + (size_t)(m + 1) * 4, 256);
     o = align_up(o + (size_t)(m + 1) * 4, 256);
-    o = align_up(o + 256, 256);
     o = align_up(o + scan_tmp, 256);
     *bytes = o;
     return ISPLIB_SUCCESS;
@@ -111,18 +106,14 @@ extern "C" int isplib_b200_plan_build(int64_t m, int64_t nnz, const int32_t* row
     unsigned long long* counters = (unsigned long long*)(base + L.off_counters);
     int32_t* seg_off = (int32_t*)(base + L.off_seg_off);
     int32_t* part_off = (int32_t*)(base + L.off_part_off);
-    int32_t* item_row = (int32_t*)(base + L.off_item_row);
     int4* item_desc = (int4*)(base + L.off_item_desc);
-    int32_t* split_rows = (int32_t*)(base + L.off_split_rows);
     size_t o = L.off_temp;
     int32_t* seg_cnt = (int32_t*)(base + o);  o = align_up(o + (size_t)(m + 1) * 4, 256);
     int32_t* part_cnt = (int32_t*)(base + o); o = align_up(o + (size_t)(m + 1) * 4, 256);
-    int32_t* cursor = (int32_t*)(base + o);   o = align_up(o + 256, 256);
     void* scan_tmp = base + o;
     size_t scan_bytes = plan_dev_bytes - o;
 
     ISPLIB_CUDA_TRY(cudaMemsetAsync(counters, 0, 8 * sizeof(int64_t), stream));
-    ISPLIB_CUDA_TRY(cudaMemsetAsync(cursor, 0, 256, stream));
 
     const int threads = 256;
     const int blocks = (int)((m + 1 + threads - 1) / threads);
@@ -133,7 +124,7 @@ extern "C" int isplib_b200_plan_build(int64_t m, int64_t nnz, const int32_t* row
     if (m > 0) {
         const int wpb = 8;
         plan_fill_kernel<<<(int)((m + wpb - 1) / wpb), wpb * 32, 0, stream>>>(
-            (int)m, S, rowptr, seg_off, part_off, item_row, item_desc, split_rows, counters, cursor);
+            (int)m, S, rowptr, seg_off, part_off, item_desc, counters);
         ISPLIB_LAUNCH_CHECK();
     }
     unsigned long long h[8] = {0};

@@ -24,8 +24,7 @@ struct SddmmParams {
     const float* __restrict__ a;      // [m, k]
     const float* __restrict__ x;      // [n, k]
     float* __restrict__ out;          // [nnz]
-    const int32_t* __restrict__ seg_off;
-    const int32_t* __restrict__ item_row;
+    const int4* __restrict__ item_desc;   // {row, eb, ee, .} per work item (the forward's plan)
     long long lda, ldx;
     int k, num_items, seg_len, mean_scale;
 };
@@ -53,14 +52,12 @@ sddmm_seg_kernel(const __grid_constant__ SddmmParams p) {
     const int lane = threadIdx.x & 31;
     const int item = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
     if (item >= p.num_items) return;
-    const int row = __ldg(p.item_row + item);
-    const int s = item - __ldg(p.seg_off + row);
-    const int rb = __ldg(p.rowptr + row), re = __ldg(p.rowptr + row + 1);
-    const int eb = rb + s * p.seg_len;
-    const int ee = min(re, eb + p.seg_len);
+    const int4 desc = __ldg(p.item_desc + item);
+    const int row = desc.x, eb = desc.y, ee = desc.z;
     if (eb >= ee) return;
     const int g = lane / G, lg = lane % G;
-    const float inv = p.mean_scale ? __fdiv_rn(1.f, (float)max(re - rb, 1)) : 1.f;
+    float inv = 1.f;
+    if (p.mean_scale) inv = __fdiv_rn(1.f, (float)max(__ldg(p.rowptr + row + 1) - __ldg(p.rowptr + row), 1));
     const unsigned ldxb = (unsigned)p.ldx * 4u;
     const int keff = (VEC == 4) ? ((p.k + 3) & ~3) : p.k;
     const float* arow = p.a + (size_t)row * (size_t)p.lda;
@@ -163,8 +160,7 @@ extern "C" int isplib_b200_sddmm_csr(int64_t m, int64_t n, int64_t k, int64_t nn
     const char* base = (const char*)plan_dev;
     SddmmParams p;
     p.rowptr = rowptr; p.col = col; p.a = a; p.x = x; p.out = out_val;
-    p.seg_off = (const int32_t*)(base + L.off_seg_off);
-    p.item_row = (const int32_t*)(base + L.off_item_row);
+    p.item_desc = (const int4*)(base + L.off_item_desc);
     p.lda = lda; p.ldx = ldx; p.k = (int)k; p.num_items = (int)info->num_items;
     p.seg_len = info->seg_len; p.mean_scale = mean_scale;
 

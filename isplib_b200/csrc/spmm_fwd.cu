@@ -149,7 +149,8 @@ __device__ __forceinline__ bool better_lex(float cand, IdT cand_id, float cur, I
 }
 
 // ------------------------------------------------------------------------------------
-// finalisation shared by the segment kernel (single-segment rows) and the fix-up kernel
+// finalisation of one vector of one output row: single-segment rows directly, split rows by
+// the last-arriving segment warp after the in-order merge
 // ------------------------------------------------------------------------------------
 template <int OP, int VEC>
 __device__ __forceinline__ void finalize_store(const SpmmParams& p, int row, int deg, int kk,
