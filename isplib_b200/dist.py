@@ -91,6 +91,36 @@ def split_row_block(rowptr: torch.Tensor, col: torch.Tensor, val: Optional[torch
     return local, remote, full_deg, R
 
 
+def split_row_block_by_owner(rowptr: torch.Tensor, col: torch.Tensor, val: Optional[torch.Tensor],
+                             rank: int, world: int, n_cols: int):
+    """Like split_row_block but one CSR block PER COLUMN OWNER q (columns rebased to q's slice),
+    for the per-source pipelined gather.  Returns (blocks[world], row_degree, R)."""
+    m = rowptr.numel() - 1
+    R = rows_per_rank(m, world)
+    Rc = rows_per_rank(n_cols, world)
+    r0, r1 = min(rank * R, m), min((rank + 1) * R, m)
+    e0, e1 = int(rowptr[r0]), int(rowptr[r1])
+    dev = col.device
+    sub_col = col[e0:e1]
+    sub_val = None if val is None else val[e0:e1]
+    eid = torch.arange(e0, e1, device=dev, dtype=torch.int64)
+    deg = (rowptr[r0 + 1:r1 + 1] - rowptr[r0:r1])
+    row = torch.repeat_interleave(torch.arange(r1 - r0, device=dev, dtype=torch.int64), deg)
+    owner = torch.div(sub_col, Rc, rounding_mode="floor")
+    blocks = []
+    for q in range(world):
+        mask = owner == q
+        cnt = torch.bincount(row[mask], minlength=R) if mask.numel() else torch.zeros(R, dtype=torch.int64, device=dev)
+        rp = torch.zeros(R + 1, dtype=torch.int64, device=dev)
+        rp[1:] = torch.cumsum(cnt, 0)
+        blocks.append(CsrBlock(rp.to(torch.int32), (sub_col[mask] - q * Rc).to(torch.int32),
+                               None if sub_val is None else sub_val[mask].contiguous(), eid[mask].to(torch.int32)))
+    full_deg = torch.zeros(R, dtype=torch.float32, device=dev)
+    full_deg[: r1 - r0] = deg.to(torch.float32)
+    full_deg.clamp_(min=1.0)
+    return blocks, full_deg, R
+
+
 def _cuda_block_spmm(reduce_code, block: CsrBlock, x, out, arg_out, flags, row_divisor, arg_sentinel, variant=-1):
     from . import capi
     if block.plan is None:
@@ -104,7 +134,8 @@ class RowPartitionedSpMM:
     """out_local = (A @ X)[own rows] with X given as this rank's row slice."""
 
     def __init__(self, rowptr: torch.Tensor, col: torch.Tensor, value: Optional[torch.Tensor], n_cols: int,
-                 group=None, device=None, block_spmm: Optional[Callable] = None, overlap: bool = True):
+                 group=None, device=None, block_spmm: Optional[Callable] = None, overlap: bool = True,
+                 pipelined: Optional[bool] = None):
         self.group = group
         self.world = dist.get_world_size(group) if dist.is_initialized() else 1
         self.rank = dist.get_rank(group) if dist.is_initialized() else 0
@@ -123,6 +154,15 @@ class RowPartitionedSpMM:
         self.row_degree = deg.to(self.device)
         self.comm_stream = torch.cuda.Stream(self.device) if (self.device.type == "cuda" and overlap) else None
         self.variant = -1
+        # per-source pipelined gather (copy-engine P2P over NVLink through symmetric memory, one
+        # SpMM per column owner as its slice lands): opt-in, or ISPLIB_B200_DIST_PIPELINED=1
+        if pipelined is None:
+            pipelined = os.environ.get("ISPLIB_B200_DIST_PIPELINED", "0") == "1"
+        self.pipelined = bool(pipelined) and self.world > 1 and self.device.type == "cuda"
+        self.owner_blocks = None
+        if self.pipelined:
+            blocks, _, _ = split_row_block_by_owner(rowptr, col, value, self.rank, self.world, self.n)
+            self.owner_blocks = [mv(b) for b in blocks]
         self.k_chunk = None        # feature-chunk width of the all-gather/SpMM pipeline (None = auto)
 
     # rows this rank owns (without padding)
@@ -160,6 +200,9 @@ class RowPartitionedSpMM:
             self.block_spmm(inner, self.local, x_slice, out, arg, 0, div, self.nnz, self.variant)
             return out, arg
 
+        if self.pipelined:
+            return self._forward_pipelined(x_slice, inner, div, out, arg)
+
         # K-chunk pipeline: the all-gather of feature chunk c+1 runs on the comm stream while the
         # SpMM of chunk c runs on the compute stream, so only the first chunk's transfer is
         # exposed; a 64-wide chunk is also the K tile that keeps an [N, 64] slab L2-resident.
@@ -186,6 +229,37 @@ class RowPartitionedSpMM:
         gathered = self._all_gather(x_slice)
         self.block_spmm(inner, self.local, x_slice, out, arg, 0, None, self.nnz, self.variant)
         self.block_spmm(inner, self.remote, gathered, out, arg, FLAG_ACCUMULATE, div, self.nnz, self.variant)
+        return out, arg
+
+    def _forward_pipelined(self, x_slice, inner, div, out, arg):
+        """X slices travel peer-to-peer over NVLink by the copy engines (torch symmetric memory,
+        no SMs taken from the SpMM); the column block of source rank q is multiplied as soon as
+        q's slice has landed, while the next slice is in flight.  The block kernels accumulate
+        into the same rows, so they are chained by events: the merge order is fixed (own block
+        first, then ring order) -> deterministic; max/min stay bit-identical to one GPU."""
+        import torch.distributed._symmetric_memory as symm
+        group = self.group if self.group is not None else dist.group.WORLD
+        gname = group.group_name
+        if not symm.is_symm_mem_enabled_for_group(gname):
+            symm.enable_symm_mem_for_group(gname)
+        K = x_slice.size(1)
+        ag_out = torch.empty((self.world * self.Rc, K), dtype=x_slice.dtype, device=x_slice.device)
+        last_src = (self.rank + self.world - 1) % self.world
+        state = {"prev": None}
+
+        def consumer(shard, src):
+            stream = torch.cuda.current_stream(x_slice.device)
+            if state["prev"] is not None:
+                stream.wait_event(state["prev"])
+            flags = 0 if src == self.rank else FLAG_ACCUMULATE
+            self.block_spmm(inner, self.owner_blocks[src], shard, out, arg, flags,
+                            div if src == last_src else None, self.nnz, self.variant)
+            ev = torch.cuda.Event()
+            ev.record(stream)
+            state["prev"] = ev
+
+        symm._pipelined_all_gather_and_consume(x_slice.contiguous(), consumer, ag_out, gname, ag_out_needed=False)
+        torch.cuda.current_stream(x_slice.device).wait_event(state["prev"])
         return out, arg
 
     def _k_chunks(self, K: int):
@@ -246,11 +320,11 @@ class DistSpMM:
     machinery as the forward), max/min through a local arg-scatter + reduce-scatter."""
 
     def __init__(self, rowptr, col, value, n_cols, group=None, device=None, block_spmm=None,
-                 arg_backward=None, overlap=True):
+                 arg_backward=None, overlap=True, pipelined=None):
         self.rowptr, self.col, self.value = rowptr, col, value
         self.m, self.n = rowptr.numel() - 1, int(n_cols)
         self.group, self.device = group, device
-        self._kw = dict(group=group, device=device, block_spmm=block_spmm, overlap=overlap)
+        self._kw = dict(group=group, device=device, block_spmm=block_spmm, overlap=overlap, pipelined=pipelined)
         self.fwd = RowPartitionedSpMM(rowptr, col, value, n_cols, **self._kw)
         self._bwd = {}
         self._arg_backward = arg_backward or _cuda_arg_backward

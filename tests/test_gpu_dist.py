@@ -14,7 +14,7 @@ pytestmark = pytest.mark.gpu
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 
 
-def worker(rank, world, port, results):
+def worker(rank, world, port, results, pipelined=False):
     sys.path.insert(0, ROOT)
     os.environ["MASTER_ADDR"] = "127.0.0.1"
     os.environ["MASTER_PORT"] = str(port)
@@ -30,7 +30,8 @@ def worker(rank, world, port, results):
         K = 32
         x = torch.randint(-3, 4, (g.n, K), generator=torch.Generator().manual_seed(1)).float()
         go = torch.randn(g.m, K, generator=torch.Generator().manual_seed(2))
-        op = DistSpMM(g.rowptr.to(dev), g.col.to(dev), val.to(dev), g.n, device=dev)
+        op = DistSpMM(g.rowptr.to(dev), g.col.to(dev), val.to(dev), g.n, device=dev, pipelined=pipelined)
+        assert op.fwd.pipelined == pipelined
         f = op.fwd
         r0, r1 = rank * f.R, min((rank + 1) * f.R, g.m)
         c0, c1 = rank * f.Rc, min((rank + 1) * f.Rc, g.n)
@@ -65,6 +66,19 @@ def test_row_partitioned_spmm_two_gpus_nccl():
     mgr = mp.Manager()
     results = mgr.dict()
     mp.spawn(worker, args=(2, 29650 + os.getpid() % 300, results), nprocs=2, join=True)
+    for rank in range(2):
+        bad = [k for k, v in results[rank].items() if not v]
+        assert not bad, f"rank {rank}: {bad}"
+
+
+def test_row_partitioned_spmm_two_gpus_pipelined_p2p():
+    """Same, with the per-source pipelined gather: X slices move peer-to-peer over NVLink by the
+    copy engines (torch symmetric memory) and each column-owner block is multiplied as it lands."""
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs 2 GPUs")
+    mgr = mp.Manager()
+    results = mgr.dict()
+    mp.spawn(worker, args=(2, 29950 + os.getpid() % 300, results, True), nprocs=2, join=True)
     for rank in range(2):
         bad = [k for k, v in results[rank].items() if not v]
         assert not bad, f"rank {rank}: {bad}"
