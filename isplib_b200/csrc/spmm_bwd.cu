@@ -15,19 +15,27 @@ namespace isplib {
 // + 16 B when the rows allow it); the scatter target row differs per element (that is the
 // operation), so the adds are fp32 RED atomics into L2.  All dependent gathers of a thread's
 // 4 elements (col[e], val[e], x[col[e]]) are issued together before the first atomic.
+//
+// K tiling (blockIdx.y, slowest): the atomics are read-modify-writes of 32-byte sectors of
+// grad_x at random rows; if grad_x does not fit L2 every one of them costs a DRAM sector read
+// and a write-back.  Sweeping one [n, kt] column slab at a time keeps the slab L2-resident, and
+// -- unlike in the forward -- narrow tiles are free here: arg / grad_out are still read exactly
+// once, just in kt-wide row pieces (>= 32 bytes).
 template <int V>
 __global__ void __launch_bounds__(256)
-arg_backward_kernel(long long m, int k, const int32_t* __restrict__ col,
+arg_backward_kernel(long long m, int k, int kt, const int32_t* __restrict__ col,
                     const float* __restrict__ val, const float* __restrict__ x, long long ldx,
                     const long long* __restrict__ arg, long long ld_arg, long long sentinel,
                     const float* __restrict__ grad_out, long long ldgo,
                     float* __restrict__ grad_x, long long ldgx, float* __restrict__ grad_val) {
-    const int kv = (k + V - 1) / V;                       // V-wide groups per row
+    const int k0 = blockIdx.y * kt;
+    const int kw = min(kt, k - k0);                       // width of this tile
+    const int kv = (kw + V - 1) / V;                      // V-wide groups per row in this tile
     const long long total = m * (long long)kv;
     for (long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x; t < total;
          t += (long long)gridDim.x * blockDim.x) {
         const long long i = t / kv;
-        const int kk = (int)(t - i * kv) * V;
+        const int kk = k0 + (int)(t - i * kv) * V;
         long long e[V];
         float g[V];
         if constexpr (V == 4) {
@@ -89,17 +97,30 @@ extern "C" int isplib_b200_spmm_arg_backward(int64_t m, int64_t n, int64_t k, in
     if (m == 0 || k == 0 || nnz == 0) return ISPLIB_SUCCESS;
     const bool v4 = (k % 4 == 0) && (ld_arg % 2 == 0) && (ldgo % 4 == 0) &&
                     ((reinterpret_cast<uintptr_t>(arg) & 15u) == 0) && ((reinterpret_cast<uintptr_t>(grad_out) & 15u) == 0);
-    const long long total = (long long)m * (v4 ? k / 4 : k);
+    // K tile: the widest power-of-two slab (>= 32 floats) whose [n, kt] slice of grad_x stays
+    // L2-resident; untiled when grad_x fits anyway or when no such slab exists.  Measured
+    // (B200): Reddit-shape K=256 1.32 -> 0.98 ms with 32-wide tiles; Amazon-shape K=200 would
+    // need 8-wide tiles and gets SLOWER (8.5 -> 12.0 ms), hence the 32-float floor.
+    int kt = (int)k;
+    if (grad_x && (double)n * (double)k * 4.0 > 64.0 * 1024 * 1024) {
+        kt = 256;
+        while (kt > 32 && (double)n * (double)kt * 4.0 > 48.0 * 1024 * 1024) kt >>= 1;
+        if (kt >= k || (double)n * (double)kt * 4.0 > 48.0 * 1024 * 1024) kt = (int)k;
+    }
+    const int ntiles = (int)((k + kt - 1) / kt);
+    if (ntiles > 65535) return ISPLIB_NO_OPT_IMPL;
+    const long long total = (long long)m * (v4 ? (kt + 3) / 4 : kt);
     long long blocks = (total + 255) / 256;
     const long long cap = (long long)kNumSMs * 8 * 32;  // grid-stride beyond 32 waves of 8 CTAs/SM
     if (blocks > cap) blocks = cap;
+    const dim3 grid((unsigned)blocks, (unsigned)ntiles);
     if (v4)
-        arg_backward_kernel<4><<<(unsigned)blocks, 256, 0, stream>>>(
-            (long long)m, (int)k, col, val, x, (long long)ldx, (const long long*)arg, (long long)ld_arg,
+        arg_backward_kernel<4><<<grid, 256, 0, stream>>>(
+            (long long)m, (int)k, kt, col, val, x, (long long)ldx, (const long long*)arg, (long long)ld_arg,
             (long long)arg_sentinel, grad_out, (long long)ldgo, grad_x, (long long)ldgx, grad_val);
     else
-        arg_backward_kernel<1><<<(unsigned)blocks, 256, 0, stream>>>(
-            (long long)m, (int)k, col, val, x, (long long)ldx, (const long long*)arg, (long long)ld_arg,
+        arg_backward_kernel<1><<<grid, 256, 0, stream>>>(
+            (long long)m, (int)k, kt, col, val, x, (long long)ldx, (const long long*)arg, (long long)ld_arg,
             (long long)arg_sentinel, grad_out, (long long)ldgo, grad_x, (long long)ldgx, grad_val);
     ISPLIB_LAUNCH_CHECK();
     return ISPLIB_SUCCESS;
