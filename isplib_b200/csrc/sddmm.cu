@@ -27,6 +27,7 @@ struct SddmmParams {
     const int4* __restrict__ item_desc;   // {row, eb, ee, .} per work item (the forward's plan)
     long long lda, ldx;
     int k, num_items, seg_len, mean_scale;
+    int accum;   // 1: add to out (second and later K tiles), 0: overwrite
 };
 
 template <int VEC>
@@ -44,7 +45,8 @@ template <int VEC, int G, int LPL>
 __global__ void __launch_bounds__(128)
 sddmm_seg_kernel(const __grid_constant__ SddmmParams p) {
     constexpr int NG = 32 / G;
-    constexpr int P = G;                 // entries per lane group per 32-entry chunk
+    constexpr int P = (G < 16) ? G : 16; // entries per lane group per sub-chunk (partials held per lane)
+    constexpr int SUB = 32 / (P * NG);   // sub-chunks per 32-entry index chunk
     constexpr int U = (P >= 4) ? 4 : P;  // gathers in flight
     constexpr int PASS_W = G * LPL * VEC;
     constexpr unsigned FULL = 0xffffffffu;
@@ -61,80 +63,123 @@ sddmm_seg_kernel(const __grid_constant__ SddmmParams p) {
     const unsigned ldxb = (unsigned)p.ldx * 4u;
     const int keff = (VEC == 4) ? ((p.k + 3) & ~3) : p.k;
     const float* arow = p.a + (size_t)row * (size_t)p.lda;
+    const bool single_pass = keff <= PASS_W;       // the whole a-row fits the lanes once: keep it in registers
 
+    float av[LPL][VEC];
+    int ko[LPL];
+    bool ok[LPL];
+    auto load_a = [&](int kp) {
+#pragma unroll
+        for (int j = 0; j < LPL; ++j) {
+            ko[j] = kp + (lg + j * G) * VEC;
+            ok[j] = ko[j] < keff;
+#pragma unroll
+            for (int q = 0; q < VEC; ++q) av[j][q] = 0.f;
+            if (ok[j]) {
+                if (VEC == 1 || ko[j] + VEC <= p.k) ld_vec<VEC>(arow + ko[j], av[j]);
+                else {
+#pragma unroll
+                    for (int q = 0; q < VEC; ++q) if (ko[j] + q < p.k) av[j][q] = __ldg(arow + ko[j] + q);
+                }
+            }
+            if (!ok[j]) ko[j] = 0;   // out-of-range lanes re-read the row's first vector (times 0)
+        }
+    };
+    if (single_pass) load_a(0);
+
+    unsigned c_next = (eb + lane < ee) ? (unsigned)__ldcs(p.col + eb + lane) : 0u;
     for (int e0 = eb; e0 < ee; e0 += 32) {
         const int cnt = min(32, ee - e0);
-        const unsigned c = (lane < cnt) ? (unsigned)__ldcs(p.col + e0 + lane) : 0u;
-        float part[P];
+        const unsigned c = c_next;
+        if (e0 + 32 + lane < ee) c_next = (unsigned)__ldcs(p.col + e0 + 32 + lane);   // next chunk's indices
 #pragma unroll
-        for (int v = 0; v < P; ++v) part[v] = 0.f;
+        for (int sc = 0; sc < SUB; ++sc) {
+            const int sbase = sc * P * NG;
+            if (sbase >= cnt) break;                       // warp-uniform
+            float part[P];
+#pragma unroll
+            for (int v = 0; v < P; ++v) part[v] = 0.f;
 
-        for (int kp = 0; kp < keff; kp += PASS_W) {
-            // this lane's slice of the a-row for this pass (zero outside K: a's padding is not ours)
-            float av[LPL][VEC];
-            int ko[LPL];
-            bool ok[LPL];
+            for (int kp = 0; kp < keff; kp += PASS_W) {
+                if (!single_pass) load_a(kp);
+                if (cnt - sbase >= P * NG) {
 #pragma unroll
-            for (int j = 0; j < LPL; ++j) {
-                ko[j] = kp + (lg + j * G) * VEC;
-                ok[j] = ko[j] < keff;
+                    for (int v0 = 0; v0 < P; v0 += U) {
+                        float xv[U][LPL][VEC];
 #pragma unroll
-                for (int q = 0; q < VEC; ++q) av[j][q] = 0.f;
-                if (ok[j]) {
-                    if (VEC == 1 || ko[j] + VEC <= p.k) ld_vec<VEC>(arow + ko[j], av[j]);
-                    else {
+                        for (int u = 0; u < U; ++u) {
+                            const unsigned cc = __shfl_sync(FULL, c, sbase + (v0 + u) * NG + g);
+                            const float* xr = reinterpret_cast<const float*>(reinterpret_cast<const char*>(p.x) + (unsigned long long)cc * ldxb);
 #pragma unroll
-                        for (int q = 0; q < VEC; ++q) if (ko[j] + q < p.k) av[j][q] = __ldg(arow + ko[j] + q);
-                    }
-                }
-            }
-#pragma unroll
-            for (int v0 = 0; v0 < P; v0 += U) {
-                float xv[U][LPL][VEC];
-#pragma unroll
-                for (int u = 0; u < U; ++u) {
-                    const int idx = (v0 + u) * NG + g;            // entry of the chunk this group handles
-                    const unsigned cc = __shfl_sync(FULL, c, idx);
-                    const char* xr = reinterpret_cast<const char*>(p.x) + (unsigned long long)cc * ldxb;
-#pragma unroll
-                    for (int j = 0; j < LPL; ++j) {
-                        // out-of-range lanes re-read the row's first vector (valid memory, product with 0)
-                        const int off = ok[j] ? ko[j] : 0;
-                        if (idx < cnt) {
-                            ld_vec<VEC>(reinterpret_cast<const float*>(xr) + off, xv[u][j]);
-                            if (VEC == 4 && ko[j] + VEC > p.k) {      // x's own padding may hold anything
-#pragma unroll
-                                for (int q = 0; q < VEC; ++q) if (ko[j] + q >= p.k) xv[u][j][q] = 0.f;
-                            }
-                        } else {
-#pragma unroll
-                            for (int q = 0; q < VEC; ++q) xv[u][j][q] = 0.f;
+                            for (int j = 0; j < LPL; ++j) ld_vec<VEC>(xr + ko[j], xv[u][j]);
                         }
+#pragma unroll
+                        for (int u = 0; u < U; ++u)
+#pragma unroll
+                            for (int j = 0; j < LPL; ++j) {
+                                // x's own padding (K % 4 != 0) may hold anything: mask it, do not multiply it
+                                if (VEC == 4 && ok[j] && ko[j] + VEC > p.k) {
+#pragma unroll
+                                    for (int q = 0; q < VEC; ++q) if (ko[j] + q >= p.k) xv[u][j][q] = 0.f;
+                                }
+#pragma unroll
+                                for (int q = 0; q < VEC; ++q) part[v0 + u] = fmaf(av[j][q], xv[u][j][q], part[v0 + u]);
+                            }
+                    }
+                } else {
+#pragma unroll
+                    for (int v0 = 0; v0 < P; v0 += U) {
+                        float xv[U][LPL][VEC];
+#pragma unroll
+                        for (int u = 0; u < U; ++u) {
+                            const int idx = sbase + (v0 + u) * NG + g;
+                            const unsigned cc = __shfl_sync(FULL, c, idx & 31);
+                            const float* xr = reinterpret_cast<const float*>(reinterpret_cast<const char*>(p.x) + (unsigned long long)cc * ldxb);
+#pragma unroll
+                            for (int j = 0; j < LPL; ++j) {
+                                if (idx < cnt) {
+                                    ld_vec<VEC>(xr + ko[j], xv[u][j]);
+                                    if (VEC == 4 && ok[j] && ko[j] + VEC > p.k) {
+#pragma unroll
+                                        for (int q = 0; q < VEC; ++q) if (ko[j] + q >= p.k) xv[u][j][q] = 0.f;
+                                    }
+                                } else {
+#pragma unroll
+                                    for (int q = 0; q < VEC; ++q) xv[u][j][q] = 0.f;
+                                }
+                            }
+                        }
+#pragma unroll
+                        for (int u = 0; u < U; ++u)
+#pragma unroll
+                            for (int j = 0; j < LPL; ++j)
+#pragma unroll
+                                for (int q = 0; q < VEC; ++q) part[v0 + u] = fmaf(av[j][q], xv[u][j][q], part[v0 + u]);
                     }
                 }
-#pragma unroll
-                for (int u = 0; u < U; ++u)
-#pragma unroll
-                    for (int j = 0; j < LPL; ++j)
-#pragma unroll
-                        for (int q = 0; q < VEC; ++q) part[v0 + u] = fmaf(av[j][q], xv[u][j][q], part[v0 + u]);
             }
-        }
 
-        // halving butterfly inside each lane group: P values on G lanes -> 1 value per lane;
-        // lane lg ends with the total of value index lg
+            // halving butterfly inside each lane group: P values -> 1 value per lane over the low
+            // lane bits, then plain adds over the remaining lane bits (G > P); lanes lg < P end
+            // with the total of value index lg
 #pragma unroll
-        for (int o = P / 2; o >= 1; o >>= 1) {
-            const bool hi = (lg & o) != 0;
+            for (int o = P / 2; o >= 1; o >>= 1) {
+                const bool hi = (lg & o) != 0;
 #pragma unroll
-            for (int h = 0; h < o; ++h) {
-                const float keep = hi ? part[h + o] : part[h];
-                const float send = hi ? part[h] : part[h + o];
-                part[h] = keep + __shfl_xor_sync(FULL, send, o);
+                for (int h = 0; h < o; ++h) {
+                    const float keep = hi ? part[h + o] : part[h];
+                    const float send = hi ? part[h] : part[h + o];
+                    part[h] = keep + __shfl_xor_sync(FULL, send, o);
+                }
+            }
+#pragma unroll
+            for (int o = P; o < G; o <<= 1) part[0] += __shfl_xor_sync(FULL, part[0], o);
+            const int idx = sbase + lg * NG + g;
+            if (lg < P && idx < cnt) {
+                const float r = part[0] * inv;
+                p.out[e0 + idx] = p.accum ? p.out[e0 + idx] + r : r;
             }
         }
-        const int idx = lg * NG + g;
-        if (idx < cnt) p.out[e0 + idx] = part[0] * inv;
     }
 }
 
@@ -164,21 +209,34 @@ extern "C" int isplib_b200_sddmm_csr(int64_t m, int64_t n, int64_t k, int64_t nn
     p.lda = lda; p.ldx = ldx; p.k = (int)k; p.num_items = (int)info->num_items;
     p.seg_len = info->seg_len; p.mean_scale = mean_scale;
 
-    const int64_t k4 = (k + 3) & ~(int64_t)3;
-    const bool vec4 = (ldx % 4 == 0) && (ldx >= k4) && (lda % 4 == 0) &&
+    const bool vec4 = (ldx % 4 == 0) && (ldx >= ((k + 3) & ~(int64_t)3)) && (lda % 4 == 0) &&
                       ((reinterpret_cast<uintptr_t>(x) & 15u) == 0) && ((reinterpret_cast<uintptr_t>(a) & 15u) == 0);
+    // K tiling as in the forward: when x does not fit L2 but an [n, 64] slab does, sweep the
+    // slabs one launch after the other; the dot products accumulate into out_val in place
+    // (launch order = tile order, so the result is deterministic).
+    int64_t kt = k;
+    if (vec4 && k > 64 && k % 4 == 0 && (double)n * (double)k * 4.0 > 96.0 * 1024 * 1024 &&
+        (double)n * 64.0 * 4.0 <= 64.0 * 1024 * 1024)
+        kt = 64;
     const int warps = 4;
     const dim3 grid((unsigned)((p.num_items + warps - 1) / warps)), block(warps * 32);
-    if (vec4) {
-        const int64_t tv = k4 / 4;
-        if (tv <= 8) sddmm_seg_kernel<4, 8, 1><<<grid, block, 0, stream>>>(p);
-        else if (tv <= 16) sddmm_seg_kernel<4, 16, 1><<<grid, block, 0, stream>>>(p);
-        else if (tv <= 32) sddmm_seg_kernel<4, 32, 1><<<grid, block, 0, stream>>>(p);
-        else sddmm_seg_kernel<4, 32, 2><<<grid, block, 0, stream>>>(p);   // 256 floats per pass, loops for wider K
-    } else {
-        if (k <= 32) sddmm_seg_kernel<1, 32, 1><<<grid, block, 0, stream>>>(p);
-        else sddmm_seg_kernel<1, 32, 2><<<grid, block, 0, stream>>>(p);
+    for (int64_t k0 = 0; k0 < k; k0 += kt) {
+        const int64_t kw = (k - k0 < kt) ? (k - k0) : kt;
+        p.a = a + k0;
+        p.x = x + k0;
+        p.k = (int)kw;
+        p.accum = k0 > 0 ? 1 : 0;
+        if (vec4) {
+            const int64_t tv = ((kw + 3) & ~(int64_t)3) / 4;
+            if (tv <= 8) sddmm_seg_kernel<4, 8, 1><<<grid, block, 0, stream>>>(p);
+            else if (tv <= 16) sddmm_seg_kernel<4, 16, 1><<<grid, block, 0, stream>>>(p);
+            else if (tv <= 32) sddmm_seg_kernel<4, 32, 1><<<grid, block, 0, stream>>>(p);
+            else sddmm_seg_kernel<4, 32, 2><<<grid, block, 0, stream>>>(p);   // 256 floats per pass, loops for wider K
+        } else {
+            if (kw <= 32) sddmm_seg_kernel<1, 32, 1><<<grid, block, 0, stream>>>(p);
+            else sddmm_seg_kernel<1, 32, 2><<<grid, block, 0, stream>>>(p);
+        }
+        ISPLIB_LAUNCH_CHECK();
     }
-    ISPLIB_LAUNCH_CHECK();
     return ISPLIB_SUCCESS;
 }
