@@ -476,3 +476,27 @@ def test_no_out_of_bounds_writes_canaries(capi, oracle, K):
                 assert np.array_equal(out.cpu().numpy(), ref) and np.array_equal(arg.cpu().numpy(), ref_arg), name
             else:
                 assert_sum_close(out.cpu().numpy(), ref, abs_product_sum(rowptr, col, val, mat))
+
+
+def test_l2_tiled_paths_sddmm_and_arg_backward(capi, oracle):
+    """The K-tiled code paths only switch on when X / grad_x exceed the L2 budget (> 64-96 MB):
+    a wide dense operand (200k x 128 = 102 MB) with a small graph on top exercises the tiled
+    SDDMM (two 64-wide launches accumulating) and the tiled arg scatter (32-wide slabs)."""
+    rng = np.random.default_rng(4242)
+    M, N, K = 300, 200_000, 128
+    rowptr, col, val = random_csr(rng, M, N, 60, empty_prob=0.05, long_rows=[(1, 900)])
+    x = rng.standard_normal((N, K)).astype(np.float32)
+    a = rng.standard_normal((M, K)).astype(np.float32)
+    rp, co, va, xd = to_dev(rowptr, col, val, x)
+    ad = torch.from_numpy(a).to(DEV)
+    plan = capi.Plan(rp, co.numel())
+    row = np.repeat(np.arange(M), np.diff(rowptr))
+    cond = (np.abs(a.astype(np.float64))[row] * np.abs(x.astype(np.float64))[col]).sum(axis=1)
+    for mean in (False, True):
+        got = capi.sddmm_csr(rp, co, ad, xd, plan, mean).cpu().numpy()
+        ref = oracle.sddmm(rowptr, col, a, x, mean)
+        assert_sum_close(got, ref, cond / (np.maximum(np.diff(rowptr), 1)[row] if mean else 1.0))
+    _, arg = oracle.spmm_c(rowptr, col, val, x, oracle.MAX)
+    rgx, _ = oracle.arg_backward(col, val, None, arg, a, N)
+    gx, _ = capi.spmm_arg_backward(co, va, None, torch.from_numpy(arg).to(DEV), ad, N, True, False)
+    np.testing.assert_allclose(gx.cpu().numpy(), rgx, rtol=1e-5, atol=1e-5)
