@@ -17,6 +17,9 @@
 //   * the kernel variant is picked on the device per (graph, reduce, K) on first use;
 //   * the C-ABI status is checked (the reference ignores it, csrc/fusedmm.cpp:198).
 #include <ATen/cuda/CUDAContext.h>
+#include <ATen/cuda/CUDAEvent.h>
+#include <ATen/cuda/CUDAGraphsUtils.cuh>
+#include <c10/cuda/CUDACachingAllocator.h>
 #include <c10/cuda/CUDAGuard.h>
 #include <torch/library.h>
 #include <torch/torch.h>
@@ -84,6 +87,9 @@ struct GraphEntry {
     // permuted values for the backward, keyed by the identity of the value tensor
     const void* valt_key = nullptr; uint32_t valt_version = 0; Tensor val_t;
     const void* meanw_key = nullptr; uint32_t meanw_version = 0; bool meanw_built = false; Tensor mean_w;
+    // the permuted values are produced asynchronously on whatever stream first needed them;
+    // later users on other streams (autograd worker threads) wait on these events
+    at::cuda::CUDAEvent valt_ready, meanw_ready;
     std::mutex mu;
 
     GraphEntry(const Tensor& rowptr, const Tensor& col)
@@ -196,19 +202,26 @@ Tensor permuted_values(GraphEntry& e, const c10::optional<Tensor>& value, bool m
     auto stream = at::cuda::getCurrentCUDAStream();
     const void* key = value.has_value() ? value->data_ptr() : nullptr;
     const uint32_t ver = value.has_value() ? value->_version() : 0;
+    auto reuse = [&](Tensor& t, at::cuda::CUDAEvent& ready) {
+        // produced on another stream?  (no cross-stream wait while capturing a CUDA graph: the
+        // producer finished long before, during the warm-up the capture contract requires)
+        if (at::cuda::currentStreamCaptureStatus() == at::cuda::CaptureStatus::None) ready.block(stream);
+        c10::cuda::CUDACachingAllocator::recordStream(t.storage().data_ptr(), stream);
+        return t;
+    };
     if (!mean_weights) {
         if (!value.has_value()) return Tensor();  // implicit ones stay implicit
-        if (e.valt_key == key && e.valt_version == ver && e.val_t.defined()) return e.val_t;
+        if (e.valt_key == key && e.valt_version == ver && e.val_t.defined()) return reuse(e.val_t, e.valt_ready);
     } else if (e.meanw_built && e.meanw_key == key && e.meanw_version == ver) {
-        return e.mean_w;
+        return reuse(e.mean_w, e.meanw_ready);
     }
     Tensor out = torch::empty({e.fwd.nnz}, e.fwd.rowptr32.options().dtype(torch::kFloat32));
     ISPLIB_CHECK_STATUS(isplib_b200_permute_values(
         e.fwd.nnz, value.has_value() ? value->data_ptr<float>() : nullptr, e.csr2csc32.data_ptr<int32_t>(),
         e.bwd.col32.data_ptr<int32_t>(), e.fwd.rowptr32.data_ptr<int32_t>(), mean_weights ? 1 : 0,
         out.data_ptr<float>(), stream.stream()));
-    if (!mean_weights) { e.valt_key = key; e.valt_version = ver; e.val_t = out; }
-    else { e.meanw_key = key; e.meanw_version = ver; e.mean_w = out; e.meanw_built = true; }
+    if (!mean_weights) { e.valt_key = key; e.valt_version = ver; e.val_t = out; e.valt_ready.record(stream); }
+    else { e.meanw_key = key; e.meanw_version = ver; e.mean_w = out; e.meanw_built = true; e.meanw_ready.record(stream); }
     return out;
 }
 
