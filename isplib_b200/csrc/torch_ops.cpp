@@ -112,8 +112,11 @@ struct GraphKeyHash {
     }
 };
 
-std::mutex g_cache_mu;
-std::unordered_map<GraphKey, std::shared_ptr<GraphEntry>, GraphKeyHash> g_cache;
+// Deliberately leaked: the entries own device tensors and CUDA events, and static destructors
+// run after the CUDA runtime has shut down ("driver shutting down" -> std::terminate at exit).
+using GraphCache = std::unordered_map<GraphKey, std::shared_ptr<GraphEntry>, GraphKeyHash>;
+std::mutex& g_cache_mu = *new std::mutex();
+GraphCache& g_cache = *new GraphCache();
 
 Tensor to_i32(const Tensor& t) {
     if (t.scalar_type() == torch::kInt32) return t.contiguous();
