@@ -162,7 +162,8 @@ def run_reference(args):
         def spmm(row, rowptr, col, val, x):
             # the two trailing cached tensors are only read by the backward (csrc/fusedmm.cpp:246-247)
             return torch.ops.isplib.fusedmm_spmm(None, rowptr, col, val, None, None, x, val, col)
-        impl_desc = "unmodified csrc/fusedmm.cpp operator layer + restated fusedMM_csr (OpenMP)"
+        impl_desc = ("unmodified csrc/fusedmm.cpp operator layer + restated fusedMM_csr "
+                     "(gcc -O3 -march=x86-64-v3 -fopenmp; the real kernel library is un-vendored, configure:2-7)")
     else:
         from oracle import oracle
         kind = "port"
@@ -237,7 +238,7 @@ def cpu_baseline_leg(args, budget_s):
     b = synth.algorithmic_bytes(g.m, g.nnz, K, True, args.reduce)
     return {"value": round(b / dt / 1e9, 3), "unit": "GB/s", "cores": cores, "kind": "port",
             "sample": f"first-{g.m}-row sample of {args.shape}-shape ({g.nnz} nnz, columns over all {m0} nodes), "
-                      f"K={K}, median of {len(times)} runs, oracle/fusedmm_oracle.c OpenMP",
+                      f"K={K}, median of {len(times)} runs, oracle/fusedmm_oracle.c (gcc -O3 -march=x86-64-v3 -fopenmp, int64 CSR)",
             "ms": round(dt * 1e3, 2), "gflops": round(2.0 * g.nnz * K / dt / 1e9, 2)}
 
 
