@@ -236,7 +236,20 @@ def cpu_baseline_leg(args, budget_s):
     times.sort()
     dt = times[len(times) // 2]
     b = synth.algorithmic_bytes(g.m, g.nnz, K, True, args.reduce)
-    return {"value": round(b / dt / 1e9, 3), "unit": "GB/s", "cores": cores, "kind": "port",
+    # sanity second baseline: torch.sparse.mm on a CPU CSR tensor (sum only)
+    sparse_mm_ms = None
+    if args.reduce in ("sum", "add"):
+        try:
+            torch.set_num_threads(cores)
+            A = torch.sparse_csr_tensor(g.rowptr, g.col, g.value, size=(g.m, m0))
+            xt = torch.from_numpy(x)
+            torch.sparse.mm(A, xt)
+            t = time.perf_counter()
+            torch.sparse.mm(A, xt)
+            sparse_mm_ms = round((time.perf_counter() - t) * 1e3, 2)
+        except Exception:
+            sparse_mm_ms = None
+    return {"torch_sparse_mm_cpu_ms": sparse_mm_ms,"value": round(b / dt / 1e9, 3), "unit": "GB/s", "cores": cores, "kind": "port",
             "sample": f"first-{g.m}-row sample of {args.shape}-shape ({g.nnz} nnz, columns over all {m0} nodes), "
                       f"K={K}, median of {len(times)} runs, oracle/fusedmm_oracle.c (gcc -O3 -march=x86-64-v3 -fopenmp, int64 CSR)",
             "ms": round(dt * 1e3, 2), "gflops": round(2.0 * g.nnz * K / dt / 1e9, 2)}
