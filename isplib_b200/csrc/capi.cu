@@ -184,6 +184,7 @@ extern "C" int isplib_b200_spmm_autotune(int reduce, int64_t m, int64_t n, int64
         // default candidate set = the family that wins on every measured shape (U=4; 4 warps/CTA
         // for every K tile, 8 warps only untiled); the rest only with ISPLIB_B200_TUNE_ALL=1
         if (d->method == 0 && !tune_all && !(d->unroll == 4 && (d->warps == 4 || d->kt == 0))) continue;
+        if (d->method == 3 && !tune_all) continue;   // 256-bit gathers: measured slower here (register pressure)
         rc = launch_spmm(reduce, p, nnz, v, stream);  // warm-up
         if (rc) break;
         cudaEventRecord(e0, stream);

@@ -35,7 +35,7 @@ struct WorkspaceLayout {
 static inline size_t align_up_(size_t x, size_t a) { return (x + a - 1) / a * a; }
 static inline WorkspaceLayout workspace_layout(int64_t num_split_items, int64_t k, bool is_arg) {
     WorkspaceLayout W;
-    const size_t part = align_up_((size_t)num_split_items * (size_t)((k + 3) / 4 * 4) * 4, 256);
+    const size_t part = align_up_((size_t)num_split_items * (size_t)((k + 7) / 8 * 8) * 4, 256);
     size_t o = 0;
     W.off_part_val = o; o += part;
     W.off_part_arg = o; if (is_arg) o += part;
@@ -99,7 +99,7 @@ struct SpmmParams {
     long long ldx, ldo, arg_sentinel;
     int m, k, tile_w, num_items, num_split_rows, seg_len;
     int ticket_stride, ticket_capacity;   // ints per K tile / ints available
-    int kp;         // row stride of the partial buffers = roundup4(k)
+    int kp;         // row stride of the partial buffers = roundup8(k)
     int vec_store;  // 1: out (and arg_out) rows take aligned 16-byte stores
     int flags;      // ISPLIB_FLAG_*
     int div_mode;   // 0 none, 1 by max(deg,1), 2 by row_div[]

@@ -43,6 +43,16 @@ static const VariantDesc kVariants[] = {
     {"seg/w4/u2/kfull", 0, 4, 2, 0},
     {"seg/w4/u2/kt64", 0, 4, 2, 64},
     {"seg/w8/u2/kt64", 0, 8, 2, 64},
+    // method 3: 32-byte gathers (LDG.E.256), rows 32-byte aligned and padded to a multiple of 8.
+    // A bare gather loop gains +25 % from 256-bit loads (profiles/r1_l2probe.txt), but in this
+    // kernel 4 x 32 B in flight per lane cost 101 registers (20 warps/SM) and U=2 loses the gain:
+    // 5.1 ms vs 4.2 ms on Reddit-shape K=128.  Selectable by id / ISPLIB_B200_TUNE_ALL=1 only.
+    {"seg256/w4/u4/kfull", 3, 4, 4, 0},
+    {"seg256/w4/u2/kfull", 3, 4, 2, 0},
+    {"seg256/w4/u4/kt128", 3, 4, 4, 128},
+    {"seg256/w4/u4/kt64", 3, 4, 4, 64},
+    {"seg256/w4/u2/kt64", 3, 4, 2, 64},
+    {"seg256/w8/u2/kfull", 3, 8, 2, 0},
     // method 1: TMA bulk-copy gather through a per-warp shared-memory ring; `unroll` = stages
     // (measured 3x slower than the LDG gather for 256-512 B rows -- profiles/r1_kbench_bulk.txt:
     // the copy engine retires one small bulk request per ~14-30 cycles per SM -- so the on-device
@@ -94,7 +104,13 @@ __device__ __forceinline__ void load_vec(const float* __restrict__ p, float (&v)
         asm volatile("ld.global.nc.L2::cache_hint.f32 %0, [%1], %2;" : "=f"(v[0]) : "l"(p), "l"(xpol));
     }
 #else
-    if constexpr (VEC == 4) {
+    if constexpr (VEC == 8) {
+        // 256-bit load (sm_100: LDG.E.256): measured +25 % random-row-gather bandwidth over
+        // 128-bit loads out of L2 (profiles/r1_l2probe.txt, "gather256")
+        asm volatile("ld.global.nc.v8.b32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+                     : "=f"(v[0]), "=f"(v[1]), "=f"(v[2]), "=f"(v[3]), "=f"(v[4]), "=f"(v[5]), "=f"(v[6]), "=f"(v[7])
+                     : "l"(p));
+    } else if constexpr (VEC == 4) {
         const float4 t = __ldg(reinterpret_cast<const float4*>(p));
         v[0] = t.x; v[1] = t.y; v[2] = t.z; v[3] = t.w;
     } else {
@@ -105,7 +121,10 @@ __device__ __forceinline__ void load_vec(const float* __restrict__ p, float (&v)
 
 template <int VEC>
 __device__ __forceinline__ void store_vec_f(float* p, const float (&v)[VEC]) {
-    if constexpr (VEC == 4) {
+    if constexpr (VEC == 8) {
+        __stcs(reinterpret_cast<float4*>(p), make_float4(v[0], v[1], v[2], v[3]));
+        __stcs(reinterpret_cast<float4*>(p) + 1, make_float4(v[4], v[5], v[6], v[7]));
+    } else if constexpr (VEC == 4) {
         __stcs(reinterpret_cast<float4*>(p), make_float4(v[0], v[1], v[2], v[3]));
     } else {
         __stcs(p, v[0]);
@@ -114,7 +133,10 @@ __device__ __forceinline__ void store_vec_f(float* p, const float (&v)[VEC]) {
 
 template <int VEC>
 __device__ __forceinline__ void store_vec_i64(long long* p, const long long (&v)[VEC]) {
-    if constexpr (VEC == 4) {
+    if constexpr (VEC == 8) {
+#pragma unroll
+        for (int q = 0; q < 4; ++q) __stcs(reinterpret_cast<longlong2*>(p) + q, make_longlong2(v[2 * q], v[2 * q + 1]));
+    } else if constexpr (VEC == 4) {
         __stcs(reinterpret_cast<longlong2*>(p), make_longlong2(v[0], v[1]));
         __stcs(reinterpret_cast<longlong2*>(p) + 1, make_longlong2(v[2], v[3]));
     } else {
@@ -163,9 +185,12 @@ __device__ __forceinline__ void finalize_store(const SpmmParams& p, int row, int
     if constexpr (OP == OP_SUM) {
         if (p.flags & ISPLIB_FLAG_ACCUMULATE) {
             float prev[VEC];
-            if (VEC == 4 && vec_ok) {
-                const float4 t = *reinterpret_cast<const float4*>(p.out + o);
-                prev[0] = t.x; prev[1 % VEC] = t.y; prev[2 % VEC] = t.z; prev[3 % VEC] = t.w;
+            if (VEC >= 4 && vec_ok) {
+#pragma unroll
+                for (int q = 0; q < VEC / 4; ++q) {
+                    const float4 t = *(reinterpret_cast<const float4*>(p.out + o) + q);
+                    prev[(4 * q) % VEC] = t.x; prev[(4 * q + 1) % VEC] = t.y; prev[(4 * q + 2) % VEC] = t.z; prev[(4 * q + 3) % VEC] = t.w;
+                }
             } else {
 #pragma unroll
                 for (int v = 0; v < VEC; ++v) prev[v] = (v < nvalid) ? p.out[o + v] : 0.f;
@@ -270,10 +295,15 @@ __device__ __forceinline__ void finish_item(const SpmmParams& p, const int lane,
         for (int j = 0; j < LPL; ++j) {
             if (kok[j]) {
                 const size_t o = slot * (size_t)p.kp + (size_t)koff[j];
-                if constexpr (VEC == 4) {
-                    __stcg(reinterpret_cast<float4*>(p.part_val + o), make_float4(acc[j][0], acc[j][1], acc[j][2], acc[j][3]));
-                    if constexpr (OP != OP_SUM)
-                        __stcg(reinterpret_cast<int4*>(p.part_arg + o), make_int4(arg[j][0], arg[j][1], arg[j][2], arg[j][3]));
+                if constexpr (VEC >= 4) {
+#pragma unroll
+                    for (int q = 0; q < VEC / 4; ++q) {
+                        __stcg(reinterpret_cast<float4*>(p.part_val + o) + q,
+                               make_float4(acc[j][(4 * q) % VEC], acc[j][(4 * q + 1) % VEC], acc[j][(4 * q + 2) % VEC], acc[j][(4 * q + 3) % VEC]));
+                        if constexpr (OP != OP_SUM)
+                            __stcg(reinterpret_cast<int4*>(p.part_arg + o) + q,
+                                   make_int4(arg[j][(4 * q) % VEC], arg[j][(4 * q + 1) % VEC], arg[j][(4 * q + 2) % VEC], arg[j][(4 * q + 3) % VEC]));
+                    }
                 } else {
                     __stcg(p.part_val + o, acc[j][0]);
                     if constexpr (OP != OP_SUM) __stcg(p.part_arg + o, arg[j][0]);
@@ -304,12 +334,15 @@ __device__ __forceinline__ void finish_item(const SpmmParams& p, const int lane,
             const size_t o = o0 + (size_t)t * (size_t)p.kp;
             float pv[VEC];
             int pa[VEC];
-            if constexpr (VEC == 4) {
-                const float4 q = __ldcg(reinterpret_cast<const float4*>(p.part_val + o));
-                pv[0] = q.x; pv[1] = q.y; pv[2] = q.z; pv[3] = q.w;
-                if constexpr (OP != OP_SUM) {
-                    const int4 r = __ldcg(reinterpret_cast<const int4*>(p.part_arg + o));
-                    pa[0] = r.x; pa[1] = r.y; pa[2] = r.z; pa[3] = r.w;
+            if constexpr (VEC >= 4) {
+#pragma unroll
+                for (int h = 0; h < VEC / 4; ++h) {
+                    const float4 q = __ldcg(reinterpret_cast<const float4*>(p.part_val + o) + h);
+                    pv[(4 * h) % VEC] = q.x; pv[(4 * h + 1) % VEC] = q.y; pv[(4 * h + 2) % VEC] = q.z; pv[(4 * h + 3) % VEC] = q.w;
+                    if constexpr (OP != OP_SUM) {
+                        const int4 r = __ldcg(reinterpret_cast<const int4*>(p.part_arg + o) + h);
+                        pa[(4 * h) % VEC] = r.x; pa[(4 * h + 1) % VEC] = r.y; pa[(4 * h + 2) % VEC] = r.z; pa[(4 * h + 3) % VEC] = r.w;
+                    }
                 }
             } else {
                 pv[0] = __ldcg(p.part_val + o);
@@ -356,7 +389,7 @@ spmm_seg_kernel(const __grid_constant__ SpmmParams p) {
     const int lg = lane % G;
     const int k0 = blockIdx.y * p.tile_w;
     // VEC=4 loads may read up to 3 padding floats past K (the launcher checked ldx >= roundup4(K))
-    const int keff = (VEC == 4) ? ((p.k + 3) & ~3) : p.k;
+    const int keff = (VEC > 1) ? ((p.k + VEC - 1) & ~(VEC - 1)) : p.k;
     const int kend = min(keff, k0 + p.tile_w);
 
     int koff[LPL];
@@ -644,17 +677,26 @@ static int pick_vec(int64_t k, int64_t ldx, const void* x) {
     if (ldx % 4 == 0 && ldx >= ((k + 3) & ~(int64_t)3) && aligned16(x)) return 4;
     return 1;
 }
+// 32-byte (LDG.E.256) gathers: 32-byte aligned rows that own their padding up to roundup8(K)
+static bool vec8_ok(int64_t k, int64_t ldx, const void* x) {
+    return ldx % 8 == 0 && ldx >= ((k + 7) & ~(int64_t)7) && (reinterpret_cast<uintptr_t>(x) & 31u) == 0;
+}
 
 static TileShape pick_shape(int vec, int64_t k, int kt) {
     TileShape t;
     t.vec = vec;
-    const int max_tile = vec * 32 * 4;  // G=32, LPL=4
-    if (vec == 4) k = (k + 3) & ~(int64_t)3;
+    const int max_tile = vec == 8 ? 512 : vec * 32 * 4;  // G=32, LPL=4 (LPL=2 for 32-byte vectors)
+    if (vec > 1) k = (k + vec - 1) / vec * vec;
     int64_t tw = (kt <= 0 || kt >= k) ? k : kt;
     if (tw > max_tile) tw = max_tile;
-    if (vec == 4) tw = (tw + 3) / 4 * 4;
+    if (vec > 1) tw = (tw + vec - 1) / vec * vec;
     const int tv = (int)((tw + vec - 1) / vec);  // vectors per tile
-    if (vec == 4 && tv <= 8)       { t.g = 8;  t.lpl = 1; }
+    if (vec == 8 && tv <= 4)       { t.g = 4;  t.lpl = 1; }
+    else if (vec == 8 && tv <= 8)  { t.g = 8;  t.lpl = 1; }
+    else if (vec == 8 && tv <= 16) { t.g = 16; t.lpl = 1; }
+    else if (vec == 8 && tv <= 32) { t.g = 32; t.lpl = 1; }
+    else if (vec == 8)             { t.g = 32; t.lpl = 2; }
+    else if (vec == 4 && tv <= 8)  { t.g = 8;  t.lpl = 1; }
     else if (vec == 4 && tv <= 16) { t.g = 16; t.lpl = 1; }
     else if (tv <= 32)             { t.g = 32; t.lpl = 1; }
     else if (tv <= 64)             { t.g = 32; t.lpl = 2; }
@@ -680,8 +722,23 @@ static SegKernel pick_u(int u, bool partial) {
     return nullptr;
 }
 
+template <int OP, int G, int LPL>
+static SegKernel pick_u8(int u, bool partial) {   // 32-byte vectors: U = 2 or 4 gathers in flight
+    if (u <= 2)
+        return partial ? spmm_seg_kernel<OP, 8, G, LPL, 2, true> : spmm_seg_kernel<OP, 8, G, LPL, 2, false>;
+    return partial ? spmm_seg_kernel<OP, 8, G, LPL, 4, true> : spmm_seg_kernel<OP, 8, G, LPL, 4, false>;
+}
+
 template <int OP>
 static SegKernel pick_kernel(const TileShape& t, int u, bool partial) {
+    if (t.vec == 8) {
+        if (t.g == 4) return pick_u8<OP, 4, 1>(u, partial);
+        if (t.g == 8) return pick_u8<OP, 8, 1>(u, partial);
+        if (t.g == 16) return pick_u8<OP, 16, 1>(u, partial);
+        if (t.g == 32 && t.lpl == 1) return pick_u8<OP, 32, 1>(u, partial);
+        if (t.g == 32 && t.lpl == 2) return pick_u8<OP, 32, 2>(u <= 2 ? 2 : 2, partial);
+        return nullptr;
+    }
     if (t.vec == 4) {
         if (t.g == 8 && t.lpl == 1) return pick_u<OP, 4, 8, 1>(u, partial);
         if (t.g == 16 && t.lpl == 1) return pick_u<OP, 4, 16, 1>(u, partial);
@@ -724,6 +781,11 @@ bool spmm_variant_supported(int variant, int reduce, int64_t k, int64_t ldx, int
     if (!d || reduce < 0 || reduce > 3 || k <= 0) return false;
     (void)ldo; (void)out;
     const int vec = pick_vec(k, ldx, x);
+    if (d->method == 3) {   // 32-byte gathers
+        if (!vec8_ok(k, ldx, x)) return false;
+        if (d->kt > 0 && (d->kt >= k || d->kt % 8 != 0)) return false;
+        return true;
+    }
     if (d->method == 1) {
         // bulk copies need 16-byte aligned rows and sizes, and the ring must fit shared memory
         if (vec != 4) return false;
@@ -771,10 +833,14 @@ int launch_spmm(int reduce, const SpmmParams& base, int64_t nnz, int variant, cu
     if (base.m == 0 || base.k == 0) return ISPLIB_SUCCESS;
 
     SpmmParams p = base;
-    const int vec = pick_vec(p.k, p.ldx, p.x);
+    int vec = pick_vec(p.k, p.ldx, p.x);
+    if (d->method == 3) {
+        if (!vec8_ok(p.k, p.ldx, p.x)) return ISPLIB_NO_OPT_IMPL;
+        vec = 8;
+    }
     const TileShape t = pick_shape(vec, p.k, d->kt);
-    const int keff = vec == 4 ? ((p.k + 3) & ~3) : p.k;
-    p.kp = (p.k + 3) & ~3;
+    const int keff = vec > 1 ? (p.k + vec - 1) / vec * vec : p.k;
+    p.kp = (p.k + 7) & ~7;
     p.vec_store = (p.k % 4 == 0 && p.ldo % 4 == 0 && aligned16(p.out) && (!p.arg_out || aligned16(p.arg_out))) ? 1 : 0;
     p.tile_w = t.tile_w;
     const int op = (reduce == ISPLIB_REDUCE_MAX) ? OP_MAX : (reduce == ISPLIB_REDUCE_MIN ? OP_MIN : OP_SUM);

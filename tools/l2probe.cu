@@ -49,6 +49,34 @@ __global__ void row_gather(const float4* __restrict__ p, unsigned nrows, int ite
     if (acc == 123.456f) *sink = acc;
 }
 
+// same with 256-bit loads (sm_100: LDG.E.256): LANES8 lanes x 32 B cover one row
+template <int LANES8, int U>
+__global__ void row_gather256(const float4* __restrict__ p, unsigned nrows, int iters, float* sink) {
+    const int lane = threadIdx.x & 31;
+    const unsigned warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const int sub = lane / LANES8, l = lane % LANES8;
+    float acc = 0.f;
+    for (int it = 0; it < iters; it += U) {
+        unsigned w[U][8];
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+            const unsigned r = hash32((warp * 131071u + (unsigned)(it + u)) * (32 / LANES8) + sub) % nrows;
+            const float4* a = p + ((size_t)r * LANES8 + l) * 2;
+            asm volatile("ld.global.nc.v8.b32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+                         : "=r"(w[u][0]), "=r"(w[u][1]), "=r"(w[u][2]), "=r"(w[u][3]), "=r"(w[u][4]), "=r"(w[u][5]),
+                           "=r"(w[u][6]), "=r"(w[u][7]) : "l"(a));
+        }
+#pragma unroll
+        for (int u = 0; u < U; ++u)
+#pragma unroll
+            for (int q = 0; q < 8; ++q) acc += __uint_as_float(w[u][q]);
+    }
+    if (acc == 123.456f) *sink = acc;
+}
+
+template <int LANES8, int U>
+void run_gather256(const float4* buf, size_t bytes, float* sink, int warps_per_sm_target);
+
 template <typename F> float time_ms(F f, int n = 5) {
     cudaEvent_t a, b; cudaEventCreate(&a); cudaEventCreate(&b);
     f();
@@ -68,6 +96,18 @@ void run_gather(const float4* buf, size_t bytes, float* sink, int warps_per_sm_t
     CK(cudaGetLastError());
     double moved = (double)blocks * (threads / 32) * iters * 512.0;
     printf("gather  footprint=%7.1f MB row=%4d B  U=%d  warps/SM=%2d : %8.1f GB/s\n", bytes / 1e6, LANES * 16, U,
+           warps_per_sm_target, moved / ms / 1e6);
+}
+
+template <int LANES8, int U>
+void run_gather256(const float4* buf, size_t bytes, float* sink, int warps_per_sm_target) {
+    const unsigned nrows = (unsigned)(bytes / (LANES8 * 32));
+    const int threads = 256, blocks = 148 * warps_per_sm_target / 8;
+    const int iters = 4096;
+    float ms = time_ms([&] { row_gather256<LANES8, U><<<blocks, threads>>>(buf, nrows, iters, sink); });
+    CK(cudaGetLastError());
+    double moved = (double)blocks * (threads / 32) * iters * 1024.0;
+    printf("gather256 footprint=%7.1f MB row=%4d B  U=%d  warps/SM=%2d : %8.1f GB/s\n", bytes / 1e6, LANES8 * 32, U,
            warps_per_sm_target, moved / ms / 1e6);
 }
 
@@ -92,6 +132,10 @@ int main() {
         run_gather<16, 4>(buf, bytes, sink, 32);
         run_gather<16, 8>(buf, bytes, sink, 64);
         run_gather<8, 8>(buf, bytes, sink, 64);
+        run_gather256<16, 4>(buf, bytes, sink, 32);
+        run_gather256<16, 4>(buf, bytes, sink, 64);
+        run_gather256<8, 4>(buf, bytes, sink, 32);
+        run_gather256<8, 2>(buf, bytes, sink, 64);
     }
     return 0;
 }
