@@ -1,0 +1,7 @@
+// spmm_inst_max.cu -- instantiates the forward kernels of one reduction (OP_MAX).
+#include "spmm_kernels.cuh"
+
+namespace isplib {
+SegKernel seg_kernel_max(const TileShape& t, int u, bool partial) { return pick_kernel<OP_MAX>(t, u, partial); }
+SegKernel bulk_kernel_max(const TileShape& t, int stages) { return pick_bulk_kernel<OP_MAX>(t, stages); }
+}  // namespace isplib

@@ -1,0 +1,7 @@
+// spmm_inst_min.cu -- instantiates the forward kernels of one reduction (OP_MIN).
+#include "spmm_kernels.cuh"
+
+namespace isplib {
+SegKernel seg_kernel_min(const TileShape& t, int u, bool partial) { return pick_kernel<OP_MIN>(t, u, partial); }
+SegKernel bulk_kernel_min(const TileShape& t, int stages) { return pick_bulk_kernel<OP_MIN>(t, stages); }
+}  // namespace isplib

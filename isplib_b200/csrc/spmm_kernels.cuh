@@ -1,0 +1,675 @@
+// spmm_kernels.cuh -- device code of the forward SpMM (templates) and the per-reduction kernel
+// pickers.  Included by spmm_inst_{sum,max,min}.cu, which instantiate one reduction each so
+// the three translation units compile in parallel; spmm_fwd.cu holds the host-side dispatch.
+#pragma once
+#include "common.cuh"
+#include <float.h>
+#include <limits.h>
+
+namespace isplib {
+
+// ------------------------------------------------------------------------------------
+// small device helpers
+// ------------------------------------------------------------------------------------
+template <int VEC> struct VecT;
+template <> struct VecT<4> { using type = float4; };
+template <> struct VecT<1> { using type = float; };
+
+#ifndef ISPLIB_X_EVICT_LAST
+#define ISPLIB_X_EVICT_LAST 0
+#endif
+
+#if ISPLIB_X_EVICT_LAST
+// L2 cache policy for the gathered X rows: keep them (evict_last) while the index stream and
+// the output go through with evict-first hints, so a K slab of X survives in L2.
+__device__ __forceinline__ unsigned long long x_policy() {
+    unsigned long long pol;
+    asm volatile("createpolicy.fractional.L2::evict_last.b64 %0, 1.0;" : "=l"(pol));
+    return pol;
+}
+#define ISPLIB_XPOL_DECL const unsigned long long xpol = x_policy();
+#define ISPLIB_XPOL_ARG , xpol
+#define ISPLIB_XPOL_PARAM , unsigned long long xpol
+#else
+#define ISPLIB_XPOL_DECL
+#define ISPLIB_XPOL_ARG
+#define ISPLIB_XPOL_PARAM
+#endif
+
+template <int VEC>
+__device__ __forceinline__ void load_vec(const float* __restrict__ p, float (&v)[VEC] ISPLIB_XPOL_PARAM) {
+#if ISPLIB_X_EVICT_LAST
+    if constexpr (VEC == 4) {
+        asm volatile("ld.global.nc.L2::cache_hint.v4.f32 {%0,%1,%2,%3}, [%4], %5;"
+                     : "=f"(v[0]), "=f"(v[1]), "=f"(v[2]), "=f"(v[3]) : "l"(p), "l"(xpol));
+    } else {
+        asm volatile("ld.global.nc.L2::cache_hint.f32 %0, [%1], %2;" : "=f"(v[0]) : "l"(p), "l"(xpol));
+    }
+#else
+    if constexpr (VEC == 8) {
+        // 256-bit load (sm_100: LDG.E.256): measured +25 % random-row-gather bandwidth over
+        // 128-bit loads out of L2 (profiles/r1_l2probe.txt, "gather256")
+        asm volatile("ld.global.nc.v8.b32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+                     : "=f"(v[0]), "=f"(v[1]), "=f"(v[2]), "=f"(v[3]), "=f"(v[4]), "=f"(v[5]), "=f"(v[6]), "=f"(v[7])
+                     : "l"(p));
+    } else if constexpr (VEC == 4) {
+        const float4 t = __ldg(reinterpret_cast<const float4*>(p));
+        v[0] = t.x; v[1] = t.y; v[2] = t.z; v[3] = t.w;
+    } else {
+        v[0] = __ldg(p);
+    }
+#endif
+}
+
+template <int VEC>
+__device__ __forceinline__ void store_vec_f(float* p, const float (&v)[VEC]) {
+    if constexpr (VEC == 8) {
+        __stcs(reinterpret_cast<float4*>(p), make_float4(v[0], v[1], v[2], v[3]));
+        __stcs(reinterpret_cast<float4*>(p) + 1, make_float4(v[4], v[5], v[6], v[7]));
+    } else if constexpr (VEC == 4) {
+        __stcs(reinterpret_cast<float4*>(p), make_float4(v[0], v[1], v[2], v[3]));
+    } else {
+        __stcs(p, v[0]);
+    }
+}
+
+template <int VEC>
+__device__ __forceinline__ void store_vec_i64(long long* p, const long long (&v)[VEC]) {
+    if constexpr (VEC == 8) {
+#pragma unroll
+        for (int q = 0; q < 4; ++q) __stcs(reinterpret_cast<longlong2*>(p) + q, make_longlong2(v[2 * q], v[2 * q + 1]));
+    } else if constexpr (VEC == 4) {
+        __stcs(reinterpret_cast<longlong2*>(p), make_longlong2(v[0], v[1]));
+        __stcs(reinterpret_cast<longlong2*>(p) + 1, make_longlong2(v[2], v[3]));
+    } else {
+        __stcs(p, v[0]);
+    }
+}
+
+template <int VEC>
+__device__ __forceinline__ void store_vec_i32(int* p, const int (&v)[VEC]) {
+    if constexpr (VEC == 4) {
+        *reinterpret_cast<int4*>(p) = make_int4(v[0], v[1], v[2], v[3]);
+    } else {
+        *p = v[0];
+    }
+}
+
+template <int OP> __device__ __forceinline__ float init_value() {
+    // csrc/fusedmm.cpp:147-152: zeros / numeric_limits<float>::lowest() / ::max()
+    return OP == OP_SUM ? 0.f : (OP == OP_MAX ? -FLT_MAX : FLT_MAX);
+}
+
+constexpr int kNoArg = INT_MAX;  // "no entry won yet" (local edge ids are < 2^31-1)
+
+// strict compare, first (smallest edge id) wins: mirrors oracle/fusedmm_oracle.c
+template <int OP>
+__device__ __forceinline__ bool better(float cand, float cur) {
+    return OP == OP_MAX ? (cand > cur) : (cand < cur);
+}
+template <int OP, typename IdT>
+__device__ __forceinline__ bool better_lex(float cand, IdT cand_id, float cur, IdT cur_id) {
+    return better<OP>(cand, cur) || (cand == cur && cand_id < cur_id);
+}
+
+// ------------------------------------------------------------------------------------
+// finalisation of one vector of one output row: single-segment rows directly, split rows by
+// the last-arriving segment warp after the in-order merge
+// ------------------------------------------------------------------------------------
+template <int OP, int VEC>
+__device__ __forceinline__ void finalize_store(const SpmmParams& p, int row, int deg, int kk,
+                                               float (&acc)[VEC], int (&arg)[VEC]) {
+    const size_t o = (size_t)row * (size_t)p.ldo + (size_t)kk;
+    // 16-byte stores need an aligned out row and the whole vector inside [0, k); otherwise
+    // (K % 4 != 0: the last vector of a row, or an unaligned out) fall back to scalars
+    const bool vec_ok = (VEC == 1) || (p.vec_store && kk + VEC <= p.k);
+    const int nvalid = min(VEC, p.k - kk);
+    if constexpr (OP == OP_SUM) {
+        if (p.flags & ISPLIB_FLAG_ACCUMULATE) {
+            float prev[VEC];
+            if (VEC >= 4 && vec_ok) {
+#pragma unroll
+                for (int q = 0; q < VEC / 4; ++q) {
+                    const float4 t = *(reinterpret_cast<const float4*>(p.out + o) + q);
+                    prev[(4 * q) % VEC] = t.x; prev[(4 * q + 1) % VEC] = t.y; prev[(4 * q + 2) % VEC] = t.z; prev[(4 * q + 3) % VEC] = t.w;
+                }
+            } else {
+#pragma unroll
+                for (int v = 0; v < VEC; ++v) prev[v] = (v < nvalid) ? p.out[o + v] : 0.f;
+            }
+#pragma unroll
+            for (int v = 0; v < VEC; ++v) acc[v] = prev[v] + acc[v];
+        }
+        if (p.div_mode) {
+            const float d = (p.div_mode == 2) ? __ldg(p.row_div + row) : (float)max(deg, 1);
+#pragma unroll
+            for (int v = 0; v < VEC; ++v) acc[v] = __fdiv_rn(acc[v], d);
+        }
+        if (vec_ok) {
+            store_vec_f<VEC>(p.out + o, acc);
+        } else {
+#pragma unroll
+            for (int v = 0; v < VEC; ++v) if (v < nvalid) __stcs(p.out + o + v, acc[v]);
+        }
+    } else {
+        long long gid[VEC];
+#pragma unroll
+        for (int v = 0; v < VEC; ++v) {
+            if (arg[v] == kNoArg) gid[v] = p.arg_sentinel;
+            else gid[v] = p.edge_ids ? (long long)__ldg(p.edge_ids + arg[v]) : (long long)arg[v];
+        }
+        if (p.flags & ISPLIB_FLAG_ACCUMULATE) {
+#pragma unroll
+            for (int v = 0; v < VEC; ++v) {
+                if (v < nvalid) {
+                    const float pv = p.out[o + v];
+                    const long long pa = p.arg_out[o + v];
+                    // previous block wins unless ours is strictly better / equal with smaller id
+                    if (!better_lex<OP, long long>(acc[v], gid[v], pv, pa)) { acc[v] = pv; gid[v] = pa; }
+                }
+            }
+        }
+        if (p.flags & ISPLIB_FLAG_EMPTY_ZERO) {
+#pragma unroll
+            for (int v = 0; v < VEC; ++v) if (gid[v] == p.arg_sentinel) acc[v] = 0.f;
+        }
+        if (vec_ok) {
+            store_vec_f<VEC>(p.out + o, acc);
+            store_vec_i64<VEC>(p.arg_out + o, gid);
+        } else {
+#pragma unroll
+            for (int v = 0; v < VEC; ++v)
+                if (v < nvalid) { __stcs(p.out + o + v, acc[v]); __stcs(p.arg_out + o + v, gid[v]); }
+        }
+    }
+}
+
+// ------------------------------------------------------------------------------------
+// what every gather strategy ends with: merge the lane groups, then finalise the row (single
+// segment) or publish a partial and let the last-arriving segment warp merge the row
+// ------------------------------------------------------------------------------------
+template <int OP, int VEC, int G, int LPL>
+__device__ __forceinline__ void finish_item(const SpmmParams& p, const int lane, const int row, const int eb,
+                                            const int ee, const int slot_id, const int (&koff)[LPL],
+                                            const bool (&kok)[LPL], float (&acc)[LPL][VEC], int (&arg)[LPL][VEC]) {
+    constexpr int NG = 32 / G;
+    constexpr unsigned FULL = 0xffffffffu;
+    const int g = lane / G;
+    // merge the NG lane groups (they hold interleaved entries of the same segment)
+    if constexpr (NG > 1) {
+#pragma unroll
+        for (int off = G; off < 32; off <<= 1) {
+#pragma unroll
+            for (int j = 0; j < LPL; ++j)
+#pragma unroll
+                for (int v = 0; v < VEC; ++v) {
+                    const float ov = __shfl_xor_sync(FULL, acc[j][v], off);
+                    if constexpr (OP == OP_SUM) {
+                        acc[j][v] += ov;
+                    } else {
+                        const int oa = __shfl_xor_sync(FULL, arg[j][v], off);
+                        if (better_lex<OP, int>(ov, oa, acc[j][v], arg[j][v])) { acc[j][v] = ov; arg[j][v] = oa; }
+                    }
+                }
+        }
+    }
+    const bool writer = (NG == 1) || (g == 0);   // group 0 holds the merged result
+
+    if (slot_id < 0) {   // the row fits this one segment: its degree is ee - eb
+        if (writer) {
+#pragma unroll
+            for (int j = 0; j < LPL; ++j)
+                if (kok[j]) finalize_store<OP, VEC>(p, row, ee - eb, koff[j], acc[j], arg[j]);
+        }
+        return;
+    }
+
+    // ---- split row: publish this segment's partial; the LAST segment warp to arrive merges
+    // all of the row's partials in segment order (the threadFenceReduction pattern: nobody
+    // waits, the order of the merge is fixed, so the result is deterministic and max/min/arg
+    // stay bit-exact) and finalises the row.  No second kernel launch.
+    const int pbase = __ldg(p.part_off + row);
+    const int nseg = __ldg(p.seg_off + row + 1) - __ldg(p.seg_off + row);
+    const int rb = __ldg(p.rowptr + row), re = __ldg(p.rowptr + row + 1);
+    if (writer) {
+        const size_t slot = (size_t)slot_id;
+#pragma unroll
+        for (int j = 0; j < LPL; ++j) {
+            if (kok[j]) {
+                const size_t o = slot * (size_t)p.kp + (size_t)koff[j];
+                if constexpr (VEC >= 4) {
+#pragma unroll
+                    for (int q = 0; q < VEC / 4; ++q) {
+                        __stcg(reinterpret_cast<float4*>(p.part_val + o) + q,
+                               make_float4(acc[j][(4 * q) % VEC], acc[j][(4 * q + 1) % VEC], acc[j][(4 * q + 2) % VEC], acc[j][(4 * q + 3) % VEC]));
+                        if constexpr (OP != OP_SUM)
+                            __stcg(reinterpret_cast<int4*>(p.part_arg + o) + q,
+                                   make_int4(arg[j][(4 * q) % VEC], arg[j][(4 * q + 1) % VEC], arg[j][(4 * q + 2) % VEC], arg[j][(4 * q + 3) % VEC]));
+                    }
+                } else {
+                    __stcg(p.part_val + o, acc[j][0]);
+                    if constexpr (OP != OP_SUM) __stcg(p.part_arg + o, arg[j][0]);
+                }
+            }
+        }
+    }
+    __threadfence();
+    __syncwarp();
+    int* const ticket_ptr = p.row_ticket + (size_t)blockIdx.y * (size_t)p.ticket_stride + (pbase >> 1);
+    int ticket = 0;
+    if (lane == 0) ticket = atomicAdd(ticket_ptr, 1);
+    ticket = __shfl_sync(FULL, ticket, 0);
+    if (ticket != nseg - 1) return;
+    __threadfence();
+    if (lane == 0) *ticket_ptr = 0;   // leave the counters zeroed for the next launch
+    if (!writer) return;
+#pragma unroll
+    for (int j = 0; j < LPL; ++j) {
+        if (!kok[j]) continue;
+        float macc[VEC];
+        int marg[VEC];
+#pragma unroll
+        for (int v = 0; v < VEC; ++v) { macc[v] = init_value<OP>(); marg[v] = kNoArg; }
+        const size_t o0 = (size_t)pbase * (size_t)p.kp + (size_t)koff[j];
+#pragma unroll 4
+        for (int t = 0; t < nseg; ++t) {
+            const size_t o = o0 + (size_t)t * (size_t)p.kp;
+            float pv[VEC];
+            int pa[VEC];
+            if constexpr (VEC >= 4) {
+#pragma unroll
+                for (int h = 0; h < VEC / 4; ++h) {
+                    const float4 q = __ldcg(reinterpret_cast<const float4*>(p.part_val + o) + h);
+                    pv[(4 * h) % VEC] = q.x; pv[(4 * h + 1) % VEC] = q.y; pv[(4 * h + 2) % VEC] = q.z; pv[(4 * h + 3) % VEC] = q.w;
+                    if constexpr (OP != OP_SUM) {
+                        const int4 r = __ldcg(reinterpret_cast<const int4*>(p.part_arg + o) + h);
+                        pa[(4 * h) % VEC] = r.x; pa[(4 * h + 1) % VEC] = r.y; pa[(4 * h + 2) % VEC] = r.z; pa[(4 * h + 3) % VEC] = r.w;
+                    }
+                }
+            } else {
+                pv[0] = __ldcg(p.part_val + o);
+                if constexpr (OP != OP_SUM) pa[0] = __ldcg(p.part_arg + o);
+            }
+#pragma unroll
+            for (int v = 0; v < VEC; ++v) {
+                if constexpr (OP == OP_SUM) {
+                    macc[v] += pv[v];
+                } else {
+                    // segments are in increasing edge order: strict compare keeps the first
+                    if (better<OP>(pv[v], macc[v])) { macc[v] = pv[v]; marg[v] = pa[v]; }
+                }
+            }
+        }
+        finalize_store<OP, VEC>(p, row, re - rb, koff[j], macc, marg);
+    }
+}
+
+// ------------------------------------------------------------------------------------
+// main kernel: one warp = one row segment x one K tile
+// ------------------------------------------------------------------------------------
+// PARTIAL: some lanes of the widest K tile fall outside [k0, kend) (K = 100, 200, 47 ...).
+// Those lanes gather the tile's first vector instead (same 16 bytes a valid lane reads, so
+// no extra traffic, and no predicate or zero-fill on the hot loads) and never store.
+template <int OP, int VEC, int G, int LPL, int U, bool PARTIAL>
+__global__ void __launch_bounds__(256)
+spmm_seg_kernel(const __grid_constant__ SpmmParams p) {
+    constexpr int NG = 32 / G;         // lane groups per warp = entries gathered per step
+    constexpr unsigned FULL = 0xffffffffu;
+    static_assert(32 % (NG * U) == 0, "a 32-entry chunk must be a whole number of steps");
+
+    const int lane = threadIdx.x & 31;
+    const int item = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    if (item >= p.num_items) return;
+
+    // one 16-byte descriptor per work item {row, first entry, end entry, partial slot or -1}:
+    // a single load instead of the item_row -> seg_off -> rowptr chain, which matters for
+    // short rows (products-shape: ~50 entries per row, the chain was ~1/3 of a warp's life)
+    const int4 desc = __ldg(p.item_desc + item);
+    const int row = desc.x, eb = desc.y, ee = desc.z, slot_id = desc.w;
+
+    const int g = lane / G;
+    const int lg = lane % G;
+    const int k0 = blockIdx.y * p.tile_w;
+    // VEC=4 loads may read up to 3 padding floats past K (the launcher checked ldx >= roundup4(K))
+    const int keff = (VEC > 1) ? ((p.k + VEC - 1) & ~(VEC - 1)) : p.k;
+    const int kend = min(keff, k0 + p.tile_w);
+
+    int koff[LPL];
+    bool kok[LPL];
+#pragma unroll
+    for (int j = 0; j < LPL; ++j) {
+        koff[j] = k0 + (lg + j * G) * VEC;
+        kok[j] = koff[j] < kend;
+    }
+
+    // gather address = lane base + col * ldx_bytes: one IMAD.WIDE.U32 per gathered row
+    // instead of a 64x64-bit multiply; further vectors of the lane sit at immediate offsets
+    const char* xlane[PARTIAL ? LPL : 1];
+    xlane[0] = reinterpret_cast<const char*>(p.x + (kok[0] ? koff[0] : k0));
+    if constexpr (PARTIAL) {
+#pragma unroll
+        for (int j = 1; j < LPL; ++j) xlane[j] = reinterpret_cast<const char*>(p.x + (kok[j] ? koff[j] : k0));
+    }
+    const unsigned ldxb = (unsigned)p.ldx * 4u;
+
+    float acc[LPL][VEC];
+    int arg[LPL][VEC];
+#pragma unroll
+    for (int j = 0; j < LPL; ++j)
+#pragma unroll
+        for (int v = 0; v < VEC; ++v) { acc[j][v] = init_value<OP>(); arg[j][v] = kNoArg; }
+
+    const bool has_val = (p.val != nullptr);
+    ISPLIB_XPOL_DECL
+
+    // one 32-entry chunk of (col, val) per lane, one chunk prefetched ahead
+    unsigned c_next = 0;
+    float a_next = 0.f;
+    if (eb + lane < ee) {
+        c_next = (unsigned)__ldcs(p.col + eb + lane);
+        a_next = has_val ? __ldcs(p.val + eb + lane) : 1.f;
+    }
+
+    for (int e0 = eb; e0 < ee; e0 += 32) {
+        const unsigned c = c_next;
+        const float a = a_next;
+        const int cnt = min(32, ee - e0);
+        {
+            const int en = e0 + 32 + lane;
+            if (en < ee) {
+                c_next = (unsigned)__ldcs(p.col + en);
+                a_next = has_val ? __ldcs(p.val + en) : 1.f;
+            }
+        }
+        if (cnt == 32) {
+#pragma unroll
+            for (int t = 0; t < 32; t += NG * U) {
+                float xv[U][LPL][VEC];
+                float aa[U];
+#pragma unroll
+                for (int u = 0; u < U; ++u) {
+                    const int idx = t + u * NG + g;
+                    const unsigned cc = __shfl_sync(FULL, c, idx);
+                    aa[u] = __shfl_sync(FULL, a, idx);
+                    const unsigned long long off = (unsigned long long)cc * ldxb;
+#pragma unroll
+                    for (int j = 0; j < LPL; ++j) {
+                        if constexpr (PARTIAL) load_vec<VEC>(reinterpret_cast<const float*>(xlane[j] + off), xv[u][j] ISPLIB_XPOL_ARG);
+                        else load_vec<VEC>(reinterpret_cast<const float*>(xlane[0] + off) + j * G * VEC, xv[u][j] ISPLIB_XPOL_ARG);
+                    }
+                }
+#pragma unroll
+                for (int u = 0; u < U; ++u) {
+                    const int e = e0 + t + u * NG + g;
+#pragma unroll
+                    for (int j = 0; j < LPL; ++j)
+#pragma unroll
+                        for (int v = 0; v < VEC; ++v) {
+                            if constexpr (OP == OP_SUM) {
+                                acc[j][v] = fmaf(aa[u], xv[u][j][v], acc[j][v]);
+                            } else {
+                                const float tt = __fmul_rn(aa[u], xv[u][j][v]);
+                                if (better<OP>(tt, acc[j][v])) { acc[j][v] = tt; arg[j][v] = e; }
+                            }
+                        }
+                }
+            }
+        } else {
+            // ragged tail of the segment: same steps, predicated per entry
+            for (int t = 0; t < cnt; t += NG * U) {
+                float xv[U][LPL][VEC];
+                float aa[U];
+                bool ok[U];
+#pragma unroll
+                for (int u = 0; u < U; ++u) {
+                    const int idx = t + u * NG + g;
+                    ok[u] = idx < cnt;
+                    const unsigned cc = __shfl_sync(FULL, c, idx & 31);
+                    aa[u] = __shfl_sync(FULL, a, idx & 31);
+                    const unsigned long long off = (unsigned long long)cc * ldxb;
+                    if (ok[u]) {
+#pragma unroll
+                        for (int j = 0; j < LPL; ++j) {
+                            if constexpr (PARTIAL) load_vec<VEC>(reinterpret_cast<const float*>(xlane[j] + off), xv[u][j] ISPLIB_XPOL_ARG);
+                            else load_vec<VEC>(reinterpret_cast<const float*>(xlane[0] + off) + j * G * VEC, xv[u][j] ISPLIB_XPOL_ARG);
+                        }
+                    }
+                }
+#pragma unroll
+                for (int u = 0; u < U; ++u) {
+                    const int e = e0 + t + u * NG + g;
+                    if (ok[u]) {
+#pragma unroll
+                        for (int j = 0; j < LPL; ++j)
+#pragma unroll
+                            for (int v = 0; v < VEC; ++v) {
+                                if constexpr (OP == OP_SUM) {
+                                    acc[j][v] = fmaf(aa[u], xv[u][j][v], acc[j][v]);
+                                } else {
+                                    const float tt = __fmul_rn(aa[u], xv[u][j][v]);
+                                    if (better<OP>(tt, acc[j][v])) { acc[j][v] = tt; arg[j][v] = e; }
+                                }
+                            }
+                    }
+                }
+            }
+        }
+    }
+
+    finish_item<OP, VEC, G, LPL>(p, lane, row, eb, ee, slot_id, koff, kok, acc, arg);
+}
+
+// ------------------------------------------------------------------------------------
+// bulk-copy gather variant: the dense rows are fetched by the TMA engine
+// (cp.async.bulk global -> shared, completion on an mbarrier) instead of by LDG into registers.
+// Every lane issues the bulk copy of ONE row (no address math or data registers per 16 bytes),
+// SE rows per stage and STAGES stages per warp are in flight -- bytes in flight are bounded by
+// shared memory (24-48 KB per warp), not by registers -- and the FMA / compare loop reads the
+// rows back with conflict-free LDS.128.  Warp-private ring: no __syncthreads, each warp owns
+// its stage buffers and its mbarriers.  Same work items, same finish_item as the LDG kernel.
+// ------------------------------------------------------------------------------------
+__device__ __forceinline__ unsigned smem_u32(const void* ptr) { return (unsigned)__cvta_generic_to_shared(ptr); }
+__device__ __forceinline__ void mbar_init(unsigned bar, unsigned count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive_expect_tx(unsigned bar, unsigned bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ bool mbar_try_wait(unsigned bar, unsigned parity) {
+    unsigned ok;
+    asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
+                 : "=r"(ok) : "r"(bar), "r"(parity) : "memory");
+    return ok != 0;
+}
+__device__ __forceinline__ void bulk_g2s(unsigned dst, const void* src, unsigned bytes, unsigned bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                 ::"r"(dst), "l"(src), "r"(bytes), "r"(bar) : "memory");
+}
+
+constexpr int kBulkSE = 16;   // rows (entries) per stage
+
+template <int OP, int G, int LPL, int STAGES>
+__global__ void __launch_bounds__(256)
+spmm_bulk_kernel(const __grid_constant__ SpmmParams p) {
+    constexpr int VEC = 4;
+    constexpr int NG = 32 / G;
+    constexpr int SE = kBulkSE;
+    constexpr int ROW_STRIDE = G * LPL * 16;          // bytes of one staged row slot
+    constexpr int STAGE_BYTES = SE * ROW_STRIDE;
+    constexpr unsigned FULL = 0xffffffffu;
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+
+    const int lane = threadIdx.x & 31;
+    const int wib = threadIdx.x >> 5;
+    const int nwarps = blockDim.x >> 5;
+    const int item = blockIdx.x * nwarps + wib;
+    if (item >= p.num_items) return;
+
+    unsigned char* my = smem_raw + (size_t)wib * (STAGES * STAGE_BYTES);
+    unsigned long long* bars = reinterpret_cast<unsigned long long*>(smem_raw + (size_t)nwarps * (STAGES * STAGE_BYTES)) + wib * STAGES;
+    const unsigned buf0 = smem_u32(my);
+    const unsigned bar0 = smem_u32(bars);
+    if (lane == 0) {
+#pragma unroll
+        for (int i = 0; i < STAGES; ++i) mbar_init(bar0 + 8u * i, 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncwarp();
+
+    const int4 desc = __ldg(p.item_desc + item);
+    const int row = desc.x, eb = desc.y, ee = desc.z, slot_id = desc.w;
+    const int g = lane / G, lg = lane % G;
+    const int k0 = blockIdx.y * p.tile_w;
+    const int keff = (p.k + 3) & ~3;
+    const int kend = min(keff, k0 + p.tile_w);
+    const unsigned row_bytes = (unsigned)(kend - k0) * 4u;
+
+    int koff[LPL];
+    bool kok[LPL];
+#pragma unroll
+    for (int j = 0; j < LPL; ++j) { koff[j] = k0 + (lg + j * G) * VEC; kok[j] = koff[j] < kend; }
+    float acc[LPL][VEC];
+    int arg[LPL][VEC];
+#pragma unroll
+    for (int j = 0; j < LPL; ++j)
+#pragma unroll
+        for (int v = 0; v < VEC; ++v) { acc[j][v] = init_value<OP>(); arg[j][v] = kNoArg; }
+
+    const bool has_val = (p.val != nullptr);
+    const char* const xbase = reinterpret_cast<const char*>(p.x + k0);
+    const unsigned ldxb = (unsigned)p.ldx * 4u;
+    const int nstages = (ee - eb + SE - 1) / SE;
+    float a_reg[STAGES];
+
+    auto issue = [&](int s, int i) {
+        if (s >= nstages) return;
+        const int e0 = eb + s * SE;
+        const int cnt = min(SE, ee - e0);
+        unsigned c = 0;
+        a_reg[i] = 0.f;
+        if (lane < cnt) {
+            c = (unsigned)__ldcs(p.col + e0 + lane);
+            a_reg[i] = has_val ? __ldcs(p.val + e0 + lane) : 1.f;
+        }
+        if (lane == 0) mbar_arrive_expect_tx(bar0 + 8u * i, (unsigned)cnt * row_bytes);
+        __syncwarp();
+        if (lane < cnt)
+            bulk_g2s(buf0 + (unsigned)(i * STAGE_BYTES + lane * ROW_STRIDE), xbase + (unsigned long long)c * ldxb,
+                     row_bytes, bar0 + 8u * i);
+    };
+
+    // prologue: fill the ring
+#pragma unroll
+    for (int i = 0; i < STAGES; ++i) issue(i, i);
+
+    for (int base = 0; base < nstages; base += STAGES) {
+        const unsigned parity = (unsigned)((base / STAGES) & 1);
+#pragma unroll
+        for (int i = 0; i < STAGES; ++i) {
+            const int s = base + i;
+            if (s < nstages) {                      // warp-uniform
+                const int e0 = eb + s * SE;
+                const int cnt = min(SE, ee - e0);
+                while (!mbar_try_wait(bar0 + 8u * i, parity)) { }
+                const unsigned char* stage = my + i * STAGE_BYTES;
+#pragma unroll
+                for (int t = 0; t < SE; t += NG) {
+                    const int idx = t + g;
+                    const float a = __shfl_sync(FULL, a_reg[i], idx);
+                    if (idx < cnt) {
+                        const int e = e0 + idx;
+#pragma unroll
+                        for (int j = 0; j < LPL; ++j) {
+                            if (kok[j]) {
+                                const float4 q = *reinterpret_cast<const float4*>(stage + idx * ROW_STRIDE + (lg + j * G) * 16);
+                                const float xv[4] = {q.x, q.y, q.z, q.w};
+#pragma unroll
+                                for (int v = 0; v < VEC; ++v) {
+                                    if constexpr (OP == OP_SUM) {
+                                        acc[j][v] = fmaf(a, xv[v], acc[j][v]);
+                                    } else {
+                                        const float tt = __fmul_rn(a, xv[v]);
+                                        if (better<OP>(tt, acc[j][v])) { acc[j][v] = tt; arg[j][v] = e; }
+                                    }
+                                }
+                            }
+                        }
+                    }
+                }
+                // every lane is done reading this stage before the TMA engine may overwrite it
+                __syncwarp();
+                asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+                issue(s + STAGES, i);
+            }
+        }
+    }
+    finish_item<OP, VEC, G, LPL>(p, lane, row, eb, ee, slot_id, koff, kok, acc, arg);
+}
+
+struct TileShape { int vec, g, lpl, tile_w, ntiles; };
+typedef void (*SegKernel)(const SpmmParams);
+
+template <int OP, int VEC, int G, int LPL>
+static inline SegKernel pick_u(int u, bool partial) {
+    constexpr int NG = 32 / G;
+    // keep (entries per step) * U <= 32 and at most 64 staged floats per lane
+    if constexpr (LPL * VEC * 8 <= 64)
+        if (u >= 8 && NG * 8 <= 32)
+            return partial ? spmm_seg_kernel<OP, VEC, G, LPL, 8, true> : spmm_seg_kernel<OP, VEC, G, LPL, 8, false>;
+    if (u <= 2)
+        return partial ? spmm_seg_kernel<OP, VEC, G, LPL, 2, true> : spmm_seg_kernel<OP, VEC, G, LPL, 2, false>;
+    if (NG * 4 <= 32)
+        return partial ? spmm_seg_kernel<OP, VEC, G, LPL, 4, true> : spmm_seg_kernel<OP, VEC, G, LPL, 4, false>;
+    return nullptr;
+}
+
+template <int OP, int G, int LPL>
+static inline SegKernel pick_u8(int u, bool partial) {   // 32-byte vectors: U = 2 or 4 gathers in flight
+    if (u <= 2)
+        return partial ? spmm_seg_kernel<OP, 8, G, LPL, 2, true> : spmm_seg_kernel<OP, 8, G, LPL, 2, false>;
+    return partial ? spmm_seg_kernel<OP, 8, G, LPL, 4, true> : spmm_seg_kernel<OP, 8, G, LPL, 4, false>;
+}
+
+template <int OP>
+static inline SegKernel pick_kernel(const TileShape& t, int u, bool partial) {
+    if (t.vec == 8) {
+        if (t.g == 4) return pick_u8<OP, 4, 1>(u, partial);
+        if (t.g == 8) return pick_u8<OP, 8, 1>(u, partial);
+        if (t.g == 16) return pick_u8<OP, 16, 1>(u, partial);
+        if (t.g == 32 && t.lpl == 1) return pick_u8<OP, 32, 1>(u, partial);
+        if (t.g == 32 && t.lpl == 2) return pick_u8<OP, 32, 2>(u <= 2 ? 2 : 2, partial);
+        return nullptr;
+    }
+    if (t.vec == 4) {
+        if (t.g == 8 && t.lpl == 1) return pick_u<OP, 4, 8, 1>(u, partial);
+        if (t.g == 16 && t.lpl == 1) return pick_u<OP, 4, 16, 1>(u, partial);
+        if (t.g == 32 && t.lpl == 1) return pick_u<OP, 4, 32, 1>(u, partial);
+        if (t.g == 32 && t.lpl == 2) return pick_u<OP, 4, 32, 2>(u, partial);
+        if (t.g == 32 && t.lpl == 4) return pick_u<OP, 4, 32, 4>(u, partial);
+    } else {
+        if (t.lpl == 1) return pick_u<OP, 1, 32, 1>(u, partial);
+        if (t.lpl == 2) return pick_u<OP, 1, 32, 2>(u, partial);
+        if (t.lpl == 4) return pick_u<OP, 1, 32, 4>(u, partial);
+    }
+    return nullptr;
+}
+
+template <int OP, int G, int LPL>
+static inline SegKernel pick_bulk_stages(int stages) {
+    (void)stages;
+    return spmm_bulk_kernel<OP, G, LPL, 3>;
+}
+
+template <int OP>
+static inline SegKernel pick_bulk_kernel(const TileShape& t, int stages) {
+    if (t.vec != 4) return nullptr;
+    if (t.g == 8 && t.lpl == 1) return pick_bulk_stages<OP, 8, 1>(stages);
+    if (t.g == 16 && t.lpl == 1) return pick_bulk_stages<OP, 16, 1>(stages);
+    if (t.g == 32 && t.lpl == 1) return pick_bulk_stages<OP, 32, 1>(stages);
+    if (t.g == 32 && t.lpl == 2) return pick_bulk_stages<OP, 32, 2>(stages);
+    if (t.g == 32 && t.lpl == 4) return pick_bulk_stages<OP, 32, 4>(stages);
+    return nullptr;
+}
+
+
+}  // namespace isplib

@@ -132,8 +132,12 @@ int main() {
         run_gather<16, 4>(buf, bytes, sink, 32);
         run_gather<16, 8>(buf, bytes, sink, 64);
         run_gather<8, 8>(buf, bytes, sink, 64);
+        run_gather256<16, 4>(buf, bytes, sink, 16);
+        run_gather256<16, 4>(buf, bytes, sink, 24);
         run_gather256<16, 4>(buf, bytes, sink, 32);
         run_gather256<16, 4>(buf, bytes, sink, 64);
+        run_gather<32, 4>(buf, bytes, sink, 16);
+        run_gather<32, 4>(buf, bytes, sink, 24);
         run_gather256<8, 4>(buf, bytes, sink, 32);
         run_gather256<8, 2>(buf, bytes, sink, 64);
     }
