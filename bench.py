@@ -297,8 +297,12 @@ def run_ours(args):
 
         def step(i):
             capi.spmm_csr(reduce, rp32, co32, g.value, xs[i & 1], plan, best, out=out, arg_out=arg)
-        launches_per_step = 1   # one spmm_seg_kernel per SpMM (split rows are merged inside it)
         variant_name = capi.variant_names()[best]
+        # one kernel per SpMM (split rows are merged inside it); */seq variants launch once per K tile
+        launches_per_step = 1
+        if variant_name.endswith("/seq"):
+            kt = int(variant_name.split("/kt")[1].split("/")[0])
+            launches_per_step = K // kt
         tune = {capi.variant_names()[v]: round(t, 3) for v, t in enumerate(times) if t >= 0}
     else:
         op = RowPartitionedSpMM(g.rowptr, g.col, g.value, N, device=dev)
@@ -486,11 +490,13 @@ def run_ours(args):
     roofline = {"bound": "hbm", "achieved": round(value / world, 2) if world > 1 else round(value, 2), "peak": peak,
                 "unit": "GB/s", "frac": round((value / world) / peak, 4),
                 "traffic": NCU_TRAFFIC_BYTES.get((args.shape, K, reduce, variant_name)) if world == 1 else None,
-                "kernel": "isplib::spmm_seg_kernel",
+                "kernel": ("isplib::spmm_lean256_kernel" if variant_name.startswith("lean256")
+                           else "isplib::spmm_bulk_kernel" if variant_name.startswith("bulk")
+                           else "isplib::spmm_seg_kernel"),
                 "peak_source": peak_src,
-                "algorithmic_bytes_per_launch": b_alg // world,
-                "note": "achieved = B_alg per step / CUDA-event step time; a step is exactly one launch of the "
-                        "segment kernel. B_alg counts one K-row gather per stored entry, so it exceeds HBM "
+                "algorithmic_bytes_per_launch": b_alg // world // (launches_per_step if world == 1 else 1),
+                "note": "achieved = B_alg per step / CUDA-event step time; a step is exactly one launch of "
+                        "that kernel (one per K tile for */seq variants). B_alg counts one K-row gather per stored entry, so it exceeds HBM "
                         "traffic when X rows hit in the 126 MB L2 (ncu dram bytes in profiles/)."}
     line = {
         "metric": "spmm_sum_effective_gbs", "value": round(value, 2), "unit": "GB/s", "n_gpus": world,

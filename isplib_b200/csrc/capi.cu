@@ -111,6 +111,7 @@ static int fill_params(SpmmParams& p, int reduce, int64_t m, int64_t n, int64_t 
     p.num_items = (int)info->num_items;
     p.num_split_rows = (int)info->num_split_rows;
     p.seg_len = info->seg_len;
+    p.tile_base = 0;
     p.flags = flags;
     p.div_mode = row_divisor ? 2 : (reduce == ISPLIB_REDUCE_MEAN ? 1 : 0);
     return ISPLIB_SUCCESS;
@@ -185,6 +186,7 @@ extern "C" int isplib_b200_spmm_autotune(int reduce, int64_t m, int64_t n, int64
         // for every K tile, 8 warps only untiled); the rest only with ISPLIB_B200_TUNE_ALL=1
         if (d->method == 0 && !tune_all && !(d->unroll == 4 && (d->warps == 4 || d->kt == 0))) continue;
         if (d->method == 3 && !tune_all) continue;   // 256-bit gathers: measured slower here (register pressure)
+        if (d->method == 5 && (reduce == ISPLIB_REDUCE_MAX || reduce == ISPLIB_REDUCE_MIN) && !tune_all) continue;   // lean max/min: never ahead of seg/* (r1_kbench)
         rc = launch_spmm(reduce, p, nnz, v, stream);  // warm-up
         if (rc) break;
         cudaEventRecord(e0, stream);

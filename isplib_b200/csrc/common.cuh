@@ -99,6 +99,7 @@ struct SpmmParams {
     long long ldx, ldo, arg_sentinel;
     int m, k, tile_w, num_items, num_split_rows, seg_len;
     int ticket_stride, ticket_capacity;   // ints per K tile / ints available
+    int tile_base;  // K tile index of blockIdx.y == 0 (sequential-tile launches)
     int kp;         // row stride of the partial buffers = roundup8(k)
     int vec_store;  // 1: out (and arg_out) rows take aligned 16-byte stores
     int flags;      // ISPLIB_FLAG_*
@@ -113,6 +114,7 @@ struct VariantDesc {
     int warps;    // warps per CTA
     int unroll;   // gathers in flight per lane group
     int kt;       // K tile width in elements, 0 = widest the lane mapping allows
+    int seq;      // 1: one launch per K tile (stream-ordered) instead of grid.y tiles
 };
 
 int variant_count();

@@ -27,37 +27,47 @@ namespace isplib {
 // variant table
 // ------------------------------------------------------------------------------------
 static const VariantDesc kVariants[] = {
-    {"seg/w8/u4/kfull", 0, 8, 4, 0},
-    {"seg/w4/u4/kfull", 0, 4, 4, 0},
-    {"seg/w8/u8/kfull", 0, 8, 8, 0},
-    {"seg/w4/u8/kfull", 0, 4, 8, 0},
-    {"seg/w8/u4/kt128", 0, 8, 4, 128},
-    {"seg/w4/u4/kt128", 0, 4, 4, 128},
-    {"seg/w8/u4/kt64", 0, 8, 4, 64},
-    {"seg/w4/u4/kt64", 0, 4, 4, 64},
-    {"seg/w8/u4/kt32", 0, 8, 4, 32},
-    {"seg/w4/u4/kt32", 0, 4, 4, 32},
-    {"seg/w8/u8/kt64", 0, 8, 8, 64},
-    {"seg/w4/u2/kfull", 0, 4, 2, 0},
-    {"seg/w4/u2/kt64", 0, 4, 2, 64},
-    {"seg/w8/u2/kt64", 0, 8, 2, 64},
+    {"seg/w8/u4/kfull", 0, 8, 4, 0, 0},
+    {"seg/w4/u4/kfull", 0, 4, 4, 0, 0},
+    {"seg/w8/u8/kfull", 0, 8, 8, 0, 0},
+    {"seg/w4/u8/kfull", 0, 4, 8, 0, 0},
+    {"seg/w8/u4/kt128", 0, 8, 4, 128, 0},
+    {"seg/w4/u4/kt128", 0, 4, 4, 128, 0},
+    {"seg/w8/u4/kt64", 0, 8, 4, 64, 0},
+    {"seg/w4/u4/kt64", 0, 4, 4, 64, 0},
+    {"seg/w8/u4/kt32", 0, 8, 4, 32, 0},
+    {"seg/w4/u4/kt32", 0, 4, 4, 32, 0},
+    {"seg/w8/u8/kt64", 0, 8, 8, 64, 0},
+    {"seg/w4/u2/kfull", 0, 4, 2, 0, 0},
+    {"seg/w4/u2/kt64", 0, 4, 2, 64, 0},
+    {"seg/w8/u2/kt64", 0, 8, 2, 64, 0},
     // method 3: 32-byte gathers (LDG.E.256), rows 32-byte aligned and padded to a multiple of 8.
     // A bare gather loop gains +25 % from 256-bit loads (profiles/r1_l2probe.txt), but in this
     // kernel 4 x 32 B in flight per lane cost 101 registers (20 warps/SM) and U=2 loses the gain:
     // 5.1 ms vs 4.2 ms on Reddit-shape K=128.  Selectable by id / ISPLIB_B200_TUNE_ALL=1 only.
-    {"seg256/w4/u4/kfull", 3, 4, 4, 0},
-    {"seg256/w4/u2/kfull", 3, 4, 2, 0},
-    {"seg256/w4/u4/kt128", 3, 4, 4, 128},
-    {"seg256/w4/u4/kt64", 3, 4, 4, 64},
-    {"seg256/w4/u2/kt64", 3, 4, 2, 64},
-    {"seg256/w8/u2/kfull", 3, 8, 2, 0},
+    {"seg256/w4/u4/kfull", 3, 4, 4, 0, 0},
+    {"seg256/w4/u2/kfull", 3, 4, 2, 0, 0},
+    {"seg256/w4/u4/kt128", 3, 4, 4, 128, 0},
+    {"seg256/w4/u4/kt64", 3, 4, 4, 64, 0},
+    {"seg256/w4/u2/kt64", 3, 4, 2, 64, 0},
+    {"seg256/w8/u2/kfull", 3, 8, 2, 0, 0},
+    // method 5: lean kernel with 32-byte gathers inside 64 (sum) / 80 (max, min) registers;
+    // full tiles of 32/64/128/256 floats only
+    {"lean256/w4/kfull", 5, 4, 4, 0, 0},
+    {"lean256/w4/kt128", 5, 4, 4, 128, 0},
+    {"lean256/w4/kt64", 5, 4, 4, 64, 0},
+    // sequential K tiles: one launch per tile, so only ONE [N, tile] slab of X is live in L2 at a
+    // time (with grid.y tiles the tail of tile t overlaps the head of tile t+1)
+    {"seg/w4/u4/kt64/seq", 0, 4, 4, 64, 1},
+    {"lean256/w4/kt64/seq", 5, 4, 4, 64, 1},
+    {"lean256/w4/kt128/seq", 5, 4, 4, 128, 1},
     // method 1: TMA bulk-copy gather through a per-warp shared-memory ring; `unroll` = stages
     // (measured 3x slower than the LDG gather for 256-512 B rows -- profiles/r1_kbench_bulk.txt:
     // the copy engine retires one small bulk request per ~14-30 cycles per SM -- so the on-device
     // selection skips these unless ISPLIB_B200_TUNE_BULK=1; they stay selectable by id)
-    {"bulk/w4/s3/kfull", 1, 4, 3, 0},
-    {"bulk/w4/s3/kt64", 1, 4, 3, 64},
-    {"bulk/w8/s3/kt64", 1, 8, 3, 64},
+    {"bulk/w4/s3/kfull", 1, 4, 3, 0, 0},
+    {"bulk/w4/s3/kt64", 1, 4, 3, 64, 0},
+    {"bulk/w8/s3/kt64", 1, 8, 3, 64, 0},
 };
 int variant_count() { return (int)(sizeof(kVariants) / sizeof(kVariants[0])); }
 const VariantDesc* variant_desc(int v) {
@@ -77,6 +87,9 @@ SegKernel seg_kernel_min(const TileShape&, int, bool);
 SegKernel bulk_kernel_sum(const TileShape&, int);
 SegKernel bulk_kernel_max(const TileShape&, int);
 SegKernel bulk_kernel_min(const TileShape&, int);
+SegKernel lean256_kernel_sum(int g);
+SegKernel lean256_kernel_max(int g);
+SegKernel lean256_kernel_min(int g);
 
 static bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15u) == 0; }
 
@@ -126,6 +139,12 @@ bool spmm_variant_supported(int variant, int reduce, int64_t k, int64_t ldx, int
     if (!d || reduce < 0 || reduce > 3 || k <= 0) return false;
     (void)ldo; (void)out;
     const int vec = pick_vec(k, ldx, x);
+    if (d->method == 5) {   // lean 32-byte kernel: full tiles of 32..256 floats
+        if (!vec8_ok(k, ldx, x)) return false;
+        const int64_t tw = d->kt > 0 ? d->kt : k;
+        if (d->kt > 0 && d->kt >= k) return false;
+        return (tw == 32 || tw == 64 || tw == 128 || tw == 256) && k % tw == 0;
+    }
     if (d->method == 3) {   // 32-byte gathers
         if (!vec8_ok(k, ldx, x)) return false;
         if (d->kt > 0 && (d->kt >= k || d->kt % 8 != 0)) return false;
@@ -144,31 +163,40 @@ bool spmm_variant_supported(int variant, int reduce, int64_t k, int64_t ldx, int
     return true;
 }
 
-static int find_variant(int warps, int unroll, int kt) {
+static int find_variant(int method, int warps, int unroll, int kt, int seq = 0) {
     for (int v = 0; v < variant_count(); ++v)
-        if (kVariants[v].warps == warps && kVariants[v].unroll == unroll && kVariants[v].kt == kt) return v;
-    return 0;
+        if (kVariants[v].method == method && kVariants[v].seq == seq && kVariants[v].warps == warps &&
+            kVariants[v].unroll == unroll && kVariants[v].kt == kt) return v;
+    return -1;
 }
 
 // Shape-only default (the op layer replaces it by the measured winner when autotuning is on).
-// Measured on B200 (profiles/r1_kbench_*.txt): 4 warps/CTA and U=4 win everywhere; a K tile
-// pays off only when it makes an [n, tile] slab of x L2-resident (126 MB L2) while x itself
-// is not (Reddit-shape K>=128 -> 64-wide); when nothing can be resident (products/amazon
-// shapes) 128-wide tiles are marginally ahead for K > 128.
+// Measured on B200 (profiles/r1_kbench_*.txt): 4 warps/CTA and 4 gathers in flight win
+// everywhere; sum/mean on 32-byte-aligned rows of 32..256 floats prefer the lean 256-bit kernel;
+// a K tile pays off only when it makes an [n, tile] slab of x L2-resident (126 MB L2) while x
+// itself is not (Reddit-shape K>=128 -> 64-wide); when nothing can be resident
+// (products/amazon shapes) 128-wide tiles are marginally ahead for K > 128.
 int spmm_variant_default(int reduce, int64_t n, int64_t k, int64_t ldx, int64_t ldo, const void* x,
                          const void* out, double avg_degree) {
-    (void)reduce; (void)avg_degree;
+    (void)avg_degree;
     const double MB = 1024.0 * 1024.0;
     const double x_bytes = (double)n * (double)k * 4.0;
+    const bool slab64 = (double)n * 64.0 * 4.0 <= 64.0 * MB;
+    if (reduce == ISPLIB_REDUCE_SUM || reduce == ISPLIB_REDUCE_MEAN) {   // for max / min the lean kernel measured 3-20 % slower (80 registers)
+        int v = -1;
+        if (x_bytes > 96.0 * MB && k > 64 && slab64) v = find_variant(5, 4, 4, 64);
+        else v = find_variant(5, 4, 4, 0);
+        if (v >= 0 && spmm_variant_supported(v, reduce, k, ldx, ldo, x, out)) return v;
+    }
     int kt = 0;
     if (x_bytes > 96.0 * MB) {
         if (k > 128 && (double)n * 128.0 * 4.0 <= 64.0 * MB) kt = 128;
-        else if (k > 64 && (double)n * 64.0 * 4.0 <= 64.0 * MB) kt = 64;
+        else if (k > 64 && slab64) kt = 64;
         else if (k > 128) kt = 128;
     }
-    int v = find_variant(4, 4, kt);
-    if (!spmm_variant_supported(v, reduce, k, ldx, ldo, x, out)) v = find_variant(4, 4, 0);
-    return v;
+    int v = find_variant(0, 4, 4, kt);
+    if (v < 0 || !spmm_variant_supported(v, reduce, k, ldx, ldo, x, out)) v = find_variant(0, 4, 4, 0);
+    return v < 0 ? 0 : v;
 }
 
 int launch_spmm(int reduce, const SpmmParams& base, int64_t nnz, int variant, cudaStream_t stream) {
@@ -183,7 +211,13 @@ int launch_spmm(int reduce, const SpmmParams& base, int64_t nnz, int variant, cu
         if (!vec8_ok(p.k, p.ldx, p.x)) return ISPLIB_NO_OPT_IMPL;
         vec = 8;
     }
-    const TileShape t = pick_shape(vec, p.k, d->kt);
+    TileShape t = pick_shape(vec, p.k, d->kt);
+    if (d->method == 5) {
+        if (!vec8_ok(p.k, p.ldx, p.x)) return ISPLIB_NO_OPT_IMPL;
+        const int tw = d->kt > 0 ? d->kt : p.k;
+        t.vec = 8; t.g = tw / 8; t.lpl = 1; t.tile_w = tw; t.ntiles = p.k / tw;
+        vec = 8;
+    }
     const int keff = vec > 1 ? (p.k + vec - 1) / vec * vec : p.k;
     p.kp = (p.k + 7) & ~7;
     p.vec_store = (p.k % 4 == 0 && p.ldo % 4 == 0 && aligned16(p.out) && (!p.arg_out || aligned16(p.arg_out))) ? 1 : 0;
@@ -194,7 +228,9 @@ int launch_spmm(int reduce, const SpmmParams& base, int64_t nnz, int variant, cu
     const bool partial = (t.tile_w != t.g * t.lpl * t.vec) || (keff % t.tile_w != 0);
     SegKernel kern = nullptr;
     size_t smem = 0;
-    if (d->method == 1) {
+    if (d->method == 5) {
+        kern = op == OP_SUM ? lean256_kernel_sum(t.g) : (op == OP_MAX ? lean256_kernel_max(t.g) : lean256_kernel_min(t.g));
+    } else if (d->method == 1) {
         if (op == OP_SUM) kern = bulk_kernel_sum(t, d->unroll);
         else if (op == OP_MAX) kern = bulk_kernel_max(t, d->unroll);
         else kern = bulk_kernel_min(t, d->unroll);
@@ -219,6 +255,16 @@ int launch_spmm(int reduce, const SpmmParams& base, int64_t nnz, int variant, cu
         // anyway so an aborted launch cannot poison the next one)
         if ((size_t)t.ntiles * (size_t)p.ticket_stride > (size_t)p.ticket_capacity) return ISPLIB_NOT_ENOUGH_MEM;
         ISPLIB_CUDA_TRY(cudaMemsetAsync(p.row_ticket, 0, (size_t)t.ntiles * (size_t)p.ticket_stride * sizeof(int), stream));
+    }
+    p.tile_base = 0;
+    if (d->seq && t.ntiles > 1) {
+        const dim3 grid1(grid.x, 1);
+        for (int tile = 0; tile < t.ntiles; ++tile) {
+            p.tile_base = tile;
+            kern<<<grid1, block, smem, stream>>>(p);
+            ISPLIB_LAUNCH_CHECK();
+        }
+        return ISPLIB_SUCCESS;
     }
     kern<<<grid, block, smem, stream>>>(p);
     ISPLIB_LAUNCH_CHECK();

@@ -8,6 +8,8 @@
 
 namespace isplib {
 
+typedef void (*SegKernel)(const SpmmParams);
+
 // ------------------------------------------------------------------------------------
 // small device helpers
 // ------------------------------------------------------------------------------------
@@ -255,7 +257,7 @@ __device__ __forceinline__ void finish_item(const SpmmParams& p, const int lane,
     }
     __threadfence();
     __syncwarp();
-    int* const ticket_ptr = p.row_ticket + (size_t)blockIdx.y * (size_t)p.ticket_stride + (pbase >> 1);
+    int* const ticket_ptr = p.row_ticket + (size_t)(blockIdx.y + p.tile_base) * (size_t)p.ticket_stride + (pbase >> 1);
     int ticket = 0;
     if (lane == 0) ticket = atomicAdd(ticket_ptr, 1);
     ticket = __shfl_sync(FULL, ticket, 0);
@@ -329,7 +331,7 @@ spmm_seg_kernel(const __grid_constant__ SpmmParams p) {
 
     const int g = lane / G;
     const int lg = lane % G;
-    const int k0 = blockIdx.y * p.tile_w;
+    const int k0 = (blockIdx.y + p.tile_base) * p.tile_w;
     // VEC=4 loads may read up to 3 padding floats past K (the launcher checked ldx >= roundup4(K))
     const int keff = (VEC > 1) ? ((p.k + VEC - 1) & ~(VEC - 1)) : p.k;
     const int kend = min(keff, k0 + p.tile_w);
@@ -519,7 +521,7 @@ spmm_bulk_kernel(const __grid_constant__ SpmmParams p) {
     const int4 desc = __ldg(p.item_desc + item);
     const int row = desc.x, eb = desc.y, ee = desc.z, slot_id = desc.w;
     const int g = lane / G, lg = lane % G;
-    const int k0 = blockIdx.y * p.tile_w;
+    const int k0 = (blockIdx.y + p.tile_base) * p.tile_w;
     const int keff = (p.k + 3) & ~3;
     const int kend = min(keff, k0 + p.tile_w);
     const unsigned row_bytes = (unsigned)(kend - k0) * 4u;
@@ -606,8 +608,104 @@ spmm_bulk_kernel(const __grid_constant__ SpmmParams p) {
     finish_item<OP, VEC, G, LPL>(p, lane, row, eb, ee, slot_id, koff, kok, acc, arg);
 }
 
+// ------------------------------------------------------------------------------------
+// lean 256-bit sum kernel (method 5): the 32-byte gather pays off only if four of them stay in
+// flight per lane at >= 32 warps/SM, i.e. within 64 registers.  This specialisation drops
+// everything the general kernel carries (arg tracking, partial tiles, index prefetch, staged
+// edge values) and keeps the step loop rolled so only U x 8 staging registers are live.
+// Full tiles only (tile = G x 8 floats, K % tile == 0); max/min carry 8 more registers (arg).
+// ------------------------------------------------------------------------------------
+template <int OP, int G>
+__global__ void __launch_bounds__(128, OP == OP_SUM ? 8 : 6)
+spmm_lean256_kernel(const __grid_constant__ SpmmParams p) {
+    constexpr int VEC = 8, U = 4;
+    constexpr int NG = 32 / G;
+    constexpr unsigned FULL = 0xffffffffu;
+    const int lane = threadIdx.x & 31;
+    const int item = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    if (item >= p.num_items) return;
+    const int4 desc = __ldg(p.item_desc + item);
+    const int eb = desc.y, ee = desc.z;
+    const int g = lane / G;
+    const int k0 = (blockIdx.y + p.tile_base) * p.tile_w + (lane % G) * VEC;
+    const char* const xlane = reinterpret_cast<const char*>(p.x + k0);
+    const unsigned ldxb = (unsigned)p.ldx * 4u;
+    const bool has_val = (p.val != nullptr);
+
+    float acc[1][VEC];
+    int arg[1][VEC];
+#pragma unroll
+    for (int v = 0; v < VEC; ++v) { acc[0][v] = init_value<OP>(); arg[0][v] = kNoArg; }
+
+    for (int e0 = eb; e0 < ee; e0 += 32) {
+        const int cnt = min(32, ee - e0);
+        unsigned c = 0;
+        float a = 0.f;
+        if (lane < cnt) {
+            c = (unsigned)__ldcs(p.col + e0 + lane);
+            a = has_val ? __ldcs(p.val + e0 + lane) : 1.f;
+        }
+        if (cnt == 32) {
+#pragma unroll 1
+            for (int t = 0; t < 32; t += NG * U) {
+                float xv[U][VEC];
+#pragma unroll
+                for (int u = 0; u < U; ++u) {
+                    const unsigned cc = __shfl_sync(FULL, c, t + u * NG + g);
+                    load_vec<VEC>(reinterpret_cast<const float*>(xlane + (unsigned long long)cc * ldxb), xv[u]);
+                }
+#pragma unroll
+                for (int u = 0; u < U; ++u) {
+                    const float aa = __shfl_sync(FULL, a, t + u * NG + g);
+#pragma unroll
+                    for (int v = 0; v < VEC; ++v) {
+                        if constexpr (OP == OP_SUM) {
+                            acc[0][v] = fmaf(aa, xv[u][v], acc[0][v]);
+                        } else {
+                            const float tt = __fmul_rn(aa, xv[u][v]);
+                            if (better<OP>(tt, acc[0][v])) { acc[0][v] = tt; arg[0][v] = e0 + t + u * NG + g; }
+                        }
+                    }
+                }
+            }
+        } else {
+            for (int t = 0; t < cnt; t += NG) {
+                const int idx = t + g;
+                const unsigned cc = __shfl_sync(FULL, c, idx & 31);
+                const float aa = __shfl_sync(FULL, a, idx & 31);
+                if (idx < cnt) {
+                    float xv[VEC];
+                    load_vec<VEC>(reinterpret_cast<const float*>(xlane + (unsigned long long)cc * ldxb), xv);
+#pragma unroll
+                    for (int v = 0; v < VEC; ++v) {
+                        if constexpr (OP == OP_SUM) {
+                            acc[0][v] = fmaf(aa, xv[v], acc[0][v]);
+                        } else {
+                            const float tt = __fmul_rn(aa, xv[v]);
+                            if (better<OP>(tt, acc[0][v])) { acc[0][v] = tt; arg[0][v] = e0 + idx; }
+                        }
+                    }
+                }
+            }
+        }
+    }
+    const int koff[1] = {k0};
+    const bool kok[1] = {true};
+    finish_item<OP, VEC, G, 1>(p, lane, desc.x, eb, ee, desc.w, koff, kok, acc, arg);
+}
+
+template <int OP>
+static inline SegKernel pick_lean256(int g) {
+    switch (g) {
+        case 4: return spmm_lean256_kernel<OP, 4>;
+        case 8: return spmm_lean256_kernel<OP, 8>;
+        case 16: return spmm_lean256_kernel<OP, 16>;
+        case 32: return spmm_lean256_kernel<OP, 32>;
+        default: return nullptr;
+    }
+}
+
 struct TileShape { int vec, g, lpl, tile_w, ntiles; };
-typedef void (*SegKernel)(const SpmmParams);
 
 template <int OP, int VEC, int G, int LPL>
 static inline SegKernel pick_u(int u, bool partial) {
