@@ -185,8 +185,13 @@ extern "C" int isplib_b200_spmm_autotune(int reduce, int64_t m, int64_t n, int64
         // default candidate set = the family that wins on every measured shape (U=4; 4 warps/CTA
         // for every K tile, 8 warps only untiled); the rest only with ISPLIB_B200_TUNE_ALL=1
         if (d->method == 0 && !tune_all && !(d->unroll == 4 && (d->warps == 4 || d->kt == 0))) continue;
-        if (d->method == 3 && !tune_all) continue;   // 256-bit gathers: measured slower here (register pressure)
-        if (d->method == 5 && (reduce == ISPLIB_REDUCE_MAX || reduce == ISPLIB_REDUCE_MIN) && !tune_all) continue;   // lean max/min: never ahead of seg/* (r1_kbench)
+        // 256-bit gathers in the general kernel: slower while x is L2-resident (register pressure);
+        // with x far beyond L2 two 32-byte gathers in flight win (Amazon-shape max: 37.9 vs 41.1 ms)
+        const bool hbm_regime = (double)n * (double)k * 4.0 > 512.0 * 1024 * 1024;
+        if (d->method == 3 && !tune_all && !(hbm_regime && d->warps == 4 && d->unroll == 2 && d->kt == 0)) continue;
+        // lean max/min: never ahead of seg/* while x is L2-resident (r1_kbench_lean256)
+        if (d->method == 5 && (reduce == ISPLIB_REDUCE_MAX || reduce == ISPLIB_REDUCE_MIN) && !tune_all &&
+            !(hbm_regime && d->kt == 0)) continue;
         rc = launch_spmm(reduce, p, nnz, v, stream);  // warm-up
         if (rc) break;
         cudaEventRecord(e0, stream);

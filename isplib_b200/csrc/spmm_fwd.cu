@@ -87,9 +87,9 @@ SegKernel seg_kernel_min(const TileShape&, int, bool);
 SegKernel bulk_kernel_sum(const TileShape&, int);
 SegKernel bulk_kernel_max(const TileShape&, int);
 SegKernel bulk_kernel_min(const TileShape&, int);
-SegKernel lean256_kernel_sum(int g);
-SegKernel lean256_kernel_max(int g);
-SegKernel lean256_kernel_min(int g);
+SegKernel lean256_kernel_sum(int g, bool ragged);
+SegKernel lean256_kernel_max(int g, bool ragged);
+SegKernel lean256_kernel_min(int g, bool ragged);
 
 static bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15u) == 0; }
 
@@ -139,11 +139,13 @@ bool spmm_variant_supported(int variant, int reduce, int64_t k, int64_t ldx, int
     if (!d || reduce < 0 || reduce > 3 || k <= 0) return false;
     (void)ldo; (void)out;
     const int vec = pick_vec(k, ldx, x);
-    if (d->method == 5) {   // lean 32-byte kernel: full tiles of 32..256 floats
+    if (d->method == 5) {   // lean 32-byte kernel: whole tiles of 32..256 floats
         if (!vec8_ok(k, ldx, x)) return false;
         const int64_t tw = d->kt > 0 ? d->kt : k;
         if (d->kt > 0 && d->kt >= k) return false;
-        return (tw == 32 || tw == 64 || tw == 128 || tw == 256) && k % tw == 0;
+        // an untiled launch may end inside a vector (K = 47 in rows padded to 48): the loads stay
+        // inside the padded row, finalize_store writes only the valid columns
+        return tw >= 32 && tw <= 256 && (d->kt == 0 || tw % 8 == 0) && k % tw == 0;
     }
     if (d->method == 3) {   // 32-byte gathers
         if (!vec8_ok(k, ldx, x)) return false;
@@ -172,7 +174,8 @@ static int find_variant(int method, int warps, int unroll, int kt, int seq = 0) 
 
 // Shape-only default (the op layer replaces it by the measured winner when autotuning is on).
 // Measured on B200 (profiles/r1_kbench_*.txt): 4 warps/CTA and 4 gathers in flight win
-// everywhere; sum/mean on 32-byte-aligned rows of 32..256 floats prefer the lean 256-bit kernel;
+// everywhere; sum/mean on 32-byte-aligned rows of 32..256 floats (any multiple of 8) prefer the
+// lean 256-bit kernel, max/min only when x is HBM-resident;
 // a K tile pays off only when it makes an [n, tile] slab of x L2-resident (126 MB L2) while x
 // itself is not (Reddit-shape K>=128 -> 64-wide); when nothing can be resident
 // (products/amazon shapes) 128-wide tiles are marginally ahead for K > 128.
@@ -182,10 +185,15 @@ int spmm_variant_default(int reduce, int64_t n, int64_t k, int64_t ldx, int64_t 
     const double MB = 1024.0 * 1024.0;
     const double x_bytes = (double)n * (double)k * 4.0;
     const bool slab64 = (double)n * 64.0 * 4.0 <= 64.0 * MB;
-    if (reduce == ISPLIB_REDUCE_SUM || reduce == ISPLIB_REDUCE_MEAN) {   // for max / min the lean kernel measured 3-20 % slower (80 registers)
+    const bool additive = (reduce == ISPLIB_REDUCE_SUM || reduce == ISPLIB_REDUCE_MEAN);
+    // max / min: the lean kernel (80 registers) is 3-20 % behind seg/* while x is L2-resident and
+    // ahead once x is far beyond L2 (Amazon-shape K=200: 36.0 vs 40.9 ms)
+    if (additive || x_bytes > 512.0 * MB) {
         int v = -1;
-        if (x_bytes > 96.0 * MB && k > 64 && slab64) v = find_variant(5, 4, 4, 64);
+        if (additive && x_bytes > 96.0 * MB && k > 64 && slab64) v = find_variant(5, 4, 4, 64, 1);   // one launch per 64-wide slab
         else v = find_variant(5, 4, 4, 0);
+        if (v >= 0 && spmm_variant_supported(v, reduce, k, ldx, ldo, x, out)) return v;
+        v = find_variant(5, 4, 4, 0);
         if (v >= 0 && spmm_variant_supported(v, reduce, k, ldx, ldo, x, out)) return v;
     }
     int kt = 0;
@@ -215,7 +223,9 @@ int launch_spmm(int reduce, const SpmmParams& base, int64_t nnz, int variant, cu
     if (d->method == 5) {
         if (!vec8_ok(p.k, p.ldx, p.x)) return ISPLIB_NO_OPT_IMPL;
         const int tw = d->kt > 0 ? d->kt : p.k;
-        t.vec = 8; t.g = tw / 8; t.lpl = 1; t.tile_w = tw; t.ntiles = p.k / tw;
+        int g = 4;
+        while (g * 8 < tw) g <<= 1;               // lanes per row: 4, 8, 16 or 32
+        t.vec = 8; t.g = g; t.lpl = 1; t.tile_w = tw; t.ntiles = p.k / tw;
         vec = 8;
     }
     const int keff = vec > 1 ? (p.k + vec - 1) / vec * vec : p.k;
@@ -229,7 +239,9 @@ int launch_spmm(int reduce, const SpmmParams& base, int64_t nnz, int variant, cu
     SegKernel kern = nullptr;
     size_t smem = 0;
     if (d->method == 5) {
-        kern = op == OP_SUM ? lean256_kernel_sum(t.g) : (op == OP_MAX ? lean256_kernel_max(t.g) : lean256_kernel_min(t.g));
+        const bool ragged = (t.g * 8 != t.tile_w);
+        kern = op == OP_SUM ? lean256_kernel_sum(t.g, ragged)
+                            : (op == OP_MAX ? lean256_kernel_max(t.g, ragged) : lean256_kernel_min(t.g, ragged));
     } else if (d->method == 1) {
         if (op == OP_SUM) kern = bulk_kernel_sum(t, d->unroll);
         else if (op == OP_MAX) kern = bulk_kernel_max(t, d->unroll);

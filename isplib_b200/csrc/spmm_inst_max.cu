@@ -4,5 +4,5 @@
 namespace isplib {
 SegKernel seg_kernel_max(const TileShape& t, int u, bool partial) { return pick_kernel<OP_MAX>(t, u, partial); }
 SegKernel bulk_kernel_max(const TileShape& t, int stages) { return pick_bulk_kernel<OP_MAX>(t, stages); }
-SegKernel lean256_kernel_max(int g) { return pick_lean256<OP_MAX>(g); }
+SegKernel lean256_kernel_max(int g, bool ragged) { return pick_lean256<OP_MAX>(g, ragged); }
 }  // namespace isplib

@@ -4,5 +4,5 @@
 namespace isplib {
 SegKernel seg_kernel_min(const TileShape& t, int u, bool partial) { return pick_kernel<OP_MIN>(t, u, partial); }
 SegKernel bulk_kernel_min(const TileShape& t, int stages) { return pick_bulk_kernel<OP_MIN>(t, stages); }
-SegKernel lean256_kernel_min(int g) { return pick_lean256<OP_MIN>(g); }
+SegKernel lean256_kernel_min(int g, bool ragged) { return pick_lean256<OP_MIN>(g, ragged); }
 }  // namespace isplib

@@ -613,9 +613,12 @@ spmm_bulk_kernel(const __grid_constant__ SpmmParams p) {
 // flight per lane at >= 32 warps/SM, i.e. within 64 registers.  This specialisation drops
 // everything the general kernel carries (arg tracking, partial tiles, index prefetch, staged
 // edge values) and keeps the step loop rolled so only U x 8 staging registers are live.
-// Full tiles only (tile = G x 8 floats, K % tile == 0); max/min carry 8 more registers (arg).
+// Whole tiles only (K % tile == 0, tile % 8 == 0); a tile narrower than G x 8 floats (RAGGED,
+// e.g. K = 200 -> 25 of 32 lanes) parks the surplus lanes on the tile's first vector (same
+// sectors as lane 0, so no extra traffic) and keeps them out of the stores.  max/min carry 8
+// more registers (arg).
 // ------------------------------------------------------------------------------------
-template <int OP, int G>
+template <int OP, int G, bool RAGGED>
 __global__ void __launch_bounds__(128, OP == OP_SUM ? 8 : 6)
 spmm_lean256_kernel(const __grid_constant__ SpmmParams p) {
     constexpr int VEC = 8, U = 4;
@@ -627,7 +630,8 @@ spmm_lean256_kernel(const __grid_constant__ SpmmParams p) {
     const int4 desc = __ldg(p.item_desc + item);
     const int eb = desc.y, ee = desc.z;
     const int g = lane / G;
-    const int k0 = (blockIdx.y + p.tile_base) * p.tile_w + (lane % G) * VEC;
+    const bool lane_ok = !RAGGED || (lane % G) * VEC < p.tile_w;
+    const int k0 = (blockIdx.y + p.tile_base) * p.tile_w + (lane_ok ? (lane % G) * VEC : 0);
     const char* const xlane = reinterpret_cast<const char*>(p.x + k0);
     const unsigned ldxb = (unsigned)p.ldx * 4u;
     const bool has_val = (p.val != nullptr);
@@ -690,17 +694,17 @@ spmm_lean256_kernel(const __grid_constant__ SpmmParams p) {
         }
     }
     const int koff[1] = {k0};
-    const bool kok[1] = {true};
+    const bool kok[1] = {lane_ok};
     finish_item<OP, VEC, G, 1>(p, lane, desc.x, eb, ee, desc.w, koff, kok, acc, arg);
 }
 
 template <int OP>
-static inline SegKernel pick_lean256(int g) {
+static inline SegKernel pick_lean256(int g, bool ragged) {
     switch (g) {
-        case 4: return spmm_lean256_kernel<OP, 4>;
-        case 8: return spmm_lean256_kernel<OP, 8>;
-        case 16: return spmm_lean256_kernel<OP, 16>;
-        case 32: return spmm_lean256_kernel<OP, 32>;
+        case 4: return ragged ? spmm_lean256_kernel<OP, 4, true> : spmm_lean256_kernel<OP, 4, false>;
+        case 8: return ragged ? spmm_lean256_kernel<OP, 8, true> : spmm_lean256_kernel<OP, 8, false>;
+        case 16: return ragged ? spmm_lean256_kernel<OP, 16, true> : spmm_lean256_kernel<OP, 16, false>;
+        case 32: return ragged ? spmm_lean256_kernel<OP, 32, true> : spmm_lean256_kernel<OP, 32, false>;
         default: return nullptr;
     }
 }

@@ -242,10 +242,10 @@ std::tuple<Tensor, c10::optional<Tensor>> spmm_fw(CsrView& g, const c10::optiona
     const int64_t M = g.m, N = mat.size(0), K = mat.size(1);
     int64_t ldx = K;
     if (K % 4 != 0 && K > 4 && env_int("ISPLIB_B200_PAD_K", 1)) {
-        // feature widths like 47 or 602: give every row 16-byte alignment and its own padding
-        // so the kernel can gather with 16-byte loads (the reference pads features to multiples
+        // feature widths like 47 or 602: give every row 32-byte alignment and its own padding
+        // so the kernel can gather with 16- and 32-byte loads (the reference pads features to multiples
         // of 16 for its SIMD kernels, tests/cpu/dataset_loader.py:145-160); out stays [M, K]
-        const int64_t Kp = (K + 3) / 4 * 4;
+        const int64_t Kp = (K + 7) / 8 * 8;
         Tensor padded = torch::zeros({N, Kp}, mat.options());
         padded.narrow(1, 0, K).copy_(mat);
         mat = padded;

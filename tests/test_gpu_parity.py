@@ -118,7 +118,7 @@ def test_every_variant(capi, oracle, reduce):
     assert ran >= 4
 
 
-@pytest.mark.parametrize("K", [32, 64, 256])
+@pytest.mark.parametrize("K", [32, 40, 64, 104, 200, 256])   # 40/104/200: ragged tiles of the lean 256-bit kernel
 def test_every_variant_other_widths(capi, oracle, K):
     rng = np.random.default_rng(6 + K)
     M, N = 200, 300
@@ -442,8 +442,9 @@ def test_sddmm_matches_oracle(capi, oracle, K, mean):
         assert_sum_close(got2, ref, cond)
 
 
-@pytest.mark.parametrize("K", [47, 64, 100, 128])
-def test_no_out_of_bounds_writes_canaries(capi, oracle, K):
+@pytest.mark.parametrize("pad", [4, 8])   # 8: rows stay 32-byte aligned, so the 256-bit kernels run too
+@pytest.mark.parametrize("K", [40, 47, 64, 100, 128, 200])
+def test_no_out_of_bounds_writes_canaries(capi, oracle, K, pad):
     """compute-sanitizer is not available on this pool, so out-of-bounds WRITES are caught with
     canaries: out / arg_out live inside larger buffers whose guard rows and guard columns must
     be untouched after every variant has run (split rows, partial tiles, scalar-store tail)."""
@@ -452,8 +453,8 @@ def test_no_out_of_bounds_writes_canaries(capi, oracle, K):
     rowptr, col, val = random_csr(rng, M, N, 40, empty_prob=0.1, long_rows=[(0, 1200), (96, 700)])
     mat = rng.standard_normal((N, K)).astype(np.float32)
     rp, co, va, _ = to_dev(rowptr, col, val, mat)
-    Kp = (K + 3) // 4 * 4
-    xb = torch.full((N + 2, Kp + 4), 3.0, device=DEV)
+    Kp = (K + pad - 1) // pad * pad
+    xb = torch.full((N + 2, Kp + pad), 3.0, device=DEV)
     xb[1:N + 1, :K] = torch.from_numpy(mat).to(DEV)
     x = xb[1:N + 1, :K]
     plan = capi.Plan(rp, co.numel(), 256)
@@ -462,10 +463,10 @@ def test_no_out_of_bounds_writes_canaries(capi, oracle, K):
         code = capi.REDUCE_CODE[reduce]
         ref, ref_arg = oracle.spmm_c(rowptr, col, val, mat, code)
         for v in range(L.isplib_b200_variant_count()):
-            if not L.isplib_b200_variant_supported(v, code, K, x.stride(0), Kp + 4, x.data_ptr(), x.data_ptr()):
+            if not L.isplib_b200_variant_supported(v, code, K, x.stride(0), Kp + pad, x.data_ptr(), x.data_ptr()):
                 continue
-            ob = torch.full((M + 2, Kp + 4), 7.0, device=DEV)
-            ab = torch.full((M + 2, Kp + 4), -5, dtype=torch.int64, device=DEV)
+            ob = torch.full((M + 2, Kp + pad), 7.0, device=DEV)
+            ab = torch.full((M + 2, Kp + pad), -5, dtype=torch.int64, device=DEV)
             out, arg = capi.spmm_csr(reduce, rp, co, va, x, plan, v, out=ob[1:M + 1, :K],
                                      arg_out=ab[1:M + 1, :K] if reduce == "max" else None)
             torch.cuda.synchronize()
