@@ -54,7 +54,12 @@ def parse_args():
 # dram__bytes_read.sum + dram__bytes_write.sum per launch from the committed `ncu --set full`
 # capture of this very command (profiles/r1_full_spmm_seg_sum_k128_w4u4kt64.txt); null for
 # configurations that were not captured.
-NCU_TRAFFIC_BYTES = {("reddit", 128, "sum", "seg/w4/u4/kt64"): 5_251_204_000 + 263_436_800}
+NCU_TRAFFIC_BYTES = {
+    # per LAUNCH, like roofline.algorithmic_bytes_per_launch (dram__bytes_read.sum + dram__bytes_write.sum)
+    ("reddit", 128, "sum", "seg/w4/u4/kt64"): 5_251_204_000 + 263_436_800,        # profiles/r1_full_spmm_seg_sum_k128_w4u4kt64.txt
+    ("reddit", 128, "sum", "lean256/w4/kt64/seq"): 2_571_400_000 + 107_322_880,   # profiles/r1_full_lean256_sum_k128_kt64seq.txt (one of the two 64-wide launches)
+    ("reddit", 128, "sum", "lean256/w4/kt64"): 5_122_809_000 + 217_247_488,       # profiles/r1_full_lean256_sum_k128_kt64.txt
+}
 
 
 def workload_name(shape, reduce, k):
