@@ -495,7 +495,7 @@ def run_ours(args):
     roofline = {"bound": "hbm", "achieved": round(value / world, 2) if world > 1 else round(value, 2), "peak": peak,
                 "unit": "GB/s", "frac": round((value / world) / peak, 4),
                 "traffic": NCU_TRAFFIC_BYTES.get((args.shape, K, reduce, variant_name)) if world == 1 else None,
-                "kernel": ("isplib::spmm_lean256_kernel" if variant_name.startswith("lean256")
+                "kernel": ("isplib::spmm_lean_kernel" if variant_name.startswith("lean")
                            else "isplib::spmm_bulk_kernel" if variant_name.startswith("bulk")
                            else "isplib::spmm_seg_kernel"),
                 "peak_source": peak_src,

@@ -59,6 +59,9 @@ static const VariantDesc kVariants[] = {
     // sequential K tiles: one launch per tile, so only ONE [N, tile] slab of X is live in L2 at a
     // time (with grid.y tiles the tail of tile t overlaps the head of tile t+1)
     {"seg/w4/u4/kt64/seq", 0, 4, 4, 64, 1},
+    {"lean128/w4/kfull", 6, 4, 4, 0, 0},
+    {"lean128/w4/kt64", 6, 4, 4, 64, 0},
+    {"lean128/w4/kt64/seq", 6, 4, 4, 64, 1},
     {"lean256/w4/kt64/seq", 5, 4, 4, 64, 1},
     {"lean256/w4/kt128/seq", 5, 4, 4, 128, 1},
     // method 1: TMA bulk-copy gather through a per-warp shared-memory ring; `unroll` = stages
@@ -90,6 +93,9 @@ SegKernel bulk_kernel_min(const TileShape&, int);
 SegKernel lean256_kernel_sum(int g, bool ragged);
 SegKernel lean256_kernel_max(int g, bool ragged);
 SegKernel lean256_kernel_min(int g, bool ragged);
+SegKernel lean128_kernel_sum(int g, bool ragged);
+SegKernel lean128_kernel_max(int g, bool ragged);
+SegKernel lean128_kernel_min(int g, bool ragged);
 
 static bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15u) == 0; }
 
@@ -146,6 +152,12 @@ bool spmm_variant_supported(int variant, int reduce, int64_t k, int64_t ldx, int
         // an untiled launch may end inside a vector (K = 47 in rows padded to 48): the loads stay
         // inside the padded row, finalize_store writes only the valid columns
         return tw >= 32 && tw <= 256 && (d->kt == 0 || tw % 8 == 0) && k % tw == 0;
+    }
+    if (d->method == 6) {   // lean 16-byte kernel: whole tiles of 16..128 floats
+        if (vec != 4) return false;
+        const int64_t tw = d->kt > 0 ? d->kt : k;
+        if (d->kt > 0 && d->kt >= k) return false;
+        return tw >= 16 && tw <= 128 && tw % 4 == 0 && k % tw == 0;
     }
     if (d->method == 3) {   // 32-byte gathers
         if (!vec8_ok(k, ldx, x)) return false;
@@ -228,6 +240,13 @@ int launch_spmm(int reduce, const SpmmParams& base, int64_t nnz, int variant, cu
         t.vec = 8; t.g = g; t.lpl = 1; t.tile_w = tw; t.ntiles = p.k / tw;
         vec = 8;
     }
+    if (d->method == 6) {
+        if (vec != 4) return ISPLIB_NO_OPT_IMPL;
+        const int tw = d->kt > 0 ? d->kt : p.k;
+        int g = 4;
+        while (g * 4 < tw) g <<= 1;
+        t.vec = 4; t.g = g; t.lpl = 1; t.tile_w = tw; t.ntiles = p.k / tw;
+    }
     const int keff = vec > 1 ? (p.k + vec - 1) / vec * vec : p.k;
     p.kp = (p.k + 7) & ~7;
     p.vec_store = (p.k % 4 == 0 && p.ldo % 4 == 0 && aligned16(p.out) && (!p.arg_out || aligned16(p.arg_out))) ? 1 : 0;
@@ -242,6 +261,10 @@ int launch_spmm(int reduce, const SpmmParams& base, int64_t nnz, int variant, cu
         const bool ragged = (t.g * 8 != t.tile_w);
         kern = op == OP_SUM ? lean256_kernel_sum(t.g, ragged)
                             : (op == OP_MAX ? lean256_kernel_max(t.g, ragged) : lean256_kernel_min(t.g, ragged));
+    } else if (d->method == 6) {
+        const bool ragged = (t.g * 4 != t.tile_w);
+        kern = op == OP_SUM ? lean128_kernel_sum(t.g, ragged)
+                            : (op == OP_MAX ? lean128_kernel_max(t.g, ragged) : lean128_kernel_min(t.g, ragged));
     } else if (d->method == 1) {
         if (op == OP_SUM) kern = bulk_kernel_sum(t, d->unroll);
         else if (op == OP_MAX) kern = bulk_kernel_max(t, d->unroll);

@@ -609,19 +609,20 @@ spmm_bulk_kernel(const __grid_constant__ SpmmParams p) {
 }
 
 // ------------------------------------------------------------------------------------
-// lean 256-bit sum kernel (method 5): the 32-byte gather pays off only if four of them stay in
-// flight per lane at >= 32 warps/SM, i.e. within 64 registers.  This specialisation drops
-// everything the general kernel carries (arg tracking, partial tiles, index prefetch, staged
-// edge values) and keeps the step loop rolled so only U x 8 staging registers are live.
-// Whole tiles only (K % tile == 0, tile % 8 == 0); a tile narrower than G x 8 floats (RAGGED,
-// e.g. K = 200 -> 25 of 32 lanes) parks the surplus lanes on the tile's first vector (same
-// sectors as lane 0, so no extra traffic) and keeps them out of the stores.  max/min carry 8
-// more registers (arg).
+// lean kernel (method 5: VEC = 8, 32-byte gathers `lean256/*`; method 6: VEC = 4 `lean128/*`):
+// the 32-byte gather pays off only if four of them stay in flight per lane at >= 32 warps/SM,
+// i.e. within 64 registers.  This body drops what the general kernel carries (partial-tile
+// bookkeeping, index prefetch, staged edge values) and keeps the step loop rolled so only
+// U x VEC staging registers are live.
+// Whole tiles only (K % tile == 0); a tile narrower than G x VEC floats (RAGGED, e.g. K = 200
+// -> 25 of 32 lanes) parks the surplus lanes on the tile's first vector (same sectors as lane
+// 0, so no extra traffic) and keeps them out of the stores.  max/min carry VEC more registers
+// (arg): 80 with VEC = 8 (24 warps/SM), 56 with VEC = 4 (36 warps/SM).
 // ------------------------------------------------------------------------------------
-template <int OP, int G, bool RAGGED>
-__global__ void __launch_bounds__(128, OP == OP_SUM ? 8 : 6)
-spmm_lean256_kernel(const __grid_constant__ SpmmParams p) {
-    constexpr int VEC = 8, U = 4;
+template <int OP, int VEC, int G, bool RAGGED>
+__global__ void __launch_bounds__(128, VEC == 8 ? (OP == OP_SUM ? 8 : 6) : (OP == OP_SUM ? 10 : 9))
+spmm_lean_kernel(const __grid_constant__ SpmmParams p) {
+    constexpr int U = 4;
     constexpr int NG = 32 / G;
     constexpr unsigned FULL = 0xffffffffu;
     const int lane = threadIdx.x & 31;
@@ -698,13 +699,13 @@ spmm_lean256_kernel(const __grid_constant__ SpmmParams p) {
     finish_item<OP, VEC, G, 1>(p, lane, desc.x, eb, ee, desc.w, koff, kok, acc, arg);
 }
 
-template <int OP>
-static inline SegKernel pick_lean256(int g, bool ragged) {
+template <int OP, int VEC>
+static inline SegKernel pick_lean(int g, bool ragged) {
     switch (g) {
-        case 4: return ragged ? spmm_lean256_kernel<OP, 4, true> : spmm_lean256_kernel<OP, 4, false>;
-        case 8: return ragged ? spmm_lean256_kernel<OP, 8, true> : spmm_lean256_kernel<OP, 8, false>;
-        case 16: return ragged ? spmm_lean256_kernel<OP, 16, true> : spmm_lean256_kernel<OP, 16, false>;
-        case 32: return ragged ? spmm_lean256_kernel<OP, 32, true> : spmm_lean256_kernel<OP, 32, false>;
+        case 4: return ragged ? spmm_lean_kernel<OP, VEC, 4, true> : spmm_lean_kernel<OP, VEC, 4, false>;
+        case 8: return ragged ? spmm_lean_kernel<OP, VEC, 8, true> : spmm_lean_kernel<OP, VEC, 8, false>;
+        case 16: return ragged ? spmm_lean_kernel<OP, VEC, 16, true> : spmm_lean_kernel<OP, VEC, 16, false>;
+        case 32: return ragged ? spmm_lean_kernel<OP, VEC, 32, true> : spmm_lean_kernel<OP, VEC, 32, false>;
         default: return nullptr;
     }
 }
