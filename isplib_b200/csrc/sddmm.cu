@@ -183,6 +183,98 @@ sddmm_seg_kernel(const __grid_constant__ SddmmParams p) {
     }
 }
 
+
+// ------------------------------------------------------------------------------------
+// lean 256-bit variant (same recipe as spmm_lean_kernel): 32-byte gathers, U = 4 in flight, the
+// step loop rolled so that only 4 x 8 staging registers are live.  G lanes cover one tile of up
+// to G x 8 floats of an x row, 32/G entries per step.  Every 4 steps the 4 partial dot products
+// of a lane are folded over the lane group right away (3 butterfly shuffles + log2(G/4) adds),
+// so nothing but one result register is carried across iterations; lane lg ends up holding the
+// dot product of step lg and the chunk is stored with one coalesced store.
+// RAGGED: the tile is narrower than G x 8 floats or ends inside a vector (K = 200, 47 ...):
+// surplus lanes and the columns past k are masked to zero (x's padding may hold anything).
+// ------------------------------------------------------------------------------------
+__device__ __forceinline__ void ld_vec8(const float* __restrict__ p, float (&v)[8]) {
+    asm volatile("ld.global.nc.v8.b32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+                 : "=f"(v[0]), "=f"(v[1]), "=f"(v[2]), "=f"(v[3]), "=f"(v[4]), "=f"(v[5]), "=f"(v[6]), "=f"(v[7])
+                 : "l"(p));
+}
+
+template <int G, bool RAGGED>
+__global__ void __launch_bounds__(128, 8)
+sddmm_lean256_kernel(const __grid_constant__ SddmmParams p) {
+    constexpr int VEC = 8, U = 4;
+    constexpr int NG = 32 / G;
+    constexpr unsigned FULL = 0xffffffffu;
+    const int lane = threadIdx.x & 31;
+    const int item = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    if (item >= p.num_items) return;
+    const int4 desc = __ldg(p.item_desc + item);
+    const int row = desc.x, eb = desc.y, ee = desc.z;
+    if (eb >= ee) return;
+    const int g = lane / G, lg = lane % G;
+    float inv = 1.f;
+    if (p.mean_scale) inv = __fdiv_rn(1.f, (float)max(__ldg(p.rowptr + row + 1) - __ldg(p.rowptr + row), 1));
+    const unsigned ldxb = (unsigned)p.ldx * 4u;
+    const int nvalid = RAGGED ? max(0, min(VEC, p.k - lg * VEC)) : VEC;   // columns of this lane's vector inside [0, k)
+    const int koff = (nvalid > 0) ? lg * VEC : 0;                          // surplus lanes park on the first vector
+    const char* const xlane = reinterpret_cast<const char*>(p.x + koff);
+
+    float av[VEC];
+    {
+        const float* arow = p.a + (size_t)row * (size_t)p.lda + koff;
+#pragma unroll
+        for (int q = 0; q < VEC; ++q) av[q] = (q < nvalid) ? __ldg(arow + q) : 0.f;
+    }
+
+    for (int e0 = eb; e0 < ee; e0 += 32) {
+        const int cnt = min(32, ee - e0);
+        // lanes past the segment end gather row 0 (valid memory, nnz > 0 implies n > 0); their
+        // results are never stored
+        const unsigned c = (lane < cnt) ? (unsigned)__ldcs(p.col + e0 + lane) : 0u;
+        float res = 0.f;
+#pragma unroll 1
+        for (int t = 0; t < G; t += U) {
+            if (t * NG >= cnt) break;                      // warp-uniform
+            float xv[U][VEC];
+#pragma unroll
+            for (int u = 0; u < U; ++u) {
+                const unsigned cc = __shfl_sync(FULL, c, ((t + u) * NG + g) & 31);
+                ld_vec8(reinterpret_cast<const float*>(xlane + (unsigned long long)cc * ldxb), xv[u]);
+            }
+            float part[U];
+#pragma unroll
+            for (int u = 0; u < U; ++u) {
+                part[u] = 0.f;
+#pragma unroll
+                for (int q = 0; q < VEC; ++q) {
+                    if (RAGGED && q >= nvalid) xv[u][q] = 0.f;
+                    part[u] = fmaf(av[q], xv[u][q], part[u]);
+                }
+            }
+            // 4 values -> 1 over lane bits 1 and 0 of the group, then plain adds over the rest
+            {
+                const bool hi2 = (lg & 2) != 0;
+                const float k0 = hi2 ? part[2] : part[0], s0 = hi2 ? part[0] : part[2];
+                const float k1 = hi2 ? part[3] : part[1], s1 = hi2 ? part[1] : part[3];
+                const float a0 = k0 + __shfl_xor_sync(FULL, s0, 2);   // step (lg&2) + 0
+                const float a1 = k1 + __shfl_xor_sync(FULL, s1, 2);   // step (lg&2) + 1
+                const bool hi1 = (lg & 1) != 0;
+                const float kk = hi1 ? a1 : a0, ss = hi1 ? a0 : a1;
+                float tot = kk + __shfl_xor_sync(FULL, ss, 1);        // step lg & 3
+#pragma unroll
+                for (int o = 4; o < G; o <<= 1) tot += __shfl_xor_sync(FULL, tot, o);
+                if ((lg >> 2) == (t >> 2)) res = tot;                 // lane lg keeps step lg
+            }
+        }
+        const int idx = lg * NG + g;
+        if (idx < cnt) {
+            const float r = res * inv;
+            p.out[e0 + idx] = p.accum ? p.out[e0 + idx] + r : r;
+        }
+    }
+}
+
 }  // namespace isplib
 
 using namespace isplib;
@@ -218,6 +310,11 @@ extern "C" int isplib_b200_sddmm_csr(int64_t m, int64_t n, int64_t k, int64_t nn
     if (vec4 && k > 64 && k % 4 == 0 && (double)n * (double)k * 4.0 > 96.0 * 1024 * 1024 &&
         (double)n * 64.0 * 4.0 <= 64.0 * 1024 * 1024)
         kt = 64;
+    // 32-byte gathers need 32-byte aligned x rows that hold whole vectors (the op layer pads odd
+    // K to 8); tiles of at most 256 floats per launch
+    const bool lean = (ldx % 8 == 0) && (ldx >= ((k + 7) & ~(int64_t)7)) && ((reinterpret_cast<uintptr_t>(x) & 31u) == 0) &&
+                      k >= 32 && !getenv("ISPLIB_B200_SDDMM_SEG");
+    if (lean && kt > 256) kt = 256;
     const int warps = 4;
     const dim3 grid((unsigned)((p.num_items + warps - 1) / warps)), block(warps * 32);
     for (int64_t k0 = 0; k0 < k; k0 += kt) {
@@ -226,7 +323,13 @@ extern "C" int isplib_b200_sddmm_csr(int64_t m, int64_t n, int64_t k, int64_t nn
         p.x = x + k0;
         p.k = (int)kw;
         p.accum = k0 > 0 ? 1 : 0;
-        if (vec4) {
+        if (lean) {
+            const bool ragged = (kw != 32 && kw != 64 && kw != 128 && kw != 256);
+            if (kw <= 32) { if (ragged) sddmm_lean256_kernel<4, true><<<grid, block, 0, stream>>>(p); else sddmm_lean256_kernel<4, false><<<grid, block, 0, stream>>>(p); }
+            else if (kw <= 64) { if (ragged) sddmm_lean256_kernel<8, true><<<grid, block, 0, stream>>>(p); else sddmm_lean256_kernel<8, false><<<grid, block, 0, stream>>>(p); }
+            else if (kw <= 128) { if (ragged) sddmm_lean256_kernel<16, true><<<grid, block, 0, stream>>>(p); else sddmm_lean256_kernel<16, false><<<grid, block, 0, stream>>>(p); }
+            else { if (ragged) sddmm_lean256_kernel<32, true><<<grid, block, 0, stream>>>(p); else sddmm_lean256_kernel<32, false><<<grid, block, 0, stream>>>(p); }
+        } else if (vec4) {
             const int64_t tv = ((kw + 3) & ~(int64_t)3) / 4;
             if (tv <= 8) sddmm_seg_kernel<4, 8, 1><<<grid, block, 0, stream>>>(p);
             else if (tv <= 16) sddmm_seg_kernel<4, 16, 1><<<grid, block, 0, stream>>>(p);

@@ -413,7 +413,7 @@ def test_padded_rows_vector_gather_odd_k(capi, oracle, K, reduce):
 
 
 # ----------------------------------------------------------------- SDDMM (grad_value of sum/mean)
-@pytest.mark.parametrize("K", [1, 4, 7, 32, 47, 64, 100, 128, 256, 300, 1030])
+@pytest.mark.parametrize("K", [1, 4, 7, 32, 40, 47, 64, 100, 128, 200, 256, 300, 1030])
 @pytest.mark.parametrize("mean", [False, True])
 def test_sddmm_matches_oracle(capi, oracle, K, mean):
     rng = np.random.default_rng(700 + K)
@@ -431,15 +431,17 @@ def test_sddmm_matches_oracle(capi, oracle, K, mean):
     if mean:
         cond = cond / np.maximum(np.diff(rowptr), 1)[row]
     assert_sum_close(got, ref, cond)
-    # padded rows (what the op layer hands over for odd K): NaN padding must not leak into the dot
-    if K % 4:
-        Kp = (K + 3) // 4 * 4
-        xp = torch.full((N, Kp), float("nan"), device=DEV)
-        xp[:, :K] = xd
-        ap = torch.full((M, Kp), float("nan"), device=DEV)
-        ap[:, :K] = ad
-        got2 = capi.sddmm_csr(rp, co, ap[:, :K], xp[:, :K], plan, mean).cpu().numpy()
-        assert_sum_close(got2, ref, cond)
+    # padded rows (what the op layer hands over for odd K): NaN padding must not leak into the dot;
+    # rows padded to 8 floats are 32-byte aligned, which is what selects the 256-bit kernel
+    for pad in (4, 8):
+        if K % pad:
+            Kp = (K + pad - 1) // pad * pad
+            xp = torch.full((N, Kp), float("nan"), device=DEV)
+            xp[:, :K] = xd
+            ap = torch.full((M, Kp), float("nan"), device=DEV)
+            ap[:, :K] = ad
+            got2 = capi.sddmm_csr(rp, co, ap[:, :K], xp[:, :K], plan, mean).cpu().numpy()
+            assert_sum_close(got2, ref, cond)
 
 
 @pytest.mark.parametrize("pad", [4, 8])   # 8: rows stay 32-byte aligned, so the 256-bit kernels run too
