@@ -189,8 +189,9 @@ extern "C" int isplib_b200_spmm_autotune(int reduce, int64_t m, int64_t n, int64
         // with x far beyond L2 two 32-byte gathers in flight win (Amazon-shape max: 37.9 vs 41.1 ms)
         const bool hbm_regime = (double)n * (double)k * 4.0 > 512.0 * 1024 * 1024;
         if (d->method == 3 && !tune_all && !(hbm_regime && d->warps == 4 && d->unroll == 2 && d->kt == 0)) continue;
-        // lean 16-byte body: on par with lean256 for sum; for max/min up to +9 % over seg/* (K=64), untiled only
-        if (d->method == 6 && !tune_all && !((reduce == ISPLIB_REDUCE_MAX || reduce == ISPLIB_REDUCE_MIN) && d->kt == 0)) continue;
+        // lean 16-byte body, untiled only: on par with lean256 for sum (and the one that runs on rows that
+        // are only 16-byte aligned, K = 100: +8 %); for max/min up to +9 % over seg/* (K=64)
+        if (d->method == 6 && !tune_all && d->kt != 0) continue;
         // lean max/min: never ahead of seg/* while x is L2-resident (r1_kbench_lean256)
         if (d->method == 5 && (reduce == ISPLIB_REDUCE_MAX || reduce == ISPLIB_REDUCE_MIN) && !tune_all &&
             !(hbm_regime && d->kt == 0)) continue;
