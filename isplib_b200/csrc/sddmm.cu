@@ -227,11 +227,13 @@ sddmm_lean256_kernel(const __grid_constant__ SddmmParams p) {
         for (int q = 0; q < VEC; ++q) av[q] = (q < nvalid) ? __ldg(arow + q) : 0.f;
     }
 
+    // lanes past the segment end gather row 0 (valid memory, nnz > 0 implies n > 0); their
+    // results are never stored.  The next chunk's indices are fetched one chunk ahead.
+    unsigned c_next = (eb + lane < ee) ? (unsigned)__ldcs(p.col + eb + lane) : 0u;
     for (int e0 = eb; e0 < ee; e0 += 32) {
         const int cnt = min(32, ee - e0);
-        // lanes past the segment end gather row 0 (valid memory, nnz > 0 implies n > 0); their
-        // results are never stored
-        const unsigned c = (lane < cnt) ? (unsigned)__ldcs(p.col + e0 + lane) : 0u;
+        const unsigned c = c_next;
+        c_next = (e0 + 32 + lane < ee) ? (unsigned)__ldcs(p.col + e0 + 32 + lane) : 0u;
         float res = 0.f;
 #pragma unroll 1
         for (int t = 0; t < G; t += U) {
