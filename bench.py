@@ -311,7 +311,8 @@ def run_ours(args):
         tune = {capi.variant_names()[v]: round(t, 3) for v, t in enumerate(times) if t >= 0}
     else:
         op = RowPartitionedSpMM(g.rowptr, g.col, g.value, N, device=dev)
-        slices = [op.pad_x(x[rank * op.Rc: min((rank + 1) * op.Rc, N)]) for x in xs]
+        c0, c1 = op.col_range()
+        slices = [op.pad_x(x[c0:c1]) for x in xs]
         if args.variant is not None:
             op.variant = args.variant
 

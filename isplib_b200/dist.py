@@ -3,9 +3,13 @@ SURVEY.md section 8e).
 
 One process per GPU (``torchrun``), ``torch.distributed`` over NCCL/NVLink.
 
-* A (M x N) is 1-D partitioned by rows: rank p owns rows ``[p*R, (p+1)*R)`` with
-  ``R = ceil(M / P)`` (rows of X / out are owned the same way, zero-padded to R so the
-  all-gather is regular).
+* A (M x N) is 1-D partitioned by rows: rank p owns the contiguous rows
+  ``[row_bounds[p], row_bounds[p+1])``.  ``balance="nnz"`` (default) cuts the ranges so that
+  every rank holds about nnz/P stored entries (power-law graphs whose ids are sorted by
+  locality or degree are badly skewed under an even row split); ``balance="rows"`` is the even
+  split ``R = ceil(M / P)``.  Rows of X / out are owned the same way (square A: the same
+  bounds; otherwise the columns are split evenly) and zero-padded to the widest range
+  (``R`` / ``Rc``) so the all-gather is regular.
 * Each rank's row block is split by COLUMN OWNER into a *local* CSR block (columns the
   rank already holds) and a *remote* CSR block (everything else).
 * forward:   all-gather X slices on a side stream  ||  local-block SpMM
@@ -54,18 +58,58 @@ def rows_per_rank(m: int, world: int) -> int:
     return (m + world - 1) // world
 
 
+def even_bounds(n: int, world: int):
+    """[0, R, 2R, ..., n] with R = ceil(n / world) (clipped): the even split."""
+    R = rows_per_rank(n, world)
+    return [min(p * R, n) for p in range(world + 1)]
+
+
+def nnz_balanced_bounds(rowptr: torch.Tensor, world: int):
+    """Contiguous row ranges with about nnz/world stored entries each:
+    bounds[p] = the row whose prefix count is closest to p * nnz / world."""
+    m = rowptr.numel() - 1
+    nnz = int(rowptr[-1])
+    if world == 1 or m == 0 or nnz == 0:
+        return even_bounds(m, world)
+    rp = rowptr.to(torch.int64).cpu()
+    bounds = [0]
+    for p in range(1, world):
+        target = (p * nnz) // world
+        hi = int(torch.searchsorted(rp, torch.tensor(target, dtype=torch.int64)))   # first row with prefix >= target
+        hi = min(max(hi, 0), m)
+        lo = max(hi - 1, 0)
+        b = hi if abs(int(rp[hi]) - target) <= abs(int(rp[lo]) - target) else lo
+        bounds.append(min(max(b, bounds[-1]), m))
+    bounds.append(m)
+    return bounds
+
+
+def bounds_width(bounds) -> int:
+    return max(1, max(bounds[p + 1] - bounds[p] for p in range(len(bounds) - 1)))
+
+
+def slice_position(idx: torch.Tensor, bounds, width: int) -> torch.Tensor:
+    """Global index -> position in the all-gathered, width-padded layout: owner * width + offset."""
+    b = torch.as_tensor(bounds, dtype=torch.int64, device=idx.device)
+    owner = torch.bucketize(idx, b[1:-1], right=True)
+    return owner * width + (idx - b[owner])
+
+
 def split_row_block(rowptr: torch.Tensor, col: torch.Tensor, val: Optional[torch.Tensor],
-                    rank: int, world: int, n_cols: int) -> Tuple[CsrBlock, CsrBlock, torch.Tensor, int]:
+                    rank: int, world: int, n_cols: int, row_bounds=None, col_bounds=None
+                    ) -> Tuple[CsrBlock, CsrBlock, torch.Tensor, int]:
     """From the GLOBAL CSR (int64, any device) build this rank's (local, remote) blocks.
 
     Returns (local, remote, row_degree[R] fp32 (clamped >= 1), R).  Local block columns are
     rebased to the rank's own X slice; remote block columns index the gathered [P*Rc, K]
-    matrix (Rc = rows_per_rank(n_cols, world)), where own-slice columns never appear.
+    matrix (Rc = widest column range), where own-slice columns never appear.
     """
     m = rowptr.numel() - 1
-    R = rows_per_rank(m, world)
-    Rc = rows_per_rank(n_cols, world)
-    r0, r1 = min(rank * R, m), min((rank + 1) * R, m)
+    row_bounds = even_bounds(m, world) if row_bounds is None else row_bounds
+    col_bounds = even_bounds(n_cols, world) if col_bounds is None else col_bounds
+    R = bounds_width(row_bounds)
+    Rc = bounds_width(col_bounds)
+    r0, r1 = row_bounds[rank], row_bounds[rank + 1]
     e0, e1 = int(rowptr[r0]), int(rowptr[r1])
     dev = col.device
     sub_col = col[e0:e1]
@@ -73,18 +117,18 @@ def split_row_block(rowptr: torch.Tensor, col: torch.Tensor, val: Optional[torch
     eid = torch.arange(e0, e1, device=dev, dtype=torch.int64)
     deg = (rowptr[r0 + 1:r1 + 1] - rowptr[r0:r1])
     row = torch.repeat_interleave(torch.arange(r1 - r0, device=dev, dtype=torch.int64), deg)
-    c0, c1 = rank * Rc, (rank + 1) * Rc
+    c0, c1 = col_bounds[rank], col_bounds[rank + 1]
     is_local = (sub_col >= c0) & (sub_col < c1)
 
-    def make(mask, rebase):
+    def make(mask, cols):
         cnt = torch.bincount(row[mask], minlength=R) if mask.numel() else torch.zeros(R, dtype=torch.int64, device=dev)
         rp = torch.zeros(R + 1, dtype=torch.int64, device=dev)
         rp[1:] = torch.cumsum(cnt, 0)
-        return CsrBlock(rp.to(torch.int32), (sub_col[mask] - rebase).to(torch.int32),
+        return CsrBlock(rp.to(torch.int32), cols.to(torch.int32),
                         None if sub_val is None else sub_val[mask].contiguous(), eid[mask].to(torch.int32))
 
-    local = make(is_local, c0)
-    remote = make(~is_local, 0)
+    local = make(is_local, sub_col[is_local] - c0)
+    remote = make(~is_local, slice_position(sub_col[~is_local], col_bounds, Rc))
     full_deg = torch.zeros(R, dtype=torch.float32, device=dev)
     full_deg[: r1 - r0] = deg.to(torch.float32)
     full_deg.clamp_(min=1.0)
@@ -92,13 +136,14 @@ def split_row_block(rowptr: torch.Tensor, col: torch.Tensor, val: Optional[torch
 
 
 def split_row_block_by_owner(rowptr: torch.Tensor, col: torch.Tensor, val: Optional[torch.Tensor],
-                             rank: int, world: int, n_cols: int):
+                             rank: int, world: int, n_cols: int, row_bounds=None, col_bounds=None):
     """Like split_row_block but one CSR block PER COLUMN OWNER q (columns rebased to q's slice),
     for the per-source pipelined gather.  Returns (blocks[world], row_degree, R)."""
     m = rowptr.numel() - 1
-    R = rows_per_rank(m, world)
-    Rc = rows_per_rank(n_cols, world)
-    r0, r1 = min(rank * R, m), min((rank + 1) * R, m)
+    row_bounds = even_bounds(m, world) if row_bounds is None else row_bounds
+    col_bounds = even_bounds(n_cols, world) if col_bounds is None else col_bounds
+    R = bounds_width(row_bounds)
+    r0, r1 = row_bounds[rank], row_bounds[rank + 1]
     e0, e1 = int(rowptr[r0]), int(rowptr[r1])
     dev = col.device
     sub_col = col[e0:e1]
@@ -106,14 +151,15 @@ def split_row_block_by_owner(rowptr: torch.Tensor, col: torch.Tensor, val: Optio
     eid = torch.arange(e0, e1, device=dev, dtype=torch.int64)
     deg = (rowptr[r0 + 1:r1 + 1] - rowptr[r0:r1])
     row = torch.repeat_interleave(torch.arange(r1 - r0, device=dev, dtype=torch.int64), deg)
-    owner = torch.div(sub_col, Rc, rounding_mode="floor")
+    cb = torch.as_tensor(col_bounds, dtype=torch.int64, device=dev)
+    owner = torch.bucketize(sub_col, cb[1:-1], right=True)
     blocks = []
     for q in range(world):
         mask = owner == q
         cnt = torch.bincount(row[mask], minlength=R) if mask.numel() else torch.zeros(R, dtype=torch.int64, device=dev)
         rp = torch.zeros(R + 1, dtype=torch.int64, device=dev)
         rp[1:] = torch.cumsum(cnt, 0)
-        blocks.append(CsrBlock(rp.to(torch.int32), (sub_col[mask] - q * Rc).to(torch.int32),
+        blocks.append(CsrBlock(rp.to(torch.int32), (sub_col[mask] - col_bounds[q]).to(torch.int32),
                                None if sub_val is None else sub_val[mask].contiguous(), eid[mask].to(torch.int32)))
     full_deg = torch.zeros(R, dtype=torch.float32, device=dev)
     full_deg[: r1 - r0] = deg.to(torch.float32)
@@ -135,7 +181,7 @@ class RowPartitionedSpMM:
 
     def __init__(self, rowptr: torch.Tensor, col: torch.Tensor, value: Optional[torch.Tensor], n_cols: int,
                  group=None, device=None, block_spmm: Optional[Callable] = None, overlap: bool = True,
-                 pipelined: Optional[bool] = None):
+                 pipelined: Optional[bool] = None, balance: str = "nnz", row_bounds=None, col_bounds=None):
         self.group = group
         self.world = dist.get_world_size(group) if dist.is_initialized() else 1
         self.rank = dist.get_rank(group) if dist.is_initialized() else 0
@@ -145,9 +191,23 @@ class RowPartitionedSpMM:
         self.device = torch.device(device) if device is not None else col.device
         self.block_spmm = block_spmm or _cuda_block_spmm
         self.overlap = overlap
-        local, remote, deg, R = split_row_block(rowptr, col, value, self.rank, self.world, self.n)
+        if balance not in ("nnz", "rows"):
+            raise ValueError(f"balance must be 'nnz' or 'rows', got {balance!r}")
+        if row_bounds is None:
+            row_bounds = nnz_balanced_bounds(rowptr, self.world) if balance == "nnz" else even_bounds(self.m, self.world)
+        if col_bounds is None:
+            # square A (a graph): X rows are owned like A rows, so a layer's output slice is the
+            # next layer's input slice; otherwise split the columns evenly
+            col_bounds = list(row_bounds) if self.n == self.m else even_bounds(self.n, self.world)
+        self.row_bounds, self.col_bounds = list(row_bounds), list(col_bounds)
+        if (len(self.row_bounds) != self.world + 1 or len(self.col_bounds) != self.world + 1 or
+                self.row_bounds[0] != 0 or self.row_bounds[-1] != self.m or
+                self.col_bounds[0] != 0 or self.col_bounds[-1] != self.n):
+            raise ValueError("row_bounds / col_bounds must be world+1 non-decreasing offsets from 0 to m / n")
+        local, remote, deg, R = split_row_block(rowptr, col, value, self.rank, self.world, self.n,
+                                                self.row_bounds, self.col_bounds)
         self.R = R
-        self.Rc = rows_per_rank(self.n, self.world)
+        self.Rc = bounds_width(self.col_bounds)
         mv = lambda b: CsrBlock(b.rowptr.to(self.device), b.col.to(self.device),
                                 None if b.val is None else b.val.to(self.device), b.edge_ids.to(self.device))
         self.local, self.remote = mv(local), mv(remote)
@@ -161,14 +221,25 @@ class RowPartitionedSpMM:
         self.pipelined = bool(pipelined) and self.world > 1 and self.device.type == "cuda"
         self.owner_blocks = None
         if self.pipelined:
-            blocks, _, _ = split_row_block_by_owner(rowptr, col, value, self.rank, self.world, self.n)
+            blocks, _, _ = split_row_block_by_owner(rowptr, col, value, self.rank, self.world, self.n,
+                                                    self.row_bounds, self.col_bounds)
             self.owner_blocks = [mv(b) for b in blocks]
         self.k_chunk = None        # feature-chunk width of the all-gather/SpMM pipeline (None = auto)
 
     # rows this rank owns (without padding)
     @property
     def own_rows(self) -> int:
-        return max(0, min((self.rank + 1) * self.R, self.m) - self.rank * self.R)
+        return self.row_bounds[self.rank + 1] - self.row_bounds[self.rank]
+
+    def row_range(self, rank: Optional[int] = None) -> Tuple[int, int]:
+        """Global rows of A / out owned by `rank` (default: this rank)."""
+        r = self.rank if rank is None else rank
+        return self.row_bounds[r], self.row_bounds[r + 1]
+
+    def col_range(self, rank: Optional[int] = None) -> Tuple[int, int]:
+        """Global rows of X (columns of A) owned by `rank` (default: this rank)."""
+        r = self.rank if rank is None else rank
+        return self.col_bounds[r], self.col_bounds[r + 1]
 
     def pad_x(self, x_own: torch.Tensor) -> torch.Tensor:
         """[own_cols, K] -> [Rc, K] zero padded (the regular slice the all-gather needs)."""
@@ -320,12 +391,12 @@ class DistSpMM:
     machinery as the forward), max/min through a local arg-scatter + reduce-scatter."""
 
     def __init__(self, rowptr, col, value, n_cols, group=None, device=None, block_spmm=None,
-                 arg_backward=None, overlap=True, pipelined=None):
+                 arg_backward=None, overlap=True, pipelined=None, balance="nnz"):
         self.rowptr, self.col, self.value = rowptr, col, value
         self.m, self.n = rowptr.numel() - 1, int(n_cols)
         self.group, self.device = group, device
         self._kw = dict(group=group, device=device, block_spmm=block_spmm, overlap=overlap, pipelined=pipelined)
-        self.fwd = RowPartitionedSpMM(rowptr, col, value, n_cols, **self._kw)
+        self.fwd = RowPartitionedSpMM(rowptr, col, value, n_cols, balance=balance, **self._kw)
         self._bwd = {}
         self._arg_backward = arg_backward or _cuda_arg_backward
         self._col32 = None
@@ -333,7 +404,9 @@ class DistSpMM:
     def bwd_op(self, mean: bool) -> RowPartitionedSpMM:
         if mean not in self._bwd:
             colptr, row_t, val_t = transpose_csr(self.rowptr, self.col, self.value, self.n, mean_weights=mean)
-            self._bwd[mean] = RowPartitionedSpMM(colptr, row_t, val_t, self.m, **self._kw)
+            # rows of A^T are the columns of A and vice versa: swap the forward's bounds
+            self._bwd[mean] = RowPartitionedSpMM(colptr, row_t, val_t, self.m, row_bounds=self.fwd.col_bounds,
+                                                 col_bounds=self.fwd.row_bounds, **self._kw)
         return self._bwd[mean]
 
     def __call__(self, x_slice: torch.Tensor, reduce: str = "sum") -> torch.Tensor:
@@ -366,7 +439,8 @@ class _DistSpMMFn(torch.autograd.Function):
         f = op.fwd
         dev = grad_out.device
         if op._col32 is None:
-            op._col32 = op.col.to(dev).to(torch.int32)
+            # scatter target = position of the column in the width-padded gathered layout
+            op._col32 = slice_position(op.col.to(dev).to(torch.int64), f.col_bounds, f.Rc).to(torch.int32)
             op._val_dev = None if op.value is None else op.value.to(dev)
         partial = op._arg_backward(op._col32, op._val_dev, arg, grad_out, f.world * f.Rc, f.nnz)
         if f.world == 1:

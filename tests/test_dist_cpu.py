@@ -68,7 +68,7 @@ def make_graph(seed, M, N, with_value):
     return rowptr, col, val
 
 
-def worker(rank, world, port, with_value, results):
+def worker(rank, world, port, with_value, balance, results):
     os.environ["MASTER_ADDR"] = "127.0.0.1"
     os.environ["MASTER_PORT"] = str(port)
     dist.init_process_group("gloo", rank=rank, world_size=world)
@@ -81,13 +81,19 @@ def worker(rank, world, port, with_value, results):
         x = np.random.default_rng(1).integers(-3, 4, size=(N, K)).astype(np.float32)
         go = np.random.default_rng(2).standard_normal((M, K)).astype(np.float32)
         op = DistSpMM(torch.from_numpy(rowptr), torch.from_numpy(col), None if val is None else torch.from_numpy(val),
-                      N, device="cpu", block_spmm=oracle_block_spmm, arg_backward=oracle_arg_backward, overlap=False)
+                      N, device="cpu", block_spmm=oracle_block_spmm, arg_backward=oracle_arg_backward, overlap=False,
+                      balance=balance)
         f = op.fwd
-        assert f.R == (M + world - 1) // world and f.local.nnz + f.remote.nnz == int(rowptr[min((rank + 1) * f.R, M)] - rowptr[min(rank * f.R, M)])
-        r0, r1 = rank * f.R, min((rank + 1) * f.R, M)
+        r0, r1 = f.row_range()
+        c0, c1 = f.col_range()
+        assert f.local.nnz + f.remote.nnz == int(rowptr[r1] - rowptr[r0])
+        if balance == "rows":
+            assert f.R == (M + world - 1) // world and (r0, r1) == (min(rank * f.R, M), min((rank + 1) * f.R, M))
+        else:
+            assert (c0, c1) == (r0, r1)          # square graph: X rows are owned like A rows
         ok = {}
         for reduce in ("sum", "mean", "max", "min"):
-            xs = f.pad_x(torch.from_numpy(x[rank * f.Rc: min((rank + 1) * f.Rc, N)])).requires_grad_(True)
+            xs = f.pad_x(torch.from_numpy(x[c0:c1])).requires_grad_(True)
             out = op(xs, reduce)
             gpad = torch.zeros((f.R, K))
             gpad[: r1 - r0] = torch.from_numpy(go[r0:r1])
@@ -102,20 +108,20 @@ def worker(rank, world, port, with_value, results):
                 ok[reduce + "_fwd"] = bool(np.allclose(got, ref[r0:r1], rtol=1e-5, atol=1e-5))
                 bw = oracle.spmm_backward_sum if reduce == "sum" else oracle.spmm_backward_mean
                 gref = bw(rowptr, col, val, go, N)
-            c0, c1 = rank * f.Rc, min((rank + 1) * f.Rc, N)
             ok[reduce + "_bwd"] = bool(np.allclose(xs.grad.numpy()[: c1 - c0], gref[c0:c1], rtol=1e-4, atol=1e-4))
         results[rank] = ok
     finally:
         dist.destroy_process_group()
 
 
+@pytest.mark.parametrize("balance", ["nnz", "rows"])
 @pytest.mark.parametrize("with_value", [True, False])
-def test_row_partitioned_spmm_world2_gloo(with_value):
+def test_row_partitioned_spmm_world2_gloo(with_value, balance):
     world = 2
-    port = 29500 + (os.getpid() % 2000) + (1 if with_value else 0)
+    port = 29500 + (os.getpid() % 2000) + (1 if with_value else 0) + (2 if balance == "nnz" else 0)
     mgr = mp.Manager()
     results = mgr.dict()
-    mp.spawn(worker, args=(world, port, with_value, results), nprocs=world, join=True)
+    mp.spawn(worker, args=(world, port, with_value, balance, results), nprocs=world, join=True)
     assert len(results) == world
     for rank in range(world):
         bad = [k for k, v in results[rank].items() if not v]
@@ -142,3 +148,36 @@ def test_split_row_block_partitions_every_entry_once():
                     assert (np.diff(seg) > 0).all()
             seen += loc.edge_ids.tolist() + rem.edge_ids.tolist()
         assert sorted(seen) == list(range(col.shape[0]))
+
+
+def test_nnz_balanced_bounds_even_out_a_skewed_graph():
+    """contiguous row ranges balanced by stored entries, not by rows."""
+    from isplib_b200.dist import nnz_balanced_bounds, even_bounds, split_row_block, slice_position, bounds_width
+    M = 400
+    deg = np.concatenate([np.full(40, 200), np.full(360, 3)])        # ids sorted by degree: heavy head
+    rowptr = np.zeros(M + 1, dtype=np.int64)
+    rowptr[1:] = np.cumsum(deg)
+    rng = np.random.default_rng(3)
+    col = np.concatenate([np.sort(rng.choice(M, size=d, replace=False)) for d in deg]).astype(np.int64)
+    rp, co = torch.from_numpy(rowptr), torch.from_numpy(col)
+    nnz = int(rowptr[-1])
+    for world in (2, 4, 8):
+        nb, eb = nnz_balanced_bounds(rp, world), even_bounds(M, world)
+        assert nb[0] == 0 and nb[-1] == M and all(nb[i] <= nb[i + 1] for i in range(world))
+        load = lambda b: max(int(rowptr[b[p + 1]] - rowptr[b[p]]) for p in range(world))
+        assert load(nb) <= 1.15 * nnz / world + 200          # within one heavy row of the ideal share
+        assert load(nb) < load(eb)
+        seen = []
+        Rc = bounds_width(nb)
+        for rank in range(world):
+            loc, rem, _, R = split_row_block(rp, co, None, rank, world, M, nb, nb)
+            assert R == bounds_width(nb)
+            assert loc.col.numel() == 0 or int(loc.col.max()) < nb[rank + 1] - nb[rank]
+            # remote columns point into the width-padded gathered layout, never into the own slice
+            assert not bool(((rem.col >= rank * Rc) & (rem.col < (rank + 1) * Rc)).any())
+            seen += loc.edge_ids.tolist() + rem.edge_ids.tolist()
+        assert sorted(seen) == list(range(nnz))
+        # the layout map is a bijection onto [owner * width, owner * width + size)
+        pos = slice_position(torch.arange(M), nb, Rc)
+        assert pos.unique().numel() == M and int(pos.max()) < world * Rc
+    assert nnz_balanced_bounds(torch.zeros(6, dtype=torch.int64), 4) == even_bounds(5, 4)   # empty graph

@@ -33,8 +33,8 @@ def worker(rank, world, port, results, pipelined=False):
         op = DistSpMM(g.rowptr.to(dev), g.col.to(dev), val.to(dev), g.n, device=dev, pipelined=pipelined)
         assert op.fwd.pipelined == pipelined
         f = op.fwd
-        r0, r1 = rank * f.R, min((rank + 1) * f.R, g.m)
-        c0, c1 = rank * f.Rc, min((rank + 1) * f.Rc, g.n)
+        r0, r1 = f.row_range()
+        c0, c1 = f.col_range()
         rp, co, va = g.rowptr.numpy(), g.col.numpy(), val.numpy()
         ok = {}
         for reduce in ("sum", "mean", "max", "min"):

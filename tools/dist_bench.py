@@ -18,6 +18,9 @@ ap.add_argument("--shape", default="amazon")
 ap.add_argument("--k", type=int, default=200)
 ap.add_argument("--reduce", default="max")
 ap.add_argument("--steps", type=int, default=10)
+ap.add_argument("--balance", default="nnz", choices=["nnz", "rows"], help="row ranges balanced by stored entries or by rows")
+ap.add_argument("--sort-degree", action="store_true",
+                help="relabel the nodes by descending degree first (ids sorted by degree: the skewed case)")
 a = ap.parse_args()
 world = int(os.environ.get("WORLD_SIZE", "1"))
 rank = int(os.environ.get("RANK", "0"))
@@ -31,10 +34,30 @@ from isplib_b200 import synth  # noqa: E402
 from isplib_b200.dist import DistSpMM  # noqa: E402
 
 g = synth.make_graph(a.shape, values="uniform", seed=0, device=dev)
-op = DistSpMM(g.rowptr, g.col, g.value, g.n, device=dev)
+rowptr, col, value = g.rowptr, g.col, g.value
+if a.sort_degree:
+    deg = rowptr[1:] - rowptr[:-1]
+    perm = torch.argsort(deg, descending=True, stable=True)            # new node i = old node perm[i]
+    inv = torch.empty_like(perm)
+    inv[perm] = torch.arange(g.m, device=dev)
+    new_row = inv[torch.repeat_interleave(torch.arange(g.m, device=dev), deg)]
+    new_col = inv[col]
+    order = torch.argsort(new_row * g.n + new_col)
+    col, value = new_col[order].contiguous(), value[order].contiguous()
+    rowptr = torch.zeros_like(rowptr)
+    rowptr[1:] = torch.cumsum(deg[perm], 0)
+    del new_row, new_col, order
+op = DistSpMM(rowptr, col, value, g.n, device=dev, balance=a.balance)
 f = op.fwd
+nnz_rank = torch.tensor([f.local.nnz + f.remote.nnz], device=dev, dtype=torch.int64)
+nnz_all = [torch.zeros_like(nnz_rank) for _ in range(world)]
+if world > 1:
+    dist.all_gather(nnz_all, nnz_rank)
+else:
+    nnz_all = [nnz_rank]
+nnz_all = [int(t.item()) for t in nnz_all]
 gen = torch.Generator(device=dev).manual_seed(0)
-c0, c1 = rank * f.Rc, min((rank + 1) * f.Rc, g.n)
+c0, c1 = f.col_range()
 x = f.pad_x(torch.randn(g.n, a.k, device=dev, generator=gen)[c0:c1]).requires_grad_(True)
 go = torch.randn(f.R, a.k, device=dev, generator=gen)
 
@@ -77,7 +100,10 @@ if rank == 0:
     b = synth.algorithmic_bytes(g.m, g.nnz, a.k, True, a.reduce)
     print(json.dumps({"shape": a.shape, "nodes": g.m, "nnz": g.nnz, "K": a.k, "reduce": a.reduce, "n_gpus": world,
                       "fwd_ms": round(t_f, 3), "fwd_bwd_ms": round(t_fb, 3), "bwd_ms": round(t_fb - t_f, 3),
-                      "fwd_total_effective_gbs": round(b / t_f / 1e6, 1)}), flush=True)
+                      "fwd_total_effective_gbs": round(b / t_f / 1e6, 1), "balance": a.balance,
+                      "sorted_by_degree": bool(a.sort_degree), "row_bounds": f.row_bounds,
+                      "nnz_per_rank": nnz_all, "nnz_imbalance": round(max(nnz_all) * world / max(1, sum(nnz_all)), 3)}),
+          flush=True)
 if world > 1:
     dist.barrier()
     dist.destroy_process_group()

@@ -65,7 +65,7 @@ def run(a, init_dist=True):
         f = op.fwd
         adj = None
         spmm = op
-        r0, r1 = rank * f.Rc, min((rank + 1) * f.Rc, N)
+        r0, r1 = f.col_range()
         x = f.pad_x(x_all[r0:r1])
         y = torch.zeros(f.Rc, dtype=torch.long, device=dev)
         y[: r1 - r0] = y_all[r0:r1]
