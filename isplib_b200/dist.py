@@ -4,10 +4,12 @@ SURVEY.md section 8e).
 One process per GPU (``torchrun``), ``torch.distributed`` over NCCL/NVLink.
 
 * A (M x N) is 1-D partitioned by rows: rank p owns the contiguous rows
-  ``[row_bounds[p], row_bounds[p+1])``.  ``balance="nnz"`` (default) cuts the ranges so that
-  every rank holds about nnz/P stored entries (power-law graphs whose ids are sorted by
-  locality or degree are badly skewed under an even row split); ``balance="rows"`` is the even
-  split ``R = ceil(M / P)``.  Rows of X / out are owned the same way (square A: the same
+  ``[row_bounds[p], row_bounds[p+1])``.  ``balance="rows"`` (default) is the even split
+  ``R = ceil(M / P)``; ``balance="nnz"`` cuts the ranges so that every rank holds about nnz/P
+  stored entries (power-law graphs whose ids are sorted by locality or degree are badly skewed
+  under an even row split: degree-sorted Reddit-shape graph on 2 GPUs, forward 2.76 -> 1.86 ms).
+  The backward operator (A^T) has to reuse the same bounds, because grad_x is owned like x; it
+  is balanced too when A is symmetric (undirected graphs), not in general.  Rows of X / out are owned the same way (square A: the same
   bounds; otherwise the columns are split evenly) and zero-padded to the widest range
   (``R`` / ``Rc``) so the all-gather is regular.
 * Each rank's row block is split by COLUMN OWNER into a *local* CSR block (columns the
@@ -181,7 +183,7 @@ class RowPartitionedSpMM:
 
     def __init__(self, rowptr: torch.Tensor, col: torch.Tensor, value: Optional[torch.Tensor], n_cols: int,
                  group=None, device=None, block_spmm: Optional[Callable] = None, overlap: bool = True,
-                 pipelined: Optional[bool] = None, balance: str = "nnz", row_bounds=None, col_bounds=None):
+                 pipelined: Optional[bool] = None, balance: str = "rows", row_bounds=None, col_bounds=None):
         self.group = group
         self.world = dist.get_world_size(group) if dist.is_initialized() else 1
         self.rank = dist.get_rank(group) if dist.is_initialized() else 0
@@ -391,7 +393,7 @@ class DistSpMM:
     machinery as the forward), max/min through a local arg-scatter + reduce-scatter."""
 
     def __init__(self, rowptr, col, value, n_cols, group=None, device=None, block_spmm=None,
-                 arg_backward=None, overlap=True, pipelined=None, balance="nnz"):
+                 arg_backward=None, overlap=True, pipelined=None, balance="rows"):
         self.rowptr, self.col, self.value = rowptr, col, value
         self.m, self.n = rowptr.numel() - 1, int(n_cols)
         self.group, self.device = group, device

@@ -18,7 +18,8 @@ ap.add_argument("--shape", default="amazon")
 ap.add_argument("--k", type=int, default=200)
 ap.add_argument("--reduce", default="max")
 ap.add_argument("--steps", type=int, default=10)
-ap.add_argument("--balance", default="nnz", choices=["nnz", "rows"], help="row ranges balanced by stored entries or by rows")
+ap.add_argument("--balance", default="rows", choices=["nnz", "rows"], help="row ranges balanced by stored entries or by rows")
+ap.add_argument("--prebuild", action="store_true", help="build the transposed (backward) operator before timing")
 ap.add_argument("--sort-degree", action="store_true",
                 help="relabel the nodes by descending degree first (ids sorted by degree: the skewed case)")
 a = ap.parse_args()
@@ -49,6 +50,8 @@ if a.sort_degree:
     del new_row, new_col, order
 op = DistSpMM(rowptr, col, value, g.n, device=dev, balance=a.balance)
 f = op.fwd
+if a.prebuild and a.reduce in ("sum", "mean"):
+    op.bwd_op(a.reduce == "mean")
 nnz_rank = torch.tensor([f.local.nnz + f.remote.nnz], device=dev, dtype=torch.int64)
 nnz_all = [torch.zeros_like(nnz_rank) for _ in range(world)]
 if world > 1:
