@@ -167,6 +167,24 @@ def make_graph(name_or_m, nnz: Optional[int] = None, *, n: Optional[int] = None,
     return SynthGraph(name, m, n, rowptr, col, value, int(deg.max()) if m else 0, gini(deg))
 
 
+def relabel_by_degree(rowptr: torch.Tensor, col: torch.Tensor, value: Optional[torch.Tensor], n: int):
+    """P A P^T with the nodes renumbered by descending out-degree (square graphs): the layout in
+    which an even row split is badly skewed.  Returns (rowptr, col, value), rows sorted by column."""
+    m = rowptr.numel() - 1
+    assert m == n, "relabel_by_degree needs a square adjacency"
+    dev = col.device
+    deg = rowptr[1:] - rowptr[:-1]
+    perm = torch.argsort(deg, descending=True, stable=True)            # new node i = old node perm[i]
+    inv = torch.empty_like(perm)
+    inv[perm] = torch.arange(m, device=dev)
+    new_row = inv[torch.repeat_interleave(torch.arange(m, device=dev), deg)]
+    new_col = inv[col]
+    order = torch.argsort(new_row * n + new_col)
+    out_rowptr = torch.zeros_like(rowptr)
+    out_rowptr[1:] = torch.cumsum(deg[perm], 0)
+    return out_rowptr, new_col[order].contiguous(), None if value is None else value[order].contiguous()
+
+
 def algorithmic_bytes(m: int, nnz: int, k: int, has_value: bool, reduce: str = "sum") -> int:
     """B_alg of SURVEY.md section 8d / BASELINE.md section 3 (int32 CSR, fp32)."""
     b = 4 * (m + 1) + 4 * nnz + (4 * nnz if has_value else 0) + 4 * k * nnz + 4 * k * m

@@ -164,3 +164,23 @@ def test_reordering_commutes_with_spmm():
         torch.testing.assert_close(out_p, ref[perm], rtol=1e-5, atol=1e-5)
         mx = sys.modules["torch_sparse"].matmul(adj_p, x[perm], "max")
         torch.testing.assert_close(mx, sys.modules["torch_sparse"].matmul(adj, x, "max")[perm])
+
+
+def test_relabel_by_degree_is_a_symmetric_permutation():
+    """synth.relabel_by_degree returns P A P^T with non-increasing row degrees; (P A P^T)(P x) = P (A x)."""
+    import numpy as np
+    from isplib_b200 import synth
+    from oracle import oracle
+    g = synth.make_graph(300, 5000, law="lognormal", param=1.2, seed=3, device="cpu", values="uniform")
+    rp, co, va = synth.relabel_by_degree(g.rowptr, g.col, g.value, g.n)
+    deg = (rp[1:] - rp[:-1]).numpy()
+    assert (np.diff(deg) <= 0).all() and int(rp[-1]) == g.nnz
+    for i in range(0, 300, 37):                      # columns stay sorted inside a row
+        seg = co[int(rp[i]):int(rp[i + 1])].numpy()
+        assert (np.diff(seg) >= 0).all()
+    old_deg = (g.rowptr[1:] - g.rowptr[:-1])
+    perm = torch.argsort(old_deg, descending=True, stable=True).numpy()
+    x = np.random.default_rng(0).standard_normal((300, 8)).astype(np.float32)
+    ref, _ = oracle.spmm_c(g.rowptr.numpy(), g.col.numpy(), g.value.numpy(), x, oracle.SUM)
+    got, _ = oracle.spmm_c(rp.numpy(), co.numpy(), va.numpy(), x[perm], oracle.SUM)
+    np.testing.assert_allclose(got, ref[perm], rtol=1e-5, atol=1e-5)

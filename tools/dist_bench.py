@@ -37,17 +37,7 @@ from isplib_b200.dist import DistSpMM  # noqa: E402
 g = synth.make_graph(a.shape, values="uniform", seed=0, device=dev)
 rowptr, col, value = g.rowptr, g.col, g.value
 if a.sort_degree:
-    deg = rowptr[1:] - rowptr[:-1]
-    perm = torch.argsort(deg, descending=True, stable=True)            # new node i = old node perm[i]
-    inv = torch.empty_like(perm)
-    inv[perm] = torch.arange(g.m, device=dev)
-    new_row = inv[torch.repeat_interleave(torch.arange(g.m, device=dev), deg)]
-    new_col = inv[col]
-    order = torch.argsort(new_row * g.n + new_col)
-    col, value = new_col[order].contiguous(), value[order].contiguous()
-    rowptr = torch.zeros_like(rowptr)
-    rowptr[1:] = torch.cumsum(deg[perm], 0)
-    del new_row, new_col, order
+    rowptr, col, value = synth.relabel_by_degree(rowptr, col, value, g.n)
 op = DistSpMM(rowptr, col, value, g.n, device=dev, balance=a.balance)
 f = op.fwd
 if a.prebuild and a.reduce in ("sum", "mean"):

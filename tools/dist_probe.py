@@ -18,6 +18,7 @@ ap.add_argument("--shape", default="reddit")
 ap.add_argument("--k", type=int, default=128)
 ap.add_argument("--balance", default="rows")
 ap.add_argument("--steps", type=int, default=10)
+ap.add_argument("--sort-degree", action="store_true")
 a = ap.parse_args()
 world = int(os.environ.get("WORLD_SIZE", "1"))
 rank = int(os.environ.get("RANK", "0"))
@@ -31,7 +32,10 @@ from isplib_b200 import synth  # noqa: E402
 from isplib_b200.dist import DistSpMM  # noqa: E402
 
 g = synth.make_graph(a.shape, values="uniform", seed=0, device=dev)
-op = DistSpMM(g.rowptr, g.col, g.value, g.n, device=dev, balance=a.balance)
+rowptr, col, value = g.rowptr, g.col, g.value
+if a.sort_degree:
+    rowptr, col, value = synth.relabel_by_degree(rowptr, col, value, g.n)
+op = DistSpMM(rowptr, col, value, g.n, device=dev, balance=a.balance)
 f = op.fwd
 t = op.bwd_op(False)
 gen = torch.Generator(device=dev).manual_seed(0)
@@ -64,7 +68,7 @@ def block_only(o, blk, xin):
     return lambda: o.block_spmm(0, blk, xin, out, None, 0, None, o.nnz, o.variant)
 
 
-res = {"balance": a.balance, "n_gpus": world}
+res = {"balance": a.balance, "n_gpus": world, "sorted_by_degree": bool(a.sort_degree), "row_bounds": f.row_bounds}
 for name, o, xin in (("fwd", f, x), ("bwd", t, go)):
     res[name + "_full_ms"] = timed(lambda: o.forward(xin, "sum"))
     res[name + "_local_ms"] = timed(block_only(o, o.local, xin))
