@@ -63,7 +63,7 @@ def run_shape(shape, ks, reduces, values, rows, iters):
                 if hv and red == "sum":
                     t = ev_time(lambda: capi.sddmm_csr(rp, co, go, x, plan, False), iters)
                     b = 4 * (g.m + 1) + 4 * g.nnz + 4 * k * g.nnz + 4 * k * g.m + 4 * g.nnz
-                    rows.append((shape, g.m, g.nnz, k, red, "bwd grad_value (SDDMM)", "sddmm_lean256|seg_kernel", t, 2 * g.nnz * k / t / 1e6, b / t / 1e6, b / t / 1e6 / pk))
+                    rows.append((shape, g.m, g.nnz, k, red, "bwd grad_value (SDDMM)", "sddmm_lean256 / sddmm_seg", t, 2 * g.nnz * k / t / 1e6, b / t / 1e6, b / t / 1e6 / pk))
             else:
                 _, arg = capi.spmm_csr(red, rp, co, g.value, x, plan, best)
                 t = ev_time(lambda: capi.spmm_arg_backward(co, g.value, None, arg, go.contiguous(), g.n, True, False), iters)
