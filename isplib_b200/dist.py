@@ -227,6 +227,7 @@ class RowPartitionedSpMM:
                                                     self.row_bounds, self.col_bounds)
             self.owner_blocks = [mv(b) for b in blocks]
         self.k_chunk = None        # feature-chunk width of the all-gather/SpMM pipeline (None = auto)
+        self._gather_bufs = {}     # persistent all-gather receive buffers, keyed by (K, dtype, device)
 
     # rows this rank owns (without padding)
     @property
@@ -251,10 +252,23 @@ class RowPartitionedSpMM:
         out[: x_own.size(0)] = x_own
         return out
 
-    def _all_gather(self, x_slice: torch.Tensor) -> torch.Tensor:
+    def _all_gather(self, x_slice: torch.Tensor, persistent: bool = False) -> torch.Tensor:
         if self.world == 1:
             return x_slice
-        gathered = torch.empty((self.world * self.Rc, x_slice.size(1)), dtype=x_slice.dtype, device=x_slice.device)
+        shape = (self.world * self.Rc, x_slice.size(1))
+        if persistent and x_slice.is_cuda:
+            # one receive buffer per feature width, kept for the life of the operator: a fresh
+            # multi-GB torch.empty per call on the side stream (plus record_stream, which delays
+            # its reuse) makes the caching allocator grow and cudaMalloc in the hot path.  Safe
+            # because every forward starts with comm_stream.wait_stream(current), i.e. after the
+            # previous call's remote-block SpMM has read the buffer, and nothing is saved from it.
+            key = (shape[1], x_slice.dtype, x_slice.device)
+            gathered = self._gather_bufs.get(key)
+            if gathered is None:
+                gathered = torch.empty(shape, dtype=x_slice.dtype, device=x_slice.device)
+                self._gather_bufs[key] = gathered
+        else:
+            gathered = torch.empty(shape, dtype=x_slice.dtype, device=x_slice.device)
         dist.all_gather_into_tensor(gathered, x_slice, group=self.group)
         return gathered
 
@@ -287,7 +301,9 @@ class RowPartitionedSpMM:
             with torch.cuda.stream(self.comm_stream):
                 for (c0, c1) in chunks:
                     xc = x_slice if len(chunks) == 1 else x_slice[:, c0:c1].contiguous()
-                    gathered.append(self._all_gather(xc))
+                    # chunks of one call are in flight together, so only the unchunked default
+                    # can share one persistent buffer
+                    gathered.append(self._all_gather(xc, persistent=(len(chunks) == 1)))
                     ev = torch.cuda.Event()
                     ev.record(self.comm_stream)
                     events.append(ev)
@@ -296,7 +312,8 @@ class RowPartitionedSpMM:
                 ao = None if arg is None else arg[:, c0:c1]
                 self.block_spmm(inner, self.local, xo, oo, ao, 0, None, self.nnz, self.variant)   # overlaps the gather
                 cur.wait_event(events[ci])
-                gathered[ci].record_stream(cur)
+                if len(chunks) > 1:
+                    gathered[ci].record_stream(cur)
                 self.block_spmm(inner, self.remote, gathered[ci], oo, ao, FLAG_ACCUMULATE, div, self.nnz, self.variant)
             return out, arg
         gathered = self._all_gather(x_slice)
