@@ -64,3 +64,45 @@ def test_host_side_argument_validation():
 def test_plan_info_struct_layout_matches_header():
     from isplib_b200 import capi
     assert ctypes.sizeof(capi.PlanInfo) == 8 + 8 + 4 + 4 + 8 * 5 + 8
+
+
+def test_variant_ids_quoted_in_profiles_and_bench_stay_valid():
+    """profiles/README.md and bench.py quote variant ids / names; new variants must be appended
+    to the table, never inserted, and the ncu traffic table may only name existing variants."""
+    import importlib.util
+    import os
+    from isplib_b200 import capi, synth
+    names = capi.variant_names()
+    assert names[7] == "seg/w4/u4/kt64" and names[22] == "lean256/w4/kt64" and names[24] == "lean256/w4/kt64/seq"
+    assert len(set(names)) == len(names)
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    spec = importlib.util.spec_from_file_location("bench_mod", os.path.join(root, "bench.py"))
+    bench = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(bench)
+    for (shape, k, reduce, variant), traffic in bench.NCU_TRAFFIC_BYTES.items():
+        assert variant in names and traffic > 0 and reduce in ("sum", "mean", "max", "min") and k > 0
+        assert shape in synth.SHAPES
+
+
+def test_variant_default_follows_the_measured_rules():
+    """Shape-only default (no GPU needed, pointers are only checked for alignment):
+    sum/mean -> lean 256-bit kernel, 64-wide sequential slabs once X exceeds L2; rows that are
+    only 16-byte aligned -> lean128; max/min -> seg while X can be L2-resident, lean256 beyond."""
+    from isplib_b200 import capi
+    L = capi.lib()
+    names = capi.variant_names()
+    ptr = 1 << 20                                    # 32-byte aligned fake address
+    SUM, MAX = capi.REDUCE_CODE["sum"], capi.REDUCE_CODE["max"]
+
+    def default(reduce, n, k, ldx=None, x=ptr):
+        return names[L.isplib_b200_variant_default(reduce, n, k, ldx or k, k, x, ptr, 100.0)]
+
+    assert default(SUM, 232965, 64) == "lean256/w4/kfull"
+    assert default(SUM, 232965, 128) == "lean256/w4/kt64/seq"
+    assert default(SUM, 1569960, 200) == "lean256/w4/kfull"          # ragged tile, HBM regime
+    assert default(SUM, 2449029, 100) == "lean128/w4/kfull"          # rows only 16-byte aligned
+    assert default(SUM, 2449029, 47, ldx=48) == "lean256/w4/kfull"   # padded odd width
+    assert default(SUM, 1000, 64, x=ptr + 16) == "lean128/w4/kfull"  # operand only 16-byte aligned
+    assert default(MAX, 232965, 128).startswith("seg/")
+    assert default(MAX, 1569960, 200) == "lean256/w4/kfull"
+    assert default(SUM, 1000, 7).startswith("seg/")                  # scalar rows
