@@ -47,6 +47,8 @@ def parse_args():
     ap.add_argument("--variant", type=int, default=None, help="force a kernel variant (default: on-device autotune)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-gcn", action="store_true", help="skip the secondary GCN-epoch measurement")
+    ap.add_argument("--no-parity", action="store_true", help="skip the sampled-row oracle check of the timed output")
+    ap.add_argument("--no-configs", action="store_true", help="skip the K x reduce x fwd/bwd table (N=1 only)")
     ap.add_argument("--cpu-seconds", type=float, default=12.0, help="budget for the cpu_baseline leg")
     return ap.parse_args()
 
@@ -260,6 +262,132 @@ def cpu_baseline_leg(args, budget_s):
             "ms": round(dt * 1e3, 2), "gflops": round(2.0 * g.nnz * K / dt / 1e9, 2)}
 
 
+def parity_check(torch, dist, world, g, x, out, arg, row0, reduce, n_rows=2000):
+    """Outside the timed region: `n_rows` sampled output rows (spread over all ranks' row ranges)
+    of the output the timed kernel produced, against the CPU oracle on the same inputs
+    (oracle/fusedmm_oracle.c, the restated fusedMM_csr driven like csrc/fusedmm.cpp:113-203).
+    sum/mean: |a-b| <= 1e-6 + 1e-5|b|, elements that miss it must sit inside the
+    condition-aware bound (conftest.assert_sum_close) and be < 0.1 %; max/min: bit-exact incl. arg.
+    `out` holds this rank's rows [row0, row0 + out.size(0)) (padding rows beyond M ignored)."""
+    import numpy as np
+    from oracle import oracle
+    dev = x.device
+    M = g.m
+    r1 = min(M, row0 + out.size(0))
+    per_rank = max(16, n_rows // world)
+    gen = torch.Generator(device="cpu").manual_seed(1234 + row0)
+    if r1 <= row0:
+        idx = torch.zeros(0, dtype=torch.int64, device=dev)
+    else:
+        idx = torch.randint(row0, r1, (per_rank,), generator=gen).unique().to(dev)
+    deg = g.rowptr[idx + 1] - g.rowptr[idx]
+    sub_rp = torch.zeros(idx.numel() + 1, dtype=torch.int64, device=dev)
+    sub_rp[1:] = torch.cumsum(deg, 0)
+    total = int(sub_rp[-1])
+    pos = torch.arange(total, device=dev) - torch.repeat_interleave(sub_rp[:-1], deg)
+    eidx = torch.repeat_interleave(g.rowptr[idx], deg) + pos
+    sub_col = g.col[eidx].cpu().numpy()
+    sub_val = None if g.value is None else g.value[eidx].cpu().numpy()
+    xh = x.cpu().numpy()
+    code = oracle.REDUCE_CODE[reduce]
+    ref, ref_arg = oracle.spmm_c(sub_rp.cpu().numpy(), sub_col, sub_val, xh, code)
+    got = out[idx - row0].cpu().numpy()
+    res = {"rows": int(idx.numel()), "elements": int(got.size)}
+    if idx.numel() == 0:
+        res.update({"max_abs_err": 0.0, "ok": True})
+    elif reduce in ("max", "min"):
+        ga = arg[idx - row0].cpu()
+        # global edge ids -> positions inside the sampled sub-graph
+        ga = ga.numpy()
+        ref_glob = np.where(ref_arg == total, g.nnz, eidx.cpu().numpy()[np.minimum(ref_arg, max(total - 1, 0))])
+        ok = bool(np.array_equal(got, ref) and np.array_equal(ga, ref_glob))
+        res.update({"max_abs_err": float(np.abs(got.astype(np.float64) - ref).max()), "bit_exact": ok, "ok": ok})
+    else:
+        err = np.abs(got.astype(np.float64) - ref.astype(np.float64))
+        plain_bad = err > 1e-6 + 1e-5 * np.abs(ref)
+        n_bad = int(plain_bad.sum())
+        ok = True
+        if n_bad:
+            absval = np.ones(sub_col.shape[0], np.float32) if sub_val is None else np.abs(sub_val)
+            cond = oracle.spmm_c(sub_rp.cpu().numpy(), sub_col, absval, np.abs(xh), code)[0]
+            ok = not bool((plain_bad & (err > 1e-6 + 1e-5 * np.maximum(np.abs(ref), cond))).any())
+            ok = ok and n_bad <= 1e-3 * err.size
+        res.update({"max_abs_err": float(err.max()), "need_condition_bound": n_bad, "ok": ok})
+    if world > 1:
+        t = torch.tensor([res["max_abs_err"], 0.0 if res["ok"] else 1.0, float(res["rows"]), float(res["elements"]),
+                          float(res.get("need_condition_bound", 0))], device=dev, dtype=torch.float64)
+        mx = t.clone()
+        dist.all_reduce(mx, op=dist.ReduceOp.MAX)
+        dist.all_reduce(t, op=dist.ReduceOp.SUM)
+        res["max_abs_err"] = float(mx[0])
+        res["ok"] = bool(float(mx[1]) == 0.0)
+        res["rows"], res["elements"] = int(t[2]), int(t[3])
+        if "need_condition_bound" in res:
+            res["need_condition_bound"] = int(t[4])
+        res["ranks_checked"] = world
+    res["against"] = "oracle/fusedmm_oracle.c on the same inputs, sampled rows of the timed output"
+    return res
+
+
+def configs_table(torch, capi, synth, g, rp32, co32, plan, peak):
+    """BASELINE.json configs[1] in full: K in {32,64,128,256} x {sum,mean,max,min}, forward
+    (autotuned variant) and backward (A^T SpMM over the device-built CSC view for sum/mean, the
+    streamed arg scatter for max/min); ms = median of 5 launches, frac = B_alg / ms / HBM peak."""
+    dev = g.col.device
+    M, N, nnz = g.m, g.n, g.nnz
+
+    def med_ms(fn, n=5):
+        fn()
+        ts = []
+        for _ in range(n):
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            fn()
+            e1.record()
+            torch.cuda.synchronize()
+            ts.append(e0.elapsed_time(e1))
+        ts.sort()
+        return ts[len(ts) // 2]
+
+    colptr, row_t, csr2csc = capi.csr_transpose(rp32, co32, N)
+    plan_t = capi.Plan(colptr, nnz)
+    vt = capi.permute_values(g.value, csr2csc, row_t, rp32, False)
+    names = capi.variant_names()
+    rows = []
+    gen = torch.Generator(device=dev).manual_seed(7)
+    for K in (32, 64, 128, 256):
+        x = torch.randn(N, K, device=dev, generator=gen)
+        go = torch.randn(M, K, device=dev, generator=gen)
+        for reduce in ("sum", "mean", "max", "min"):
+            best, _ = capi.spmm_autotune(reduce, rp32, co32, g.value, x, plan, iters=2)
+            out = torch.empty(M, K, device=dev)
+            is_arg = reduce in ("max", "min")
+            arg = torch.empty(M, K, dtype=torch.int64, device=dev) if is_arg else None
+            acol = torch.empty(M, K, dtype=torch.int32, device=dev) if is_arg else None
+            aval = torch.empty(M, K, device=dev) if is_arg else None
+            ms_f = med_ms(lambda: capi.spmm_csr(reduce, rp32, co32, g.value, x, plan, best, out=out, arg_out=arg))
+            b_f = synth.algorithmic_bytes(M, nnz, K, True, reduce)
+            row = {"K": K, "reduce": reduce, "fwd_ms": round(ms_f, 3), "fwd_frac": round(b_f / ms_f / 1e6 / peak, 3),
+                   "fwd_variant": names[best]}
+            if is_arg:
+                capi.spmm_csr(reduce, rp32, co32, g.value, x, plan, best, out=out, arg_out=arg, arg_col=acol, arg_val=aval)
+                ms_b = med_ms(lambda: capi.spmm_arg_backward_aux(acol, aval, go, N))
+                # SURVEY 8d: arg stream (here 4+4 B aux instead of the 8 B int64) + grad_out + RMW on grad_x + zero-init
+                b_b = (8 + 4 + 8) * K * M + 4 * K * N
+                row.update({"bwd": "arg-scatter (aux streams)"})
+            else:
+                w = vt if reduce == "sum" else capi.permute_values(g.value, csr2csc, row_t, rp32, True)
+                bt, _ = capi.spmm_autotune("sum", colptr, row_t, w, go, plan_t, iters=2)
+                gx = torch.empty(N, K, device=dev)
+                ms_b = med_ms(lambda: capi.spmm_csr("sum", colptr, row_t, w, go, plan_t, bt, out=gx))
+                b_b = synth.algorithmic_bytes(N, nnz, K, True, "sum")
+                row.update({"bwd": "A^T SpMM", "bwd_variant": names[bt]})
+            row.update({"bwd_ms": round(ms_b, 3), "bwd_frac": round(b_b / ms_b / 1e6 / peak, 3)})
+            rows.append(row)
+        del x, go
+    return rows
+
+
 def run_ours(args):
     import torch
     import torch.distributed as dist
@@ -302,6 +430,7 @@ def run_ours(args):
 
         def step(i):
             capi.spmm_csr(reduce, rp32, co32, g.value, xs[i & 1], plan, best, out=out, arg_out=arg)
+            return out, arg, 0
         variant_name = capi.variant_names()[best]
         # one kernel per SpMM (split rows are merged inside it); */seq variants launch once per K tile
         launches_per_step = 1
@@ -317,7 +446,8 @@ def run_ours(args):
             op.variant = args.variant
 
         def step(i):
-            op.forward(slices[i & 1], reduce)
+            o, a = op.forward(slices[i & 1], reduce)
+            return o, a, op.row_range()[0]
         step(0)
         launches_per_step = op.launches_per_forward() * len(op._k_chunks(K))
         variant_name = "auto" if args.variant is None else capi.variant_names()[args.variant]
@@ -352,6 +482,24 @@ def run_ours(args):
     clocks = sampler.stop(w0, w1) if rank == 0 else None
     ms_step = ms_total / args.steps
     value = b_alg / (ms_step * 1e-3) / 1e9
+
+    # --- parity of what was just timed (outside the timed region), every rank's rows -----------
+    parity = None
+    if not args.no_parity:
+        try:
+            o_chk, a_chk, row0 = step(0)
+            torch.cuda.synchronize()
+            parity = parity_check(torch, dist, world, g, xs[0], o_chk, a_chk, row0, reduce)
+        except Exception as ex:
+            parity = {"ok": False, "error": repr(ex)[:300]}
+
+    cfg_table = None
+    if world == 1 and not args.no_configs and args.shape == "reddit":
+        try:
+            cfg_table = configs_table(torch, capi, synth, g, rp32, co32, plan, peaks()[0])
+        except Exception as ex:
+            cfg_table = [{"error": repr(ex)[:300]}]
+        torch.cuda.empty_cache()
 
     # --- e2e: through the plugin (torch_sparse.matmul) with HOST buffers ---------------------
     e2e = None
@@ -493,17 +641,33 @@ def run_ours(args):
         return 0
 
     peak, peak_src = peaks()
-    roofline = {"bound": "hbm", "achieved": round(value / world, 2) if world > 1 else round(value, 2), "peak": peak,
-                "unit": "GB/s", "frac": round((value / world) / peak, 4),
+    kernel_name = ("isplib::spmm_fused_gather_kernel" if variant_name.startswith("fused-gather")
+                   else "isplib::spmm_lean_kernel" if variant_name.startswith("lean")
+                   else "isplib::spmm_bulk_kernel" if variant_name.startswith("bulk")
+                   else "isplib::spmm_seg_kernel")
+    per_gpu = value / world
+    # Which ceiling binds: with a K tile whose [N, tile] slab of X fits the 126 MB L2 the gathers are
+    # served by L2 (ncu: dram bytes ~0.09 x B_alg, lts__throughput 86 %), so the kernel runs against
+    # the L2 random-row-gather bandwidth that tools/l2probe.cu measures on the same GPU (19.8 TB/s with
+    # 32-byte loads, profiles/r1_l2probe.txt); otherwise against HBM.  `frac` stays B_alg / HBM peak
+    # (SURVEY 8d's definition, what north_star's ">= 60 % of HBM roofline" is stated on).
+    slab_bytes = N * min(K, 64) * 4
+    l2_bound = slab_bytes <= 64 * 1024 * 1024
+    L2_GATHER_PEAK = 19800.0
+    roofline = {"bound": "l2" if l2_bound else "hbm", "achieved": round(per_gpu, 2), "peak": peak,
+                "unit": "GB/s", "frac": round(per_gpu / peak, 4),
+                "l2_gather_peak": L2_GATHER_PEAK, "l2_frac": round(per_gpu / L2_GATHER_PEAK, 4),
+                "l2_peak_source": "tools/l2probe.cu gather256 over a 60 MB footprint on B200 (profiles/r1_l2probe.txt)",
                 "traffic": NCU_TRAFFIC_BYTES.get((args.shape, K, reduce, variant_name)) if world == 1 else None,
-                "kernel": ("isplib::spmm_lean_kernel" if variant_name.startswith("lean")
-                           else "isplib::spmm_bulk_kernel" if variant_name.startswith("bulk")
-                           else "isplib::spmm_seg_kernel"),
+                "traffic_source": "dram__bytes_read.sum + dram__bytes_write.sum of one `ncu --set full` capture of this "
+                                  "command's kernel (profiles/, see NCU_TRAFFIC_BYTES); not re-measured by this run",
+                "kernel": kernel_name,
                 "peak_source": peak_src,
                 "algorithmic_bytes_per_launch": b_alg // world // (launches_per_step if world == 1 else 1),
                 "note": "achieved = B_alg per step / CUDA-event step time; a step is exactly one launch of "
                         "that kernel (one per K tile for */seq variants). B_alg counts one K-row gather per stored entry, so it exceeds HBM "
-                        "traffic when X rows hit in the 126 MB L2 (ncu dram bytes in profiles/)."}
+                        "traffic when X rows hit in the 126 MB L2 (ncu dram bytes in profiles/): frac > 1 is the L2 regime, "
+                        "l2_frac is the fraction of the ceiling that actually binds there."}
     line = {
         "metric": "spmm_sum_effective_gbs", "value": round(value, 2), "unit": "GB/s", "n_gpus": world,
         "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": round(ms_step, 4),
@@ -519,6 +683,10 @@ def run_ours(args):
         "gpu_launches": launches_per_step * args.steps,
         "clocks": clocks,
     }
+    if parity is not None:
+        line["parity_check"] = parity
+    if cfg_table is not None:
+        line["configs"] = cfg_table
     if tune:
         line["autotune_ms"] = tune
     if e2e is not None:

@@ -39,7 +39,7 @@
 extern "C" {
 #endif
 
-#define ISPLIB_B200_ABI_VERSION 1
+#define ISPLIB_B200_ABI_VERSION 2
 
 /* reduction codes == `reduction` of fusedmm_spmm_fw, csrc/fusedmm.cpp:147-186 */
 #define ISPLIB_REDUCE_SUM  0
@@ -60,6 +60,8 @@ extern "C" {
 #define ISPLIB_FLAG_EMPTY_ZERO  0x2   /* max/min: rows with no entry produce 0 (torch_sparse
                                          convention) instead of keeping lowest()/max()
                                          (what csrc/fusedmm.cpp:147-150 leaves behind) */
+
+#define ISPLIB_FLAG_RELU        0x4   /* out = max(out, 0) after everything else (isplib_b200_spmm_csr_fused) */
 
 #define ISPLIB_VARIANT_AUTO (-1)
 
@@ -127,6 +129,37 @@ int isplib_b200_spmm_csr_ex(int reduce, int64_t m, int64_t n, int64_t k, int64_t
                             const int32_t* edge_ids, int64_t arg_sentinel,
                             isplib_stream_t stream);
 
+/* Fused form: the forward plus what the reference's callers do to its result in separate
+ * [M,K] passes, applied when a row is finalised:
+ *     out[i,:] = relu?( REDUCE(...)[i,:] + addend_scale * addend[i,:] + bias[:] )
+ *   GCN   `+ bias`, ReLU            /root/reference/tests/cpu/gcn-sparse.py:61-68 (GCNConv bias, F.relu)
+ *   GIN   (1 + eps) * x_i + sum_j   /root/reference/tests/cpu/gin-sparse.py:73-78 (addend = x, scale = 1 + eps)
+ *   SAGE  root term / residual      /root/reference/tests/cpu/graphSAGE-sparse.py:71-78
+ * and, for max/min, two auxiliary outputs the backward scatter then streams instead of
+ * gathering col[arg] / val[arg] (csrc/fusedmm.cpp:432-441): arg_col[i,kk] = col[arg] (-1 where
+ * no entry won), arg_val[i,kk] = val[arg].  Every member is optional (NULL / 0); epi == NULL is
+ * isplib_b200_spmm_csr_ex.  ReLU is requested with ISPLIB_FLAG_RELU in `flags`.  With
+ * ISPLIB_FLAG_ACCUMULATE pass the epilogue on the LAST block only; arg_col/arg_val cannot be
+ * combined with ISPLIB_FLAG_ACCUMULATE.                                                        */
+typedef struct isplib_b200_epilogue {
+    const float* bias;         /* [k] */
+    const float* addend;       /* [m,k], row stride ld_addend */
+    int64_t      ld_addend;
+    float        addend_scale;
+    int32_t      reserved;
+    int32_t*     arg_col;      /* [m,k], row stride ldo (max/min only) */
+    float*       arg_val;      /* [m,k], row stride ldo (max/min only, needs arg_col) */
+} isplib_b200_epilogue;
+int isplib_b200_spmm_csr_fused(int reduce, int64_t m, int64_t n, int64_t k, int64_t nnz,
+                               const int32_t* rowptr, const int32_t* col, const float* val,
+                               const float* x, int64_t ldx, float* out, int64_t ldo,
+                               int64_t* arg_out,
+                               const isplib_b200_plan_info* info, const void* plan_dev,
+                               void* workspace, size_t workspace_bytes,
+                               int variant, int flags, const float* row_divisor,
+                               const int32_t* edge_ids, int64_t arg_sentinel,
+                               const isplib_b200_epilogue* epi, isplib_stream_t stream);
+
 /* ---- kernel variants + on-device selection: replaces autotuner/findbestk.py:29-41
  *      (an offline K sweep) by timing the eligible row-split / K-tile / unroll
  *      variants on the device, on the caller's own graph and buffers ------------ */
@@ -182,6 +215,15 @@ int isplib_b200_spmm_arg_backward(int64_t m, int64_t n, int64_t k, int64_t nnz,
                                   const float* grad_out, int64_t ldgo,
                                   float* grad_x, int64_t ldgx, float* grad_val,
                                   int zero_init, isplib_stream_t stream);
+/* The same grad_x from the forward's auxiliary outputs (isplib_b200_epilogue.arg_col / arg_val,
+ * row stride ld_aux): two coalesced 4-byte streams replace the int64 arg read and the
+ * col[arg] / val[arg] sector gathers; only the adds into grad_x stay random.
+ *     grad_x[arg_col[i,kk], kk] += (arg_val ? arg_val[i,kk] : 1) * grad_out[i,kk]   where arg_col >= 0 */
+int isplib_b200_spmm_arg_backward_aux(int64_t m, int64_t n, int64_t k,
+                                      const int32_t* arg_col, const float* arg_val, int64_t ld_aux,
+                                      const float* grad_out, int64_t ldgo,
+                                      float* grad_x, int64_t ldgx,
+                                      int zero_init, isplib_stream_t stream);
 
 /* Gradient w.r.t. the stored values of the sum / mean SpMM (SDDMM on the CSR pattern):
  *     out_val[e] = < a[row(e),:], x[col[e],:] >   (mean_scale != 0: / max(deg(row(e)),1))

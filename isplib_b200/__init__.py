@@ -20,7 +20,7 @@ import sys
 
 import torch
 
-__version__ = "0.2.0+b200.r1"
+__version__ = "0.2.0+b200.r2"
 
 # --- torch_sparse: the real package if present, the compat shim otherwise -------------
 try:  # /root/reference/isplib/__init__.py:6-8 imports it unconditionally
@@ -76,6 +76,9 @@ class iSpLibPlugin:
     # csrc/fusedmm.cpp:147-150 does; 'zero': torch_sparse's convention (what PyG's aggr='max'
     # expects for isolated nodes).  arg_out is the nnz sentinel in both.
     empty_row_mode = "reference"
+    # isplib_b200.nn layers fuse their epilogues (bias, ReLU, GIN's self term) into the SpMM while
+    # the plugin is patched in; False keeps them as separate torch ops (A/B and debugging)
+    fuse_epilogues = True
 
     @classmethod
     def set_empty_row_mode(cls, mode: str):
@@ -158,6 +161,31 @@ class iSpLibPlugin:
         return len(cls.backup) > 0
 
 
+def fused_matmul(src, other, reduce: str = "sum", bias=None, addend=None, addend_scale: float = 1.0,
+                 relu: bool = False):
+    """``relu?(matmul(src, other, reduce) + addend_scale * addend + bias)`` in ONE kernel: what the
+    reference's callers do to the SpMM result in separate [M, K] passes -- GCNConv's bias + ReLU
+    (/root/reference/tests/cpu/gcn-sparse.py:61-68), GINConv's ``(1 + eps) * x_i + aggr``
+    (gin-sparse.py:73-78; pass ``addend=other``) -- fused into the kernel's final store
+    (``isplib_b200_spmm_csr_fused``).  sum / add / mean; differentiable w.r.t. other, value, bias,
+    addend.  CUDA tensors only, like every op of this package."""
+    if not _is_sparse_tensor(src):
+        raise TypeError("isplib: expected a torch_sparse.SparseTensor")
+    rowptr, col, value = src.csr()
+    if value is not None:
+        value = value.to(other.dtype)
+    return torch.ops.isplib.fusedmm_spmm_fused(rowptr, col, value, other, reduce, bias, addend,
+                                               float(addend_scale), bool(relu))
+
+
+def pad_features(x: torch.Tensor) -> torch.Tensor:
+    """A ``[N, K]`` view of a zero-padded ``[N, roundup8(K)]`` copy of ``x``: rows start 32-byte
+    aligned, so the kernels gather them in place with 16/32-byte loads instead of re-padding on every
+    call.  The B200 counterpart of the reference's ``pad_features``
+    (/root/reference/tests/cpu/dataset_loader.py:145-160), except that the model still sees K columns."""
+    return torch.ops.isplib._b200_pad_features(x)
+
+
 def isplib_autotune(fn):
     """patch -> call -> unpatch (isplib/__init__.py:204-210); unlike the reference the
     unpatch also happens when ``fn`` raises."""
@@ -172,4 +200,4 @@ def isplib_autotune(fn):
 
 
 __all__ = ["iSpLibPlugin", "isplib_autotune", "SparseTensor", "matmul", "torch", "torch_sparse",
-           "__version__"]
+           "__version__"]   # the reference's surface; fused_matmul / pad_features are reached as isplib_b200.*

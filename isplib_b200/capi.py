@@ -21,13 +21,15 @@ SUM, MAX, MIN, MEAN = 0, 1, 2, 3
 REDUCE_CODE = {"sum": SUM, "add": SUM, "max": MAX, "min": MIN, "mean": MEAN}
 FLAG_ACCUMULATE = 0x1
 FLAG_EMPTY_ZERO = 0x2
+FLAG_RELU = 0x4
 VARIANT_AUTO = -1
 
 # every symbol include/isplib_b200.h declares (checked by tests/test_abi.py)
 EXPORTS = [
     "isplib_b200_abi_version", "isplib_b200_status_string",
     "isplib_b200_plan_bytes", "isplib_b200_plan_build", "isplib_b200_spmm_workspace_bytes",
-    "isplib_b200_spmm_csr", "isplib_b200_spmm_csr_ex",
+    "isplib_b200_spmm_csr", "isplib_b200_spmm_csr_ex", "isplib_b200_spmm_csr_fused",
+    "isplib_b200_spmm_arg_backward_aux",
     "isplib_b200_variant_count", "isplib_b200_variant_name", "isplib_b200_variant_supported",
     "isplib_b200_variant_default", "isplib_b200_spmm_autotune",
     "isplib_b200_csr_transpose_workspace_bytes", "isplib_b200_csr_transpose",
@@ -44,6 +46,15 @@ class PlanInfo(ctypes.Structure):
         ("num_items", ctypes.c_int64), ("num_split_rows", ctypes.c_int64),
         ("num_split_items", ctypes.c_int64), ("max_degree", ctypes.c_int64),
         ("num_empty_rows", ctypes.c_int64), ("plan_bytes", ctypes.c_uint64),
+    ]
+
+
+class Epilogue(ctypes.Structure):
+    """isplib_b200_epilogue (include/isplib_b200.h)."""
+    _fields_ = [
+        ("bias", ctypes.c_void_p), ("addend", ctypes.c_void_p), ("ld_addend", ctypes.c_int64),
+        ("addend_scale", ctypes.c_float), ("reserved", ctypes.c_int32),
+        ("arg_col", ctypes.c_void_p), ("arg_val", ctypes.c_void_p),
     ]
 
 
@@ -70,6 +81,8 @@ def lib() -> ctypes.CDLL:
     spmm_args = [ctypes.c_int, i64, i64, i64, i64, p, p, p, p, i64, p, i64, p, pinfo, p, p, sz]
     L.isplib_b200_spmm_csr.argtypes = spmm_args + [ctypes.c_int, p]
     L.isplib_b200_spmm_csr_ex.argtypes = spmm_args + [ctypes.c_int, ctypes.c_int, p, p, i64, p]
+    L.isplib_b200_spmm_csr_fused.argtypes = spmm_args + [ctypes.c_int, ctypes.c_int, p, p, i64, ctypes.POINTER(Epilogue), p]
+    L.isplib_b200_spmm_arg_backward_aux.argtypes = [i64, i64, i64, p, p, i64, p, i64, p, i64, ctypes.c_int, p]
     L.isplib_b200_variant_count.restype = ctypes.c_int
     L.isplib_b200_variant_name.restype = ctypes.c_char_p
     L.isplib_b200_variant_name.argtypes = [ctypes.c_int]
@@ -150,8 +163,12 @@ def variant_names():
 
 def spmm_csr(reduce, rowptr32, col32, val, x, plan: Plan, variant: int = VARIANT_AUTO, *,
              out=None, arg_out=None, flags: int = 0, row_divisor=None, edge_ids=None,
-             arg_sentinel: Optional[int] = None) -> Tuple[torch.Tensor, Optional[torch.Tensor]]:
-    """out[, arg_out] = REDUCE(A, x) through isplib_b200_spmm_csr(_ex)."""
+             arg_sentinel: Optional[int] = None, bias=None, addend=None, addend_scale: float = 1.0,
+             relu: bool = False, arg_col=None, arg_val=None) -> Tuple[torch.Tensor, Optional[torch.Tensor]]:
+    """out[, arg_out] = REDUCE(A, x) through isplib_b200_spmm_csr(_ex / _fused).
+
+    bias [K], addend [M,K] (x addend_scale), relu: the fused caller epilogue; arg_col / arg_val
+    ([M,K] int32 / fp32, contiguous like out): the auxiliary max/min outputs for the backward."""
     code = REDUCE_CODE[reduce] if isinstance(reduce, str) else int(reduce)
     assert x.is_cuda and x.dtype == torch.float32 and x.dim() == 2 and x.stride(1) == 1
     M, nnz = plan.m, plan.nnz
@@ -171,7 +188,24 @@ def spmm_csr(reduce, rowptr32, col32, val, x, plan: Plan, variant: int = VARIANT
     ldo = out.stride(0) if M > 1 else max(K, out.stride(0))
     common = (code, M, N, K, nnz, _p(rowptr32), _p(col32), _p(val), _p(x), ldx, _p(out), ldo,
               _p(arg_out) if is_arg else None, ctypes.byref(plan.info), plan.ptr, _aligned_ptr(ws), ws_bytes.value)
-    if flags or row_divisor is not None or edge_ids is not None or arg_sentinel is not None:
+    if bias is not None or addend is not None or relu or arg_col is not None:
+        epi = Epilogue()
+        epi.bias = None if bias is None else bias.data_ptr()
+        if addend is not None:
+            assert addend.is_cuda and addend.dtype == torch.float32 and addend.stride(1) == 1
+            epi.addend = addend.data_ptr()
+            epi.ld_addend = addend.stride(0) if addend.size(0) > 1 else max(K, addend.stride(0))
+            epi.addend_scale = float(addend_scale)
+        if arg_col is not None:
+            assert arg_col.dtype == torch.int32 and (M <= 1 or arg_col.stride(0) == ldo)
+            epi.arg_col = arg_col.data_ptr()
+            if arg_val is not None:
+                assert arg_val.dtype == torch.float32 and (M <= 1 or arg_val.stride(0) == ldo)
+                epi.arg_val = arg_val.data_ptr()
+        st = lib().isplib_b200_spmm_csr_fused(*common, variant, flags | (FLAG_RELU if relu else 0), _p(row_divisor),
+                                              _p(edge_ids), nnz if arg_sentinel is None else int(arg_sentinel),
+                                              ctypes.byref(epi), _stream(x.device))
+    elif flags or row_divisor is not None or edge_ids is not None or arg_sentinel is not None:
         st = lib().isplib_b200_spmm_csr_ex(*common, variant, flags, _p(row_divisor), _p(edge_ids),
                                            nnz if arg_sentinel is None else int(arg_sentinel), _stream(x.device))
     else:
@@ -238,6 +272,17 @@ def spmm_arg_backward(col32, val, x, arg, grad_out, n: int, need_grad_x=True, ne
                                               _p(grad_out), grad_out.stride(0), _p(gx), K, _p(gv), 1, _stream(dev)),
           "spmm_arg_backward")
     return gx, gv
+
+
+def spmm_arg_backward_aux(arg_col, arg_val, grad_out, n: int):
+    """grad_x from the forward's auxiliary outputs -- isplib_b200_spmm_arg_backward_aux."""
+    M, K = grad_out.shape
+    dev = grad_out.device
+    gx = torch.empty((n, K), dtype=torch.float32, device=dev)
+    check(lib().isplib_b200_spmm_arg_backward_aux(M, n, K, _p(arg_col), _p(arg_val), arg_col.stride(0) if M > 1 else K,
+                                                  _p(grad_out), grad_out.stride(0) if M > 1 else K, _p(gx), K, 1,
+                                                  _stream(dev)), "spmm_arg_backward_aux")
+    return gx
 
 
 def narrow_i64_to_i32(src: torch.Tensor) -> torch.Tensor:

@@ -114,6 +114,31 @@ static int fill_params(SpmmParams& p, int reduce, int64_t m, int64_t n, int64_t 
     p.tile_base = 0;
     p.flags = flags;
     p.div_mode = row_divisor ? 2 : (reduce == ISPLIB_REDUCE_MEAN ? 1 : 0);
+    p.bias = nullptr;
+    p.addend = nullptr;
+    p.ld_addend = 0;
+    p.addend_scale = 0.f;
+    p.has_epilogue = (flags & ISPLIB_FLAG_RELU) ? 1 : 0;
+    p.arg_col = nullptr;
+    p.arg_val = nullptr;
+    return ISPLIB_SUCCESS;
+}
+
+// fused caller epilogue + auxiliary max/min outputs (isplib_b200_epilogue)
+static int apply_epilogue_args(SpmmParams& p, int reduce, int64_t k, int flags, const isplib_b200_epilogue* epi) {
+    if (!epi) return ISPLIB_SUCCESS;
+    const bool is_arg = (reduce == ISPLIB_REDUCE_MAX || reduce == ISPLIB_REDUCE_MIN);
+    if (epi->addend && epi->ld_addend < k) return ISPLIB_INVALID_ARG;
+    if ((epi->arg_col || epi->arg_val) && !is_arg) return ISPLIB_INVALID_ARG;
+    if (epi->arg_val && !epi->arg_col) return ISPLIB_INVALID_ARG;
+    if (epi->arg_col && (flags & ISPLIB_FLAG_ACCUMULATE)) return ISPLIB_INVALID_ARG;
+    p.bias = epi->bias;
+    p.addend = epi->addend;
+    p.ld_addend = epi->ld_addend;
+    p.addend_scale = epi->addend_scale;
+    if (epi->bias || epi->addend) p.has_epilogue = 1;
+    p.arg_col = epi->arg_col;
+    p.arg_val = epi->arg_val;
     return ISPLIB_SUCCESS;
 }
 
@@ -126,11 +151,26 @@ extern "C" int isplib_b200_spmm_csr_ex(int reduce, int64_t m, int64_t n, int64_t
                                        int variant, int flags, const float* row_divisor,
                                        const int32_t* edge_ids, int64_t arg_sentinel,
                                        isplib_stream_t stream) {
+    return isplib_b200_spmm_csr_fused(reduce, m, n, k, nnz, rowptr, col, val, x, ldx, out, ldo, arg_out, info,
+                                      plan_dev, workspace, workspace_bytes, variant, flags, row_divisor, edge_ids,
+                                      arg_sentinel, nullptr, stream);
+}
+
+extern "C" int isplib_b200_spmm_csr_fused(int reduce, int64_t m, int64_t n, int64_t k, int64_t nnz,
+                                          const int32_t* rowptr, const int32_t* col, const float* val,
+                                          const float* x, int64_t ldx, float* out, int64_t ldo,
+                                          int64_t* arg_out,
+                                          const isplib_b200_plan_info* info, const void* plan_dev,
+                                          void* workspace, size_t workspace_bytes,
+                                          int variant, int flags, const float* row_divisor,
+                                          const int32_t* edge_ids, int64_t arg_sentinel,
+                                          const isplib_b200_epilogue* epi, isplib_stream_t stream) {
     SpmmParams p;
     int st = fill_params(p, reduce, m, n, k, nnz, rowptr, col, val, x, ldx, out, ldo, arg_out, info,
                          plan_dev, workspace, workspace_bytes, flags, row_divisor, edge_ids, arg_sentinel);
     if (st) return st;
     if (m == 0 || k == 0) return ISPLIB_SUCCESS;
+    if ((st = apply_epilogue_args(p, reduce, k, flags, epi))) return st;
     if (variant == ISPLIB_VARIANT_AUTO)
         variant = spmm_variant_default(reduce, n, k, ldx, ldo, x, out, m > 0 ? (double)nnz / (double)m : 0.0);
     if (!spmm_variant_supported(variant, reduce, k, ldx, ldo, x, out)) return ISPLIB_NO_OPT_IMPL;
@@ -192,9 +232,8 @@ extern "C" int isplib_b200_spmm_autotune(int reduce, int64_t m, int64_t n, int64
         // lean 16-byte body, untiled only: on par with lean256 for sum (and the one that runs on rows that
         // are only 16-byte aligned, K = 100: +8 %); for max/min up to +9 % over seg/* (K=64)
         if (d->method == 6 && !tune_all && d->kt != 0) continue;
-        // lean max/min: never ahead of seg/* while x is L2-resident (r1_kbench_lean256)
-        if (d->method == 5 && (reduce == ISPLIB_REDUCE_MAX || reduce == ISPLIB_REDUCE_MIN) && !tune_all &&
-            !(hbm_regime && d->kt == 0)) continue;
+        // lean max/min: since the step-id arg tracking (FMUL + FMNMX per element instead of FMUL, FSETP
+        // and two selects) the lean bodies are candidates in every regime, like for sum
         rc = launch_spmm(reduce, p, nnz, v, stream);  // warm-up
         if (rc) break;
         cudaEventRecord(e0, stream);

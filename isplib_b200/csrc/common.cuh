@@ -104,6 +104,14 @@ struct SpmmParams {
     int vec_store;  // 1: out (and arg_out) rows take aligned 16-byte stores
     int flags;      // ISPLIB_FLAG_*
     int div_mode;   // 0 none, 1 by max(deg,1), 2 by row_div[]
+    // fused caller epilogue + auxiliary max/min outputs (isplib_b200_epilogue)
+    const float* __restrict__ bias;     // [k] or null
+    const float* __restrict__ addend;   // [m, k], row stride ld_addend, or null
+    long long ld_addend;
+    float addend_scale;
+    int has_epilogue;                   // bias || addend || ISPLIB_FLAG_RELU
+    int32_t* __restrict__ arg_col;      // [m, k] stride ldo or null: col[arg] (-1 where no entry won)
+    float* __restrict__ arg_val;        // [m, k] stride ldo or null: val[arg]
 };
 
 enum Op { OP_SUM = 0, OP_MAX = 1, OP_MIN = 2 };

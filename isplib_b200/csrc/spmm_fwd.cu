@@ -92,12 +92,12 @@ SegKernel seg_kernel_min(const TileShape&, int, bool);
 SegKernel bulk_kernel_sum(const TileShape&, int);
 SegKernel bulk_kernel_max(const TileShape&, int);
 SegKernel bulk_kernel_min(const TileShape&, int);
-SegKernel lean256_kernel_sum(int g, bool ragged);
-SegKernel lean256_kernel_max(int g, bool ragged);
-SegKernel lean256_kernel_min(int g, bool ragged);
-SegKernel lean128_kernel_sum(int g, bool ragged);
-SegKernel lean128_kernel_max(int g, bool ragged);
-SegKernel lean128_kernel_min(int g, bool ragged);
+SegKernel lean256_kernel_sum(int g, bool ragged, bool noval);
+SegKernel lean256_kernel_max(int g, bool ragged, bool noval);
+SegKernel lean256_kernel_min(int g, bool ragged, bool noval);
+SegKernel lean128_kernel_sum(int g, bool ragged, bool noval);
+SegKernel lean128_kernel_max(int g, bool ragged, bool noval);
+SegKernel lean128_kernel_min(int g, bool ragged, bool noval);
 
 static bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15u) == 0; }
 
@@ -265,12 +265,14 @@ int launch_spmm(int reduce, const SpmmParams& base, int64_t nnz, int variant, cu
     size_t smem = 0;
     if (d->method == 5) {
         const bool ragged = (t.g * 8 != t.tile_w);
-        kern = op == OP_SUM ? lean256_kernel_sum(t.g, ragged)
-                            : (op == OP_MAX ? lean256_kernel_max(t.g, ragged) : lean256_kernel_min(t.g, ragged));
+        const bool noval = (p.val == nullptr);
+        kern = op == OP_SUM ? lean256_kernel_sum(t.g, ragged, noval)
+                            : (op == OP_MAX ? lean256_kernel_max(t.g, ragged, noval) : lean256_kernel_min(t.g, ragged, noval));
     } else if (d->method == 6) {
         const bool ragged = (t.g * 4 != t.tile_w);
-        kern = op == OP_SUM ? lean128_kernel_sum(t.g, ragged)
-                            : (op == OP_MAX ? lean128_kernel_max(t.g, ragged) : lean128_kernel_min(t.g, ragged));
+        const bool noval = (p.val == nullptr);
+        kern = op == OP_SUM ? lean128_kernel_sum(t.g, ragged, noval)
+                            : (op == OP_MAX ? lean128_kernel_max(t.g, ragged, noval) : lean128_kernel_min(t.g, ragged, noval));
     } else if (d->method == 1) {
         if (op == OP_SUM) kern = bulk_kernel_sum(t, d->unroll);
         else if (op == OP_MAX) kern = bulk_kernel_max(t, d->unroll);

@@ -121,6 +121,27 @@ __device__ __forceinline__ bool better_lex(float cand, IdT cand_id, float cur, I
 // finalisation of one vector of one output row: single-segment rows directly, split rows by
 // the last-arriving segment warp after the in-order merge
 // ------------------------------------------------------------------------------------
+// fused caller epilogue, applied to the finished row vector:
+//   out = relu( out + addend_scale * addend[row, :] + bias[:] )
+// GCN: + bias, ReLU (tests/cpu/gcn-sparse.py:61-68); GIN: (1 + eps) * x_i + sum_j x_j
+// (gin-sparse.py:73-78) with addend = x; every part optional.
+template <int VEC>
+__device__ __forceinline__ void apply_epilogue(const SpmmParams& p, int row, int kk, int nvalid, float (&acc)[VEC]) {
+    if (p.addend) {
+        const float* a = p.addend + (size_t)row * (size_t)p.ld_addend + kk;
+#pragma unroll
+        for (int v = 0; v < VEC; ++v) if (v < nvalid) acc[v] = fmaf(p.addend_scale, __ldg(a + v), acc[v]);
+    }
+    if (p.bias) {
+#pragma unroll
+        for (int v = 0; v < VEC; ++v) if (v < nvalid) acc[v] += __ldg(p.bias + kk + v);
+    }
+    if (p.flags & ISPLIB_FLAG_RELU) {
+#pragma unroll
+        for (int v = 0; v < VEC; ++v) acc[v] = fmaxf(acc[v], 0.f);
+    }
+}
+
 template <int OP, int VEC>
 __device__ __forceinline__ void finalize_store(const SpmmParams& p, int row, int deg, int kk,
                                                float (&acc)[VEC], int (&arg)[VEC]) {
@@ -150,6 +171,7 @@ __device__ __forceinline__ void finalize_store(const SpmmParams& p, int row, int
 #pragma unroll
             for (int v = 0; v < VEC; ++v) acc[v] = __fdiv_rn(acc[v], d);
         }
+        if (p.has_epilogue) apply_epilogue<VEC>(p, row, kk, nvalid, acc);
         if (vec_ok) {
             store_vec_f<VEC>(p.out + o, acc);
         } else {
@@ -169,15 +191,44 @@ __device__ __forceinline__ void finalize_store(const SpmmParams& p, int row, int
                 if (v < nvalid) {
                     const float pv = p.out[o + v];
                     const long long pa = p.arg_out[o + v];
-                    // previous block wins unless ours is strictly better / equal with smaller id
-                    if (!better_lex<OP, long long>(acc[v], gid[v], pv, pa)) { acc[v] = pv; gid[v] = pa; }
+                    // a previous block that found no entry (sentinel) holds no candidate: ours is
+                    // taken as is (its stored value may be the EMPTY_ZERO placeholder, not a product);
+                    // otherwise the previous block wins unless ours is strictly better / equal with
+                    // a smaller edge id
+                    if (pa != p.arg_sentinel && !better_lex<OP, long long>(acc[v], gid[v], pv, pa)) { acc[v] = pv; gid[v] = pa; }
                 }
+            }
+        }
+        if (p.arg_col) {
+            // the winner's column (and value) for the backward scatter, so that it reads two
+            // coalesced 4-byte streams instead of gathering col[arg] / val[arg] by 32-byte sectors
+            // (csrc/fusedmm.cpp:432-441 does the same gathers with index_select)
+            int cw[VEC];
+            float aw[VEC];
+#pragma unroll
+            for (int v = 0; v < VEC; ++v) {
+                const bool has = (arg[v] != kNoArg);
+                cw[v] = has ? __ldg(p.col + arg[v]) : -1;
+                aw[v] = (has && p.val) ? __ldg(p.val + arg[v]) : 1.f;
+            }
+            if (VEC >= 4 && vec_ok) {
+#pragma unroll
+                for (int q = 0; q < VEC / 4; ++q) {
+                    __stcs(reinterpret_cast<int4*>(p.arg_col + o) + q, make_int4(cw[(4 * q) % VEC], cw[(4 * q + 1) % VEC], cw[(4 * q + 2) % VEC], cw[(4 * q + 3) % VEC]));
+                    if (p.arg_val)
+                        __stcs(reinterpret_cast<float4*>(p.arg_val + o) + q, make_float4(aw[(4 * q) % VEC], aw[(4 * q + 1) % VEC], aw[(4 * q + 2) % VEC], aw[(4 * q + 3) % VEC]));
+                }
+            } else {
+#pragma unroll
+                for (int v = 0; v < VEC; ++v)
+                    if (v < nvalid) { __stcs(p.arg_col + o + v, cw[v]); if (p.arg_val) __stcs(p.arg_val + o + v, aw[v]); }
             }
         }
         if (p.flags & ISPLIB_FLAG_EMPTY_ZERO) {
 #pragma unroll
             for (int v = 0; v < VEC; ++v) if (gid[v] == p.arg_sentinel) acc[v] = 0.f;
         }
+        if (p.has_epilogue) apply_epilogue<VEC>(p, row, kk, nvalid, acc);
         if (vec_ok) {
             store_vec_f<VEC>(p.out + o, acc);
             store_vec_i64<VEC>(p.arg_out + o, gid);
@@ -622,7 +673,55 @@ spmm_bulk_kernel(const __grid_constant__ SpmmParams p) {
 // 0, so no extra traffic) and keeps them out of the stores.  max/min carry VEC more registers
 // (arg): 80 with VEC = 8 (24 warps/SM), 56 with VEC = 4 (36 warps/SM).
 // ------------------------------------------------------------------------------------
-template <int OP, int VEC, int G, bool RAGGED>
+template <int OP> __device__ __forceinline__ float pick2(float a, float b) {
+    // NaN-dropping max / min (FMNMX): a NaN product never wins, like the strict compare of the oracle
+    return OP == OP_MAX ? fmaxf(a, b) : fminf(a, b);
+}
+
+// max / min in the lean body (the r1 body spent 4 instructions per gathered element: FMUL,
+// FSETP, 2 selects, and was issue-bound in the L2 regime).  Here the U entries of a step are
+// folded with FMUL + FMNMX only, and ONE compare + 2 selects per accumulator and step record the
+// step (its first entry id) in which the running extremum strictly improved.  `resolve_step_winner`
+// then re-reads the <= U entries of that one step per accumulator and takes the first whose product
+// equals the extremum -- the smallest edge id, and that entry's own product bit for bit (so the
+// -0.0 / +0.0 tie of the oracle's strict scan is reproduced too).  NOVAL: val == NULL (SAGE / GIN
+// drop the values), no multiply and no value shuffle at all.
+template <int OP, int VEC, int NG, int U, bool NOVAL>
+__device__ __forceinline__ void resolve_step_winner(const SpmmParams& p, const char* xlane, unsigned ldxb, int ee,
+                                                    float (&acc)[VEC], int (&arg)[VEC]) {
+#pragma unroll
+    for (int v = 0; v < VEC; ++v) {
+        const int base = arg[v];
+        if (base == kNoArg) continue;
+        float tt[U];
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+            const int e = base + u * NG;
+            if (u == 0 || e < ee) {
+                const unsigned cc = (unsigned)__ldg(p.col + e);
+                const float xx = __ldg(reinterpret_cast<const float*>(xlane + (unsigned long long)cc * ldxb) + v);
+                tt[u] = NOVAL ? xx : __fmul_rn(__ldg(p.val + e), xx);
+            } else {
+                tt[u] = OP == OP_MAX ? -INFINITY : INFINITY;   // never equal to a finite extremum
+            }
+        }
+        const float m = acc[v];
+        int win = base;
+        float wv = tt[0];
+        // first u whose product equals the extremum (u = 0 always does for exactly tracked entries)
+        bool found = (tt[0] == m);
+#pragma unroll
+        for (int u = 1; u < U; ++u) {
+            const bool hit = !found && (tt[u] == m);
+            if (hit) { win = base + u * NG; wv = tt[u]; }
+            found = found || hit;
+        }
+        arg[v] = win;
+        acc[v] = wv;
+    }
+}
+
+template <int OP, int VEC, int G, bool RAGGED, bool NOVAL>
 __global__ void __launch_bounds__(128, VEC == 8 ? (OP == OP_SUM ? 8 : 6) : (OP == OP_SUM ? 10 : 9))
 spmm_lean_kernel(const __grid_constant__ SpmmParams p) {
     constexpr int U = 4;
@@ -638,7 +737,7 @@ spmm_lean_kernel(const __grid_constant__ SpmmParams p) {
     const int k0 = (blockIdx.y + p.tile_base) * p.tile_w + (lane_ok ? (lane % G) * VEC : 0);
     const char* const xlane = reinterpret_cast<const char*>(p.x + k0);
     const unsigned ldxb = (unsigned)p.ldx * 4u;
-    const bool has_val = (p.val != nullptr);
+    const bool has_val = !NOVAL && (p.val != nullptr);
 
     float acc[1][VEC];
     int arg[1][VEC];
@@ -679,18 +778,29 @@ spmm_lean_kernel(const __grid_constant__ SpmmParams p) {
                     const unsigned cc = __shfl_sync(FULL, c, t + u * NG + g);
                     load_vec<VEC>(reinterpret_cast<const float*>(xlane + (unsigned long long)cc * ldxb), xv[u]);
                 }
+                if constexpr (OP == OP_SUM) {
 #pragma unroll
-                for (int u = 0; u < U; ++u) {
-                    const float aa = __shfl_sync(FULL, a, t + u * NG + g);
+                    for (int u = 0; u < U; ++u) {
+                        const float aa = __shfl_sync(FULL, a, t + u * NG + g);
 #pragma unroll
-                    for (int v = 0; v < VEC; ++v) {
-                        if constexpr (OP == OP_SUM) {
-                            acc[0][v] = fmaf(aa, xv[u][v], acc[0][v]);
-                        } else {
-                            const float tt = __fmul_rn(aa, xv[u][v]);
-                            if (better<OP>(tt, acc[0][v])) { acc[0][v] = tt; arg[0][v] = e0 + t + u * NG + g; }
+                        for (int v = 0; v < VEC; ++v) acc[0][v] = fmaf(aa, xv[u][v], acc[0][v]);
+                    }
+                } else {
+                    float m[VEC];
+#pragma unroll
+                    for (int u = 0; u < U; ++u) {
+                        float aa = 1.f;
+                        if constexpr (!NOVAL) aa = __shfl_sync(FULL, a, t + u * NG + g);
+#pragma unroll
+                        for (int v = 0; v < VEC; ++v) {
+                            const float tt = NOVAL ? xv[u][v] : __fmul_rn(aa, xv[u][v]);
+                            m[v] = (u == 0) ? tt : pick2<OP>(m[v], tt);
                         }
                     }
+                    const int base = e0 + t + g;   // first entry of this lane group's step
+#pragma unroll
+                    for (int v = 0; v < VEC; ++v)
+                        if (better<OP>(m[v], acc[0][v])) { acc[0][v] = m[v]; arg[0][v] = base; }
                 }
             }
         } else {
@@ -699,7 +809,8 @@ spmm_lean_kernel(const __grid_constant__ SpmmParams p) {
             for (int t = 0; t < cnt; t += NG) {
                 const int idx = t + g;
                 const unsigned cc = __shfl_sync(FULL, c, idx & 31);
-                const float aa = __shfl_sync(FULL, a, idx & 31);
+                float aa = 1.f;
+                if constexpr (!NOVAL) aa = __shfl_sync(FULL, a, idx & 31);
                 if (idx < cnt) {
                     float xv[VEC];
                     load_vec<VEC>(reinterpret_cast<const float*>(xlane + (unsigned long long)cc * ldxb), xv);
@@ -708,7 +819,8 @@ spmm_lean_kernel(const __grid_constant__ SpmmParams p) {
                         if constexpr (OP == OP_SUM) {
                             acc[0][v] = fmaf(aa, xv[v], acc[0][v]);
                         } else {
-                            const float tt = __fmul_rn(aa, xv[v]);
+                            const float tt = NOVAL ? xv[v] : __fmul_rn(aa, xv[v]);
+                            // an exactly tracked entry: resolve_step_winner finds it at u = 0
                             if (better<OP>(tt, acc[0][v])) { acc[0][v] = tt; arg[0][v] = e0 + idx; }
                         }
                     }
@@ -716,20 +828,29 @@ spmm_lean_kernel(const __grid_constant__ SpmmParams p) {
             }
         }
     }
+    if constexpr (OP != OP_SUM) resolve_step_winner<OP, VEC, NG, U, NOVAL>(p, xlane, ldxb, ee, acc[0], arg[0]);
     const int koff[1] = {k0};
     const bool kok[1] = {lane_ok};
     finish_item<OP, VEC, G, 1>(p, lane, desc.x, eb, ee, desc.w, koff, kok, acc, arg);
 }
 
-template <int OP, int VEC>
-static inline SegKernel pick_lean(int g, bool ragged) {
+template <int OP, int VEC, bool NOVAL>
+static inline SegKernel pick_lean_g(int g, bool ragged) {
     switch (g) {
-        case 4: return ragged ? spmm_lean_kernel<OP, VEC, 4, true> : spmm_lean_kernel<OP, VEC, 4, false>;
-        case 8: return ragged ? spmm_lean_kernel<OP, VEC, 8, true> : spmm_lean_kernel<OP, VEC, 8, false>;
-        case 16: return ragged ? spmm_lean_kernel<OP, VEC, 16, true> : spmm_lean_kernel<OP, VEC, 16, false>;
-        case 32: return ragged ? spmm_lean_kernel<OP, VEC, 32, true> : spmm_lean_kernel<OP, VEC, 32, false>;
+        case 4: return ragged ? spmm_lean_kernel<OP, VEC, 4, true, NOVAL> : spmm_lean_kernel<OP, VEC, 4, false, NOVAL>;
+        case 8: return ragged ? spmm_lean_kernel<OP, VEC, 8, true, NOVAL> : spmm_lean_kernel<OP, VEC, 8, false, NOVAL>;
+        case 16: return ragged ? spmm_lean_kernel<OP, VEC, 16, true, NOVAL> : spmm_lean_kernel<OP, VEC, 16, false, NOVAL>;
+        case 32: return ragged ? spmm_lean_kernel<OP, VEC, 32, true, NOVAL> : spmm_lean_kernel<OP, VEC, 32, false, NOVAL>;
         default: return nullptr;
     }
+}
+
+template <int OP, int VEC>
+static inline SegKernel pick_lean(int g, bool ragged, bool noval) {
+    if constexpr (OP != OP_SUM) {
+        if (noval) return pick_lean_g<OP, VEC, true>(g, ragged);
+    }
+    return pick_lean_g<OP, VEC, false>(g, ragged);
 }
 
 struct TileShape { int vec, g, lpl, tile_w, ntiles; };

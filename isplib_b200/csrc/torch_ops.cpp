@@ -31,6 +31,7 @@
 #include <mutex>
 #include <tuple>
 #include <unordered_map>
+#include <vector>
 
 #include "../../include/isplib_b200.h"
 
@@ -84,9 +85,31 @@ struct GraphEntry {
     bool has_csc = false;
     CsrView bwd;                 // A^T as CSR: (colptr, row[csr2csc])
     Tensor csr2csc32;
-    // permuted values for the backward, keyed by the identity of the value tensor
-    const void* valt_key = nullptr; uint32_t valt_version = 0; Tensor val_t;
-    const void* meanw_key = nullptr; uint32_t meanw_version = 0; bool meanw_built = false; Tensor mean_w;
+    // permuted values for the backward, keyed by the IDENTITY of the value tensor: a weak
+    // reference to its storage (an address alone is reused by the caching allocator after a
+    // free), the offset into it and the version counter
+    struct TensorId {
+        c10::weak_intrusive_ptr<c10::StorageImpl> storage;
+        const void* ptr = nullptr; int64_t offset = 0, numel = 0; uint32_t version = 0; bool set = false;
+        TensorId() : storage(c10::weak_intrusive_ptr<c10::StorageImpl>(c10::intrusive_ptr<c10::StorageImpl>())) {}
+        void assign(const c10::optional<Tensor>& t) {
+            set = true;
+            if (!t.has_value()) { ptr = nullptr; offset = numel = 0; version = 0;
+                                  storage = c10::weak_intrusive_ptr<c10::StorageImpl>(c10::intrusive_ptr<c10::StorageImpl>()); return; }
+            storage = t->storage().getWeakStorageImpl();
+            ptr = t->data_ptr(); offset = t->storage_offset(); numel = t->numel(); version = t->_version();
+        }
+        bool matches(const c10::optional<Tensor>& t) const {
+            if (!set) return false;
+            if (!t.has_value()) return ptr == nullptr;
+            return ptr == t->data_ptr() && !storage.expired() &&
+                   storage._unsafe_get_target() == t->storage().unsafeGetStorageImpl() &&
+                   offset == t->storage_offset() && numel == t->numel() && version == t->_version();
+        }
+        void reset() { set = false; }
+    };
+    TensorId valt_id; Tensor val_t;
+    TensorId meanw_id; Tensor mean_w;
     // the permuted values are produced asynchronously on whatever stream first needed them;
     // later users on other streams (autograd worker threads) wait on these events
     at::cuda::CUDAEvent valt_ready, meanw_ready;
@@ -139,7 +162,6 @@ std::shared_ptr<GraphEntry> get_graph(const Tensor& rowptr, const Tensor& col) {
     TORCH_CHECK(rowptr.device() == col.device(), "isplib_b200: rowptr and col on different devices");
     GraphKey key{rowptr.data_ptr(), col.data_ptr(), rowptr.numel() - 1, col.numel(), (int)rowptr.get_device()};
     std::shared_ptr<GraphEntry> e;
-    std::unique_lock<std::mutex> build_lk;  // held from insertion until the entry is built
     {
         std::lock_guard<std::mutex> lk(g_cache_mu);
         auto it = g_cache.find(key);
@@ -160,17 +182,24 @@ std::shared_ptr<GraphEntry> get_graph(const Tensor& rowptr, const Tensor& col) {
             if (it2->second->rowptr_storage.expired() || it2->second->col_storage.expired()) it2 = g_cache.erase(it2);
             else ++it2;
         }
-        e = std::make_shared<GraphEntry>(rowptr, col);
-        e->rowptr_version = rowptr._version();
-        e->col_version = col._version();
-        build_lk = std::unique_lock<std::mutex>(e->mu);
-        g_cache.emplace(key, e);
     }
+    // Build OUTSIDE the cache (and its lock): if narrowing or the plan build throws (an index
+    // that does not fit int32, an ISPLIB status, an OOM) nothing half-built is ever visible, and
+    // the next call raises the same clean error again.  Two threads racing on a new graph both
+    // build; the first insertion wins.
+    e = std::make_shared<GraphEntry>(rowptr, col);
+    e->rowptr_version = rowptr._version();
+    e->col_version = col._version();
     e->fwd.m = key.m;
     e->fwd.nnz = key.nnz;
     e->fwd.rowptr32 = to_i32(rowptr);
     e->fwd.col32 = to_i32(col);
     e->fwd.build_plan(env_int("ISPLIB_B200_SEG_LEN", 0));
+    {
+        std::lock_guard<std::mutex> lk(g_cache_mu);
+        auto ins = g_cache.emplace(key, e);
+        if (!ins.second) e = ins.first->second;
+    }
     return e;
 }
 
@@ -197,14 +226,12 @@ void ensure_csc(GraphEntry& e, int64_t n) {
     e.bwd.tuned.clear();
     e.bwd.build_plan(env_int("ISPLIB_B200_SEG_LEN", 0));
     e.has_csc = true;
-    e.valt_key = nullptr;
-    e.meanw_built = false;
+    e.valt_id.reset();
+    e.meanw_id.reset();
 }
 
 Tensor permuted_values(GraphEntry& e, const c10::optional<Tensor>& value, bool mean_weights) {
     auto stream = at::cuda::getCurrentCUDAStream();
-    const void* key = value.has_value() ? value->data_ptr() : nullptr;
-    const uint32_t ver = value.has_value() ? value->_version() : 0;
     auto reuse = [&](Tensor& t, at::cuda::CUDAEvent& ready) {
         // produced on another stream?  (no cross-stream wait while capturing a CUDA graph: the
         // producer finished long before, during the warm-up the capture contract requires)
@@ -214,8 +241,8 @@ Tensor permuted_values(GraphEntry& e, const c10::optional<Tensor>& value, bool m
     };
     if (!mean_weights) {
         if (!value.has_value()) return Tensor();  // implicit ones stay implicit
-        if (e.valt_key == key && e.valt_version == ver && e.val_t.defined()) return reuse(e.val_t, e.valt_ready);
-    } else if (e.meanw_built && e.meanw_key == key && e.meanw_version == ver) {
+        if (e.valt_id.matches(value) && e.val_t.defined()) return reuse(e.val_t, e.valt_ready);
+    } else if (e.meanw_id.matches(value) && e.mean_w.defined()) {
         return reuse(e.mean_w, e.meanw_ready);
     }
     Tensor out = torch::empty({e.fwd.nnz}, e.fwd.rowptr32.options().dtype(torch::kFloat32));
@@ -223,34 +250,104 @@ Tensor permuted_values(GraphEntry& e, const c10::optional<Tensor>& value, bool m
         e.fwd.nnz, value.has_value() ? value->data_ptr<float>() : nullptr, e.csr2csc32.data_ptr<int32_t>(),
         e.bwd.col32.data_ptr<int32_t>(), e.fwd.rowptr32.data_ptr<int32_t>(), mean_weights ? 1 : 0,
         out.data_ptr<float>(), stream.stream()));
-    if (!mean_weights) { e.valt_key = key; e.valt_version = ver; e.val_t = out; e.valt_ready.record(stream); }
-    else { e.meanw_key = key; e.meanw_version = ver; e.mean_w = out; e.meanw_built = true; e.meanw_ready.record(stream); }
+    if (!mean_weights) { e.valt_id.assign(value); e.val_t = out; e.valt_ready.record(stream); }
+    else { e.meanw_id.assign(value); e.mean_w = out; e.meanw_ready.record(stream); }
     return out;
+}
+
+// ---------------------------------------------------------------------------------------
+// the dense operand as the kernels want it
+// ---------------------------------------------------------------------------------------
+// Rows with unit inner stride.  Feature widths that are not a multiple of 8 floats (47, 100,
+// 602 ...) get rows that start 32-byte aligned and own their padding up to the next multiple of
+// 8, so the kernels gather with 16- and 32-byte loads (the reference pads features to multiples
+// of 16 for its SIMD kernels, tests/cpu/dataset_loader.py:145-160).  Three ways to get there,
+// cheapest first:
+//   1. the caller already hands over such a view (x = buf[:, :K] of a [N, roundup8(K)] buffer --
+//      isplib_b200.pad_features(), or a layer that writes its activations into a padded buffer):
+//      used in place, nothing is copied;
+//   2. the same tensor was padded by an earlier call and has not been written since (dataset
+//      features that are aggregated every epoch): the cached padded copy is reused;
+//   3. one constant_pad_nd pass (read N*K, write N*Kp), remembered for case 2 when the tensor
+//      does not require grad (activations change every step; caching them would only pin memory).
+struct DenseOperand { Tensor t; int64_t ld; };
+
+struct PadCacheEntry { GraphEntry::TensorId id; Tensor padded; };
+std::mutex& g_pad_mu = *new std::mutex();
+std::vector<PadCacheEntry>& g_pad_cache = *new std::vector<PadCacheEntry>();   // leaked like g_cache
+constexpr size_t kPadCacheEntries = 4;
+
+bool rows_usable_in_place(const Tensor& m, int64_t need_cols) {
+    const int64_t N = m.size(0), K = m.size(1);
+    if (K > 1 && m.stride(1) != 1) return false;
+    const int64_t ld = N > 1 ? m.stride(0) : std::max<int64_t>(need_cols, K);
+    if (ld < need_cols) return false;
+    if (need_cols > K) {
+        // the padding of the LAST row must lie inside the storage too
+        const int64_t last = m.storage_offset() + (N > 0 ? (N - 1) * ld : 0) + need_cols;
+        if ((size_t)last * sizeof(float) > m.storage().nbytes()) return false;
+    }
+    return true;
+}
+
+DenseOperand dense_operand(const Tensor& mat_in, bool cacheable) {
+    const int64_t N = mat_in.size(0), K = mat_in.size(1);
+    const bool want_pad = (K % 8 != 0) && K > 8 && env_int("ISPLIB_B200_PAD_K", 1);
+    const int64_t Kp = want_pad ? (K + 7) / 8 * 8 : K;
+    if (N == 0 || K == 0) return {mat_in.contiguous(), K};
+    if (rows_usable_in_place(mat_in, Kp)) {
+        const int64_t ld = N > 1 ? mat_in.stride(0) : Kp;
+        const bool aligned = !want_pad || (ld % 8 == 0 && (reinterpret_cast<uintptr_t>(mat_in.data_ptr()) & 31u) == 0);
+        if (aligned) return {mat_in, ld};
+    }
+    if (!want_pad) return {mat_in.contiguous(), K};   // csrc/fusedmm.cpp:140
+    const c10::optional<Tensor> key(mat_in);
+    {
+        std::lock_guard<std::mutex> lk(g_pad_mu);
+        for (auto& e : g_pad_cache)
+            if (e.id.matches(key) && e.padded.size(0) == N && e.padded.size(1) == Kp) return {e.padded, Kp};
+    }
+    Tensor padded = at::constant_pad_nd(mat_in, {0, Kp - K}, 0);
+    if (cacheable) {
+        std::lock_guard<std::mutex> lk(g_pad_mu);
+        for (auto it = g_pad_cache.begin(); it != g_pad_cache.end();)
+            it = it->id.storage.expired() ? g_pad_cache.erase(it) : it + 1;
+        if (g_pad_cache.size() >= kPadCacheEntries) g_pad_cache.erase(g_pad_cache.begin());
+        PadCacheEntry e;
+        e.id.assign(key);
+        e.padded = padded;
+        g_pad_cache.push_back(std::move(e));
+    }
+    return {padded, Kp};
 }
 
 // ---------------------------------------------------------------------------------------
 // forward driver: the counterpart of fusedmm_spmm_fw, csrc/fusedmm.cpp:113-203
 // ---------------------------------------------------------------------------------------
-std::tuple<Tensor, c10::optional<Tensor>> spmm_fw(CsrView& g, const c10::optional<Tensor>& value,
-                                                  const Tensor& mat_in, int reduction) {
+struct FwOptions {
+    c10::optional<Tensor> bias, addend;   // fused caller epilogue (isplib_b200_epilogue)
+    double addend_scale = 1.0;
+    bool relu = false;
+    bool want_aux = false;                // max/min: also emit col[arg] (and val[arg]) for the backward
+    bool cache_padded = false;            // `mat` is a constant (dataset features): keep its padded copy
+};
+struct FwResult {
+    Tensor out;
+    c10::optional<Tensor> arg_out;
+    Tensor arg_col, arg_val;              // defined iff want_aux (arg_val only with values)
+};
+
+FwResult spmm_fw(CsrView& g, const c10::optional<Tensor>& value, const Tensor& mat_in, int reduction,
+                 const FwOptions& opt = FwOptions()) {
     TORCH_CHECK(mat_in.is_cuda(), "isplib_b200: `mat` must be a CUDA tensor (no CPU path)");
     TORCH_CHECK(mat_in.scalar_type() == torch::kFloat32, "isplib_b200: `mat` must be float32, got ", mat_in.scalar_type());
     TORCH_CHECK(mat_in.dim() == 2, "isplib_b200: `mat` must be 2-D [N, K] (the reference passes 2-D strides only, "
                                    "csrc/fusedmm.cpp:142-143)");
     TORCH_CHECK(mat_in.get_device() == g.rowptr32.get_device(), "isplib_b200: `mat` and the graph are on different devices");
-    Tensor mat = mat_in.contiguous();  // csrc/fusedmm.cpp:140
+    const DenseOperand X = dense_operand(mat_in.detach(), opt.cache_padded);
+    const Tensor& mat = X.t;
     const int64_t M = g.m, N = mat.size(0), K = mat.size(1);
-    int64_t ldx = K;
-    if (K % 4 != 0 && K > 4 && env_int("ISPLIB_B200_PAD_K", 1)) {
-        // feature widths like 47 or 602: give every row 32-byte alignment and its own padding
-        // so the kernel can gather with 16- and 32-byte loads (the reference pads features to multiples
-        // of 16 for its SIMD kernels, tests/cpu/dataset_loader.py:145-160); out stays [M, K]
-        const int64_t Kp = (K + 7) / 8 * 8;
-        Tensor padded = torch::zeros({N, Kp}, mat.options());
-        padded.narrow(1, 0, K).copy_(mat);
-        mat = padded;
-        ldx = Kp;
-    }
+    const int64_t ldx = X.ld;
     const float* val_ptr = nullptr;
     Tensor val;
     if (value.has_value()) {
@@ -260,20 +357,47 @@ std::tuple<Tensor, c10::optional<Tensor>> spmm_fw(CsrView& g, const c10::optiona
         val_ptr = val.data_ptr<float>();
     }
     const bool is_arg = reduction == ISPLIB_REDUCE_MAX || reduction == ISPLIB_REDUCE_MIN;
-    Tensor out = torch::empty({M, K}, mat.options());
-    c10::optional<Tensor> arg_out = c10::nullopt;
-    if (is_arg) arg_out = torch::empty({M, K}, mat.options().dtype(torch::kInt64));  // csrc/fusedmm.cpp:171
-    if (M == 0 || K == 0) return std::make_tuple(out, arg_out);
+    FwResult r;
+    r.out = torch::empty({M, K}, mat.options());
+    if (is_arg) r.arg_out = torch::empty({M, K}, mat.options().dtype(torch::kInt64));  // csrc/fusedmm.cpp:171
+    if (is_arg && opt.want_aux) {
+        r.arg_col = torch::empty({M, K}, mat.options().dtype(torch::kInt32));
+        if (val_ptr) r.arg_val = torch::empty({M, K}, mat.options());
+    }
+    if (M == 0 || K == 0) return r;
     if (g.nnz > 0) {
         // column indices are trusted like in the reference; only the cheap shape check is made
         TORCH_CHECK(N > 0, "isplib_b200: `mat` has no rows but the graph has entries");
+    }
+
+    isplib_b200_epilogue epi{};
+    Tensor bias_c, addend_c;
+    if (opt.bias.has_value()) {
+        TORCH_CHECK(opt.bias->is_cuda() && opt.bias->scalar_type() == torch::kFloat32 && opt.bias->numel() == K,
+                    "isplib_b200: `bias` must be a CUDA float32 tensor with K elements");
+        bias_c = opt.bias->detach().contiguous();
+        epi.bias = bias_c.data_ptr<float>();
+    }
+    if (opt.addend.has_value()) {
+        TORCH_CHECK(opt.addend->is_cuda() && opt.addend->scalar_type() == torch::kFloat32 && opt.addend->dim() == 2 &&
+                    opt.addend->size(0) >= M && opt.addend->size(1) == K,
+                    "isplib_b200: `addend` must be a CUDA float32 [>= M, K] tensor");
+        addend_c = opt.addend->detach();
+        if (!rows_usable_in_place(addend_c, K)) addend_c = addend_c.contiguous();
+        epi.addend = addend_c.data_ptr<float>();
+        epi.ld_addend = addend_c.size(0) > 1 ? addend_c.stride(0) : K;
+        epi.addend_scale = (float)opt.addend_scale;
+    }
+    if (r.arg_col.defined()) {
+        epi.arg_col = r.arg_col.data_ptr<int32_t>();
+        if (r.arg_val.defined()) epi.arg_val = r.arg_val.data_ptr<float>();
     }
 
     size_t ws = 0;
     ISPLIB_CHECK_STATUS(isplib_b200_spmm_workspace_bytes(&g.info, K, reduction, &ws));
     Tensor wst = torch::empty({(int64_t)ws}, mat.options().dtype(torch::kUInt8));
     auto stream = at::cuda::getCurrentCUDAStream();
-    int64_t* arg_ptr = is_arg ? arg_out->data_ptr<int64_t>() : nullptr;
+    int64_t* arg_ptr = is_arg ? r.arg_out->data_ptr<int64_t>() : nullptr;
 
     int variant = env_int("ISPLIB_B200_VARIANT", ISPLIB_VARIANT_AUTO);
     if (variant == ISPLIB_VARIANT_AUTO) {
@@ -281,39 +405,47 @@ std::tuple<Tensor, c10::optional<Tensor>> spmm_fw(CsrView& g, const c10::optiona
         auto it = g.tuned.find(tkey);
         if (it != g.tuned.end()) {
             variant = it->second;
-        } else if (env_int("ISPLIB_B200_AUTOTUNE", 1) && g.nnz >= (int64_t)env_int("ISPLIB_B200_AUTOTUNE_MIN_NNZ", 1 << 16)) {
+        } else if (env_int("ISPLIB_B200_AUTOTUNE", 1) && g.nnz >= (int64_t)env_int("ISPLIB_B200_AUTOTUNE_MIN_NNZ", 1 << 16) &&
+                   at::cuda::currentStreamCaptureStatus() == at::cuda::CaptureStatus::None) {
             // replaces autotuner/findbestk.py: time the eligible variants on this graph, once
             int best = 0;
             ISPLIB_CHECK_STATUS(isplib_b200_spmm_autotune(
                 reduction, M, N, K, g.nnz, g.rowptr32.data_ptr<int32_t>(), g.col32.data_ptr<int32_t>(), val_ptr,
-                mat.data_ptr<float>(), ldx, out.data_ptr<float>(), K, arg_ptr, &g.info, g.plan_ptr(), wst.data_ptr(), ws,
+                mat.data_ptr<float>(), ldx, r.out.data_ptr<float>(), K, arg_ptr, &g.info, g.plan_ptr(), wst.data_ptr(), ws,
                 env_int("ISPLIB_B200_AUTOTUNE_ITERS", 3), &best, nullptr, stream.stream()));
             g.tuned[tkey] = best;
             variant = best;
         }
     }
+    // a tuned or forced variant was chosen for ONE alignment class of x; a later call may pass a
+    // view at another offset / row stride (16- instead of 32-byte aligned rows): fall back to the
+    // shape rule instead of failing with ISPLIB_NO_OPT_IMPL
+    if (variant != ISPLIB_VARIANT_AUTO &&
+        !isplib_b200_variant_supported(variant, reduction, K, ldx, K, mat.data_ptr<float>(), r.out.data_ptr<float>()))
+        variant = ISPLIB_VARIANT_AUTO;
     // ISPLIB_B200_EMPTY_ROWS=zero: torch_sparse's convention for max/min rows without entries
     // (0) instead of what csrc/fusedmm.cpp:147-150 leaves behind (lowest()/max())
     const char* er = std::getenv("ISPLIB_B200_EMPTY_ROWS");
-    const int flags = (is_arg && er && std::string(er) == "zero") ? ISPLIB_FLAG_EMPTY_ZERO : 0;
-    ISPLIB_CHECK_STATUS(isplib_b200_spmm_csr_ex(reduction, M, N, K, g.nnz, g.rowptr32.data_ptr<int32_t>(),
-                                                g.col32.data_ptr<int32_t>(), val_ptr, mat.data_ptr<float>(), ldx,
-                                                out.data_ptr<float>(), K, arg_ptr, &g.info, g.plan_ptr(),
-                                                wst.data_ptr(), ws, variant, flags, nullptr, nullptr, g.nnz,
-                                                stream.stream()));
-    return std::make_tuple(out, arg_out);
+    int flags = (is_arg && er && std::string(er) == "zero") ? ISPLIB_FLAG_EMPTY_ZERO : 0;
+    if (opt.relu) flags |= ISPLIB_FLAG_RELU;
+    ISPLIB_CHECK_STATUS(isplib_b200_spmm_csr_fused(reduction, M, N, K, g.nnz, g.rowptr32.data_ptr<int32_t>(),
+                                                   g.col32.data_ptr<int32_t>(), val_ptr, mat.data_ptr<float>(), ldx,
+                                                   r.out.data_ptr<float>(), K, arg_ptr, &g.info, g.plan_ptr(),
+                                                   wst.data_ptr(), ws, variant, flags, nullptr, nullptr, g.nnz,
+                                                   &epi, stream.stream()));
+    return r;
 }
 
 // ---------------------------------------------------------------------------------------
 // autograd Functions -- FusedMM_SPMMSum / Mean / Max / Min of the reference
 // ---------------------------------------------------------------------------------------
 // d(loss)/d(value) of sum / mean: one SDDMM over the CSR pattern (isplib_b200_sddmm_csr)
-Tensor value_gradient(AutogradContext* ctx, GraphEntry& g, const variable_list& saved, const Tensor& grad_out_in,
-                      bool mean) {
+Tensor value_gradient(AutogradContext* ctx, GraphEntry& g, const Tensor& value, const Tensor& mat_in,
+                      const Tensor& grad_out_in, bool mean) {
     if (!ctx->saved_data["value_grad"].toBool()) return Tensor();
     c10::cuda::CUDAGuard guard(grad_out_in.device());
     Tensor grad_out = grad_out_in.contiguous();
-    Tensor value = saved[2], mat = saved[3].contiguous();
+    Tensor mat = mat_in.contiguous();
     Tensor grad_value = torch::empty_like(value, value.options().memory_format(c10::MemoryFormat::Contiguous));
     auto stream = at::cuda::getCurrentCUDAStream();
     std::lock_guard<std::mutex> lk(g.mu);
@@ -324,62 +456,41 @@ Tensor value_gradient(AutogradContext* ctx, GraphEntry& g, const variable_list& 
     return grad_value;
 }
 
-class SPMMSum : public torch::autograd::Function<SPMMSum> {
-public:
-    static variable_list forward(AutogradContext* ctx, Variable rowptr, Variable col,
-                                 c10::optional<Variable> value, Variable mat) {
-        c10::cuda::CUDAGuard guard(mat.device());
-        auto g = get_graph(rowptr, col);
-        Tensor out;
-        {
-            std::lock_guard<std::mutex> lk(g->mu);
-            out = std::get<0>(spmm_fw(g->fwd, value, mat, ISPLIB_REDUCE_SUM));
-        }
-        ctx->saved_data["n"] = mat.size(0);
-        ctx->saved_data["has_value"] = value.has_value();
-        // needs_input_grad() indexes tensor inputs only (a None `value` shifts it), so the
-        // flags are taken here, like any_variable_requires_grad at csrc/fusedmm.cpp:228
-        ctx->saved_data["mat_grad"] = mat.requires_grad();
-        const bool value_grad = value.has_value() && value->requires_grad();
-        ctx->saved_data["value_grad"] = value_grad;
-        if (value_grad) ctx->save_for_backward({rowptr, col, value.value(), mat});
-        else if (value.has_value()) ctx->save_for_backward({rowptr, col, value.value()});
-        else ctx->save_for_backward({rowptr, col});
-        return {out};
-    }
-    static variable_list backward(AutogradContext* ctx, variable_list grad_outs) {
-        auto grad_out = grad_outs[0];
-        auto saved = ctx->get_saved_variables();
-        auto g = get_graph(saved[0], saved[1]);
-        const int64_t n = ctx->saved_data["n"].toInt();
-        c10::optional<Tensor> value = c10::nullopt;
-        if (ctx->saved_data["has_value"].toBool()) value = saved[2];
-        // the reference never computes grad_value for sum (csrc/fusedmm.cpp:268-272 returns an
-        // undefined gradient); here it is the SDDMM <grad_out[row(e)], mat[col[e]]>
-        Tensor grad_value = value_gradient(ctx, *g, saved, grad_out, /*mean=*/false);
-        Tensor grad_mat;
-        if (ctx->saved_data["mat_grad"].toBool()) {
-            c10::cuda::CUDAGuard guard(grad_out.device());
-            std::lock_guard<std::mutex> lk(g->mu);
-            ensure_csc(*g, n);
-            Tensor vt = permuted_values(*g, value, false);
-            c10::optional<Tensor> ovt = vt.defined() ? c10::optional<Tensor>(vt) : c10::nullopt;
-            grad_mat = std::get<0>(spmm_fw(g->bwd, ovt, grad_out, ISPLIB_REDUCE_SUM));  // csrc/fusedmm.cpp:285
-        }
-        return {Variable(), Variable(), grad_value, grad_mat};
-    }
-};
+// grad_mat of sum / mean: the forward kernel on the cached CSC view (csrc/fusedmm.cpp:285, :375),
+// weights value[csr2csc] (sum) or value[csr2csc] / max(rowcount[row],1) (mean, isplib/__init__.py:86-93)
+Tensor transposed_spmm(GraphEntry& g, int64_t n, const c10::optional<Tensor>& value, const Tensor& grad_out, bool mean,
+                       const FwOptions& opt = FwOptions()) {
+    c10::cuda::CUDAGuard guard(grad_out.device());
+    std::lock_guard<std::mutex> lk(g.mu);
+    ensure_csc(g, n);
+    Tensor w = permuted_values(g, value, mean);
+    c10::optional<Tensor> ow = w.defined() ? c10::optional<Tensor>(w) : c10::nullopt;
+    return spmm_fw(g.bwd, ow, grad_out, ISPLIB_REDUCE_SUM, opt).out;
+}
 
-class SPMMMean : public torch::autograd::Function<SPMMMean> {
+// SPMMSum / SPMMMean, optionally with the fused caller epilogue
+//     out = relu?( REDUCE(A, mat) + addend_scale * addend + bias )
+// `self_addend`: the addend is `mat` itself (GIN's (1 + eps) x_i + sum_j x_j); its gradient is
+// then folded into the backward SpMM the same way (addend = the incoming gradient).
+template <int REDUCE>
+class SPMMAdd : public torch::autograd::Function<SPMMAdd<REDUCE>> {
 public:
     static variable_list forward(AutogradContext* ctx, Variable rowptr, Variable col,
-                                 c10::optional<Variable> value, Variable mat) {
+                                 c10::optional<Variable> value, Variable mat, c10::optional<Variable> bias,
+                                 c10::optional<Variable> addend, double addend_scale, bool relu, bool self_addend) {
         c10::cuda::CUDAGuard guard(mat.device());
         auto g = get_graph(rowptr, col);
+        FwOptions opt;
+        opt.bias = bias;
+        opt.addend = self_addend ? c10::optional<Tensor>(mat) : addend;
+        opt.addend_scale = addend_scale;
+        opt.relu = relu;
+        opt.cache_padded = !mat.requires_grad();
+        if (self_addend) TORCH_CHECK(g->fwd.m == mat.size(0), "isplib_b200: a self addend needs a square adjacency");
         Tensor out;
         {
             std::lock_guard<std::mutex> lk(g->mu);
-            out = std::get<0>(spmm_fw(g->fwd, value, mat, ISPLIB_REDUCE_MEAN));
+            out = spmm_fw(g->fwd, value, mat, REDUCE, opt).out;
         }
         ctx->saved_data["n"] = mat.size(0);
         ctx->saved_data["has_value"] = value.has_value();
@@ -388,32 +499,52 @@ public:
         ctx->saved_data["mat_grad"] = mat.requires_grad();
         const bool value_grad = value.has_value() && value->requires_grad();
         ctx->saved_data["value_grad"] = value_grad;
-        if (value_grad) ctx->save_for_backward({rowptr, col, value.value(), mat});
-        else if (value.has_value()) ctx->save_for_backward({rowptr, col, value.value()});
-        else ctx->save_for_backward({rowptr, col});
+        ctx->saved_data["bias_grad"] = bias.has_value() && bias->requires_grad();
+        ctx->saved_data["addend_grad"] = !self_addend && addend.has_value() && addend->requires_grad();
+        ctx->saved_data["addend_scale"] = addend_scale;
+        ctx->saved_data["relu"] = relu;
+        ctx->saved_data["self_addend"] = self_addend;
+        variable_list to_save = {rowptr, col};
+        if (value.has_value()) to_save.push_back(value.value());
+        if (value_grad) to_save.push_back(mat);
+        if (relu) to_save.push_back(out);       // the ReLU mask of the backward
+        ctx->save_for_backward(to_save);
         return {out};
     }
     static variable_list backward(AutogradContext* ctx, variable_list grad_outs) {
-        auto grad_out = grad_outs[0];
         auto saved = ctx->get_saved_variables();
         auto g = get_graph(saved[0], saved[1]);
         const int64_t n = ctx->saved_data["n"].toInt();
+        const bool has_value = ctx->saved_data["has_value"].toBool();
+        const bool value_grad = ctx->saved_data["value_grad"].toBool();
+        const bool relu = ctx->saved_data["relu"].toBool();
+        const bool self_addend = ctx->saved_data["self_addend"].toBool();
+        const double scale = ctx->saved_data["addend_scale"].toDouble();
+        size_t idx = 2;
         c10::optional<Tensor> value = c10::nullopt;
-        if (ctx->saved_data["has_value"].toBool()) value = saved[2];
-        Tensor grad_value = value_gradient(ctx, *g, saved, grad_out, /*mean=*/true);   // csrc/fusedmm.cpp:349-353: undefined there
-        Tensor grad_mat;
+        if (has_value) value = saved[idx++];
+        Tensor mat_saved = value_grad ? saved[idx++] : Tensor();
+        Tensor grad = grad_outs[0];
+        c10::cuda::CUDAGuard guard(grad.device());
+        if (relu) grad = at::threshold_backward(grad, saved[idx++], 0);
+        grad = grad.contiguous();
+        // the reference never computes grad_value for sum / mean (csrc/fusedmm.cpp:268-272, :349-353
+        // return an undefined gradient); here it is the SDDMM <grad_out[row(e)], mat[col[e]]>
+        Tensor grad_value = value_grad ? value_gradient(ctx, *g, value.value(), mat_saved, grad, REDUCE == ISPLIB_REDUCE_MEAN)
+                                       : Tensor();
+        Tensor grad_mat, grad_bias, grad_addend;
         if (ctx->saved_data["mat_grad"].toBool()) {
-            c10::cuda::CUDAGuard guard(grad_out.device());
-            std::lock_guard<std::mutex> lk(g->mu);
-            ensure_csc(*g, n);
-            // weights value[csr2csc] / max(rowcount[row],1): isplib/__init__.py:86-93; a SUM
-            // over the CSC view with them: csrc/fusedmm.cpp:375
-            Tensor w = permuted_values(*g, value, true);
-            grad_mat = std::get<0>(spmm_fw(g->bwd, w, grad_out, ISPLIB_REDUCE_SUM));
+            FwOptions opt;
+            if (self_addend) { opt.addend = grad; opt.addend_scale = scale; }
+            grad_mat = transposed_spmm(*g, n, value, grad, REDUCE == ISPLIB_REDUCE_MEAN, opt);
         }
-        return {Variable(), Variable(), grad_value, grad_mat};
+        if (ctx->saved_data["bias_grad"].toBool()) grad_bias = grad.sum(0);
+        if (ctx->saved_data["addend_grad"].toBool()) grad_addend = scale == 1.0 ? grad : grad * scale;
+        return {Variable(), Variable(), grad_value, grad_mat, grad_bias, grad_addend, Variable(), Variable(), Variable()};
     }
 };
+using SPMMSum = SPMMAdd<ISPLIB_REDUCE_SUM>;
+using SPMMMean = SPMMAdd<ISPLIB_REDUCE_MEAN>;
 
 template <int REDUCE>
 class SPMMArg : public torch::autograd::Function<SPMMArg<REDUCE>> {
@@ -422,40 +553,71 @@ public:
                                  c10::optional<Variable> value, Variable mat) {
         c10::cuda::CUDAGuard guard(mat.device());
         auto g = get_graph(rowptr, col);
-        Tensor out, arg_out;
+        const bool value_grad = value.has_value() && value->requires_grad();
+        // the backward scatter streams col[arg] / val[arg] if the forward wrote them next to arg_out
+        // (only worth the 4-8 extra bytes per element when a gradient w.r.t. mat will be asked for;
+        // a gradient w.r.t. value needs the edge ids anyway and takes the general kernel)
+        FwOptions opt;
+        opt.want_aux = mat.requires_grad() && !value_grad && env_int("ISPLIB_B200_ARG_AUX", 1);
+        opt.cache_padded = !mat.requires_grad();
+        FwResult r;
         {
             std::lock_guard<std::mutex> lk(g->mu);
-            auto r = spmm_fw(g->fwd, value, mat, REDUCE);
-            out = std::get<0>(r);
-            arg_out = std::get<1>(r).value();
+            r = spmm_fw(g->fwd, value, mat, REDUCE, opt);
         }
+        Tensor arg_out = r.arg_out.value();
         ctx->saved_data["has_value"] = value.has_value();
         ctx->saved_data["mat_grad"] = mat.requires_grad();
-        ctx->saved_data["value_grad"] = value.has_value() && value->requires_grad();
-        if (value.has_value()) ctx->save_for_backward({rowptr, col, mat, arg_out, value.value()});
-        else ctx->save_for_backward({rowptr, col, mat, arg_out});
+        ctx->saved_data["value_grad"] = value_grad;
+        ctx->saved_data["aux"] = opt.want_aux;
+        ctx->saved_data["n"] = mat.size(0);
+        if (opt.want_aux) {
+            if (r.arg_val.defined()) ctx->save_for_backward({rowptr, col, r.arg_col, r.arg_val});
+            else ctx->save_for_backward({rowptr, col, r.arg_col});
+        } else if (value.has_value()) {
+            ctx->save_for_backward({rowptr, col, mat, arg_out, value.value()});
+        } else {
+            ctx->save_for_backward({rowptr, col, mat, arg_out});
+        }
         ctx->mark_non_differentiable({arg_out});  // csrc/fusedmm.cpp:403
-        return {out, arg_out};
+        return {r.out, arg_out};
     }
     static variable_list backward(AutogradContext* ctx, variable_list grad_outs) {
         auto grad_out = grad_outs[0].contiguous();
         const bool has_value = ctx->saved_data["has_value"].toBool();
         auto saved = ctx->get_saved_variables();
+        c10::cuda::CUDAGuard guard(grad_out.device());
+        auto stream = at::cuda::getCurrentCUDAStream();
+        if (ctx->saved_data["aux"].toBool()) {
+            Tensor arg_col = saved[2];
+            Tensor arg_val = saved.size() > 3 ? saved[3] : Tensor();
+            const int64_t M = arg_col.size(0), K = arg_col.size(1), N = ctx->saved_data["n"].toInt();
+            Tensor grad_mat = torch::empty({N, K}, grad_out.options());
+            ISPLIB_CHECK_STATUS(isplib_b200_spmm_arg_backward_aux(
+                M, N, K, arg_col.data_ptr<int32_t>(), arg_val.defined() ? arg_val.data_ptr<float>() : nullptr, K,
+                grad_out.data_ptr<float>(), K, grad_mat.data_ptr<float>(), K, 1, stream.stream()));
+            return {Variable(), Variable(), Variable(), grad_mat};
+        }
         auto g = get_graph(saved[0], saved[1]);
         Tensor mat = saved[2].contiguous(), arg_out = saved[3];
         Tensor value = has_value ? saved[4].contiguous() : Tensor();
-        const int64_t M = arg_out.size(0), K = arg_out.size(1), N = mat.size(0), nnz = g->fwd.nnz;
+        const int64_t M = arg_out.size(0), K = arg_out.size(1), N = mat.size(0);
         const bool need_val = has_value && ctx->saved_data["value_grad"].toBool();
         const bool need_mat = ctx->saved_data["mat_grad"].toBool();
         Tensor grad_value, grad_mat;
         if (need_val || need_mat) {
-            c10::cuda::CUDAGuard guard(grad_out.device());
-            auto stream = at::cuda::getCurrentCUDAStream();
             if (need_mat) grad_mat = torch::empty_like(mat);
             if (need_val) grad_value = torch::empty_like(value);
+            Tensor col32;
+            int64_t nnz = 0;
+            {
+                std::lock_guard<std::mutex> lk(g->mu);   // a concurrent rebuild must not swap these under us
+                col32 = g->fwd.col32;
+                nnz = g->fwd.nnz;
+            }
             // one fused pass instead of csrc/fusedmm.cpp:417-446
             ISPLIB_CHECK_STATUS(isplib_b200_spmm_arg_backward(
-                M, N, K, nnz, g->fwd.col32.data_ptr<int32_t>(), has_value ? value.data_ptr<float>() : nullptr,
+                M, N, K, nnz, col32.data_ptr<int32_t>(), has_value ? value.data_ptr<float>() : nullptr,
                 mat.data_ptr<float>(), K, arg_out.data_ptr<int64_t>(), K, nnz, grad_out.data_ptr<float>(), K,
                 need_mat ? grad_mat.data_ptr<float>() : nullptr, K, need_val ? grad_value.data_ptr<float>() : nullptr,
                 1, stream.stream()));
@@ -471,7 +633,7 @@ Tensor fusedmm_spmm(c10::optional<Tensor> opt_row, Tensor rowptr, Tensor col, c1
                     c10::optional<Tensor> opt_colptr, c10::optional<Tensor> opt_csr2csc, Tensor mat,
                     c10::optional<Tensor> value_index_select, c10::optional<Tensor> row_index_select) {
     (void)opt_row; (void)opt_colptr; (void)opt_csr2csc; (void)value_index_select; (void)row_index_select;
-    return SPMMSum::apply(rowptr, col, opt_value, mat)[0];
+    return SPMMSum::apply(rowptr, col, opt_value, mat, c10::nullopt, c10::nullopt, 1.0, false, false)[0];
 }
 
 Tensor fusedmm_spmm_mean(c10::optional<Tensor> opt_row, Tensor rowptr, Tensor col, c10::optional<Tensor> opt_value,
@@ -479,7 +641,7 @@ Tensor fusedmm_spmm_mean(c10::optional<Tensor> opt_row, Tensor rowptr, Tensor co
                          c10::optional<Tensor> opt_csr2csc, Tensor mat, c10::optional<Tensor> new_row,
                          c10::optional<Tensor> new_rowcount) {
     (void)opt_row; (void)opt_rowcount; (void)opt_colptr; (void)opt_csr2csc; (void)new_row; (void)new_rowcount;
-    return SPMMMean::apply(rowptr, col, opt_value, mat)[0];
+    return SPMMMean::apply(rowptr, col, opt_value, mat, c10::nullopt, c10::nullopt, 1.0, false, false)[0];
 }
 
 std::tuple<Tensor, Tensor> fusedmm_spmm_max(Tensor rowptr, Tensor col, c10::optional<Tensor> opt_value, Tensor mat) {
@@ -490,6 +652,29 @@ std::tuple<Tensor, Tensor> fusedmm_spmm_max(Tensor rowptr, Tensor col, c10::opti
 std::tuple<Tensor, Tensor> fusedmm_spmm_min(Tensor rowptr, Tensor col, c10::optional<Tensor> opt_value, Tensor mat) {
     auto r = SPMMArg<ISPLIB_REDUCE_MIN>::apply(rowptr, col, opt_value, mat);
     return std::make_tuple(r[0], r[1]);
+}
+
+// sum / mean with the caller's epilogue fused into the kernel's final store:
+//     out = relu?( REDUCE(A, mat) + addend_scale * addend + bias )
+// GCN: bias (+ ReLU), tests/cpu/gcn-sparse.py:61-68; GIN: addend = mat, scale = 1 + eps, gin-sparse.py:73-78.
+Tensor fusedmm_spmm_fused(Tensor rowptr, Tensor col, c10::optional<Tensor> opt_value, Tensor mat, std::string reduce,
+                          c10::optional<Tensor> bias, c10::optional<Tensor> addend, double addend_scale, bool relu) {
+    const bool self_addend = addend.has_value() && addend->is_same(mat);
+    if (self_addend) addend = c10::nullopt;
+    if (reduce == "sum" || reduce == "add")
+        return SPMMSum::apply(rowptr, col, opt_value, mat, bias, addend, addend_scale, relu, self_addend)[0];
+    TORCH_CHECK(reduce == "mean", "isplib_b200: fusedmm_spmm_fused supports reduce = sum | add | mean, got ", reduce);
+    return SPMMMean::apply(rowptr, col, opt_value, mat, bias, addend, addend_scale, relu, self_addend)[0];
+}
+
+// a [N, K] view of a fresh zero-padded [N, roundup8(K)] buffer holding `x`: the layout the kernels
+// gather from without a per-call copy (the reference's pad_features, tests/cpu/dataset_loader.py:145-160,
+// pads the feature COUNT to a multiple of 16; here the width the model sees stays K)
+Tensor pad_features(Tensor x) {
+    TORCH_CHECK(x.dim() == 2, "isplib_b200: pad_features expects a 2-D tensor");
+    const int64_t K = x.size(1), Kp = (K + 7) / 8 * 8;
+    if (Kp == K) return x.contiguous();
+    return at::constant_pad_nd(x, {0, Kp - K}, 0).narrow(1, 0, K);
 }
 
 void performDummySpMM(int64_t flag) { (void)flag; }  // csrc/fusedmm.cpp:61 -- never called from Python
@@ -523,6 +708,9 @@ TORCH_LIBRARY(isplib, m) {
     m.def("fusedmm_spmm_max(Tensor rowptr, Tensor col, Tensor? value, Tensor mat) -> (Tensor, Tensor)", &fusedmm_spmm_max);
     m.def("fusedmm_spmm_min(Tensor rowptr, Tensor col, Tensor? value, Tensor mat) -> (Tensor, Tensor)", &fusedmm_spmm_min);
     m.def("performDummySpMM(int flag) -> ()", &performDummySpMM);
+    m.def("fusedmm_spmm_fused(Tensor rowptr, Tensor col, Tensor? value, Tensor mat, str reduce, Tensor? bias=None, "
+          "Tensor? addend=None, float addend_scale=1.0, bool relu=False) -> Tensor", &fusedmm_spmm_fused);
+    m.def("_b200_pad_features(Tensor x) -> Tensor", &pad_features);
     m.def("_b200_cache_size() -> int", &cache_size);
     m.def("_b200_cache_clear() -> ()", &cache_clear);
     m.def("_b200_tuned_variant(Tensor rowptr, Tensor col, int reduce, int k, bool has_value, bool transposed) -> int",

@@ -24,6 +24,26 @@ def _matmul(adj_t, x, reduce):
     return sys.modules["torch_sparse"].matmul(adj_t, x, reduce)   # looked up per call: honours the patch
 
 
+def _fused_available(x, spmm) -> bool:
+    """The fused-epilogue kernels run when the plugin is patched in (the CUDA path is the active
+    matmul), the data is on the GPU and no external spmm callable (multi-GPU) was handed in."""
+    if spmm is not None or not x.is_cuda:
+        return False
+    from . import iSpLibPlugin
+    return iSpLibPlugin.is_patched() and iSpLibPlugin.fuse_epilogues
+
+
+def _linear_padded(x, weight):
+    """x @ weight.T written into rows padded to a multiple of 8 floats, returned as the [N, out]
+    view: the SpMM that follows gathers these rows in place with 32-byte loads (out = 47 -> 48)
+    instead of re-padding them on every call."""
+    out = weight.size(0)
+    pad = (-out) % 8
+    if pad == 0 or out <= 8 or not x.is_cuda:
+        return F.linear(x, weight)
+    return F.linear(x, F.pad(weight, (0, 0, 0, pad))).narrow(1, 0, out)
+
+
 class GCNConv(nn.Module):
     """out = A @ (x W) + b  (PyG GCNConv with normalize=False propagates AFTER the linear
     layer, at width out_channels).
@@ -33,20 +53,27 @@ class GCNConv(nn.Module):
     grad, i.e. in the first layer -- needs no backward SpMM at all; 'auto' (default) picks
     aggregate_first iff in_channels < out_channels."""
 
-    def __init__(self, in_channels: int, out_channels: int, bias: bool = True, order: str = "auto"):
+    def __init__(self, in_channels: int, out_channels: int, bias: bool = True, order: str = "auto",
+                 relu: bool = False):
         super().__init__()
         assert order in ("auto", "linear_first", "aggregate_first")
         self.lin = nn.Linear(in_channels, out_channels, bias=False)
         self.bias = nn.Parameter(torch.zeros(out_channels)) if bias else None
         self.aggregate_first = (order == "aggregate_first") or (order == "auto" and in_channels < out_channels)
+        self.relu = relu      # the activation that follows the layer (tests/cpu/gcn-sparse.py:64), fused when possible
 
     def forward(self, x, adj_t, spmm: Optional[Callable] = None):
         agg = (lambda t: spmm(t, "sum")) if spmm is not None else (lambda t: _matmul(adj_t, t, "sum"))
         if self.aggregate_first:
-            out = self.lin(agg(x))
-        else:
-            out = agg(self.lin(x))
-        return out if self.bias is None else out + self.bias
+            out = F.linear(agg(x), self.lin.weight, self.bias)        # bias in the GEMM epilogue
+            return F.relu(out) if self.relu else out
+        if _fused_available(x, spmm):
+            # + bias and ReLU inside the SpMM's final store: two [N, K] passes less
+            from . import fused_matmul
+            return fused_matmul(adj_t, _linear_padded(x, self.lin.weight), "sum", bias=self.bias, relu=self.relu)
+        out = agg(self.lin(x))
+        out = out if self.bias is None else out + self.bias
+        return F.relu(out) if self.relu else out
 
 
 class SAGEConv(nn.Module):
@@ -63,7 +90,10 @@ class SAGEConv(nn.Module):
             agg = spmm(x, self.aggr)
         else:
             agg = _matmul(adj_t.set_value(None) if adj_t.has_value() else adj_t, x, self.aggr)
-        return self.lin_l(agg) + self.lin_r(x[: agg.size(0)])
+        # lin_l(agg) + lin_r(x) as ONE accumulate-GEMM: the root term (with lin_l's bias) is the
+        # addmm's initial value, so no separate [N, out] add pass
+        root = F.linear(x[: agg.size(0)], self.lin_r.weight, self.lin_l.bias)
+        return torch.addmm(root, agg, self.lin_l.weight.t())
 
 
 class GINConv(nn.Module):
@@ -75,22 +105,24 @@ class GINConv(nn.Module):
         self.eps = eps
 
     def forward(self, x, adj_t, spmm: Optional[Callable] = None):
-        if spmm is not None:
-            agg = spmm(x, "sum")
-        else:
-            agg = _matmul(adj_t.set_value(None) if adj_t.has_value() else adj_t, x, "sum")
+        adj = adj_t.set_value(None) if (spmm is None and adj_t.has_value()) else adj_t
+        if _fused_available(x, spmm) and adj.sparse_sizes()[0] == x.size(0):
+            # (1 + eps) * x_i + sum_j x_j in the SpMM's final store (addend = x itself)
+            from . import fused_matmul
+            return self.nn(fused_matmul(adj, x, "sum", addend=x, addend_scale=1.0 + self.eps))
+        agg = spmm(x, "sum") if spmm is not None else _matmul(adj, x, "sum")
         return self.nn((1.0 + self.eps) * x[: agg.size(0)] + agg)
 
 
 class GCN(nn.Module):
     def __init__(self, in_channels, hidden, num_classes, dropout: float = 0.5, order: str = "auto"):
         super().__init__()
-        self.conv1 = GCNConv(in_channels, hidden, order=order)
+        self.conv1 = GCNConv(in_channels, hidden, order=order, relu=True)    # F.relu(conv1(...)), gcn-sparse.py:64
         self.conv2 = GCNConv(hidden, num_classes, order=order)
         self.dropout = dropout
 
     def forward(self, x, adj_t, spmm=None):
-        x = F.relu(self.conv1(x, adj_t, spmm))
+        x = self.conv1(x, adj_t, spmm)
         x = F.dropout(x, p=self.dropout, training=self.training)
         x = self.conv2(x, adj_t, spmm)
         return F.log_softmax(x, dim=1)

@@ -258,3 +258,20 @@ def sddmm(rowptr, col, a, x, mean_scale: bool = False) -> np.ndarray:
     if st != 0:
         raise RuntimeError(f"oracle_sddmm status {st}")
     return out
+
+
+def apply_epilogue(out, bias=None, addend=None, addend_scale: float = 1.0, relu: bool = False) -> np.ndarray:
+    """What the reference's callers do to the SpMM result in separate passes, restated:
+    GCNConv's `out + bias` and F.relu (tests/cpu/gcn-sparse.py:61-68), GINConv's
+    `(1 + eps) * x_i + aggr` (gin-sparse.py:73-78; addend = x, addend_scale = 1 + eps).
+    fp32, one rounding per step, in the order  relu((out + scale * addend) + bias)."""
+    o = np.asarray(out, dtype=np.float32).copy()
+    if addend is not None:
+        a = np.asarray(addend, dtype=np.float32)[: o.shape[0]]
+        # the kernel uses one fused multiply-add for `scale * addend + out`
+        o = (o.astype(np.float64) + np.float64(np.float32(addend_scale)) * a.astype(np.float64)).astype(np.float32)
+    if bias is not None:
+        o = o + np.asarray(bias, dtype=np.float32)[None, :]
+    if relu:
+        o = np.maximum(o, np.float32(0))
+    return o

@@ -23,7 +23,7 @@ def test_library_exports_every_declared_symbol():
     for s in syms:
         assert hasattr(lib, s), f"{s} declared in include/isplib_b200.h but not exported"
     assert sorted(capi.EXPORTS) == syms, "capi.EXPORTS out of sync with the header"
-    assert lib.isplib_b200_abi_version() == 1
+    assert lib.isplib_b200_abi_version() == 2
 
 
 def test_no_torch_types_in_the_c_abi():
