@@ -306,26 +306,38 @@ def parity_check(torch, dist, world, g, x, out, arg, row0, reduce, n_rows=2000):
         err = np.abs(got.astype(np.float64) - ref.astype(np.float64))
         plain_bad = err > 1e-6 + 1e-5 * np.abs(ref)
         n_bad = int(plain_bad.sum())
-        ok = True
+        # the float64-accumulated sum: how far is each fp32 ORDER (the reference's sequential one,
+        # the kernel's) from the exact result
+        truth = oracle.spmm_sum_f64(sub_rp.cpu().numpy(), sub_col, sub_val, xh, reduce == "mean").astype(np.float64)
+        tol = 1e-6 + 1e-5 * np.abs(truth)
+        k_miss = int((np.abs(got.astype(np.float64) - truth) > tol).sum())
+        r_miss = int((np.abs(ref.astype(np.float64) - truth) > tol).sum())
+        ok = k_miss <= 1.1 * r_miss + 1e-4 * err.size
         if n_bad:
             absval = np.ones(sub_col.shape[0], np.float32) if sub_val is None else np.abs(sub_val)
             cond = oracle.spmm_c(sub_rp.cpu().numpy(), sub_col, absval, np.abs(xh), code)[0]
-            ok = not bool((plain_bad & (err > 1e-6 + 1e-5 * np.maximum(np.abs(ref), cond))).any())
-            ok = ok and n_bad <= 1e-3 * err.size
-        res.update({"max_abs_err": float(err.max()), "need_condition_bound": n_bad, "ok": ok})
+            ok = ok and not bool((plain_bad & (err > 1e-6 + 1e-5 * np.maximum(np.abs(ref), cond))).any())
+        res.update({"max_abs_err": float(err.max()), "outside_plain_tolerance_vs_reference_order": n_bad,
+                    "kernel_outside_vs_float64_sum": k_miss, "reference_order_outside_vs_float64_sum": r_miss, "ok": ok})
     if world > 1:
         t = torch.tensor([res["max_abs_err"], 0.0 if res["ok"] else 1.0, float(res["rows"]), float(res["elements"]),
-                          float(res.get("need_condition_bound", 0))], device=dev, dtype=torch.float64)
+                          float(res.get("outside_plain_tolerance_vs_reference_order", 0)),
+                          float(res.get("kernel_outside_vs_float64_sum", 0)),
+                          float(res.get("reference_order_outside_vs_float64_sum", 0))], device=dev, dtype=torch.float64)
         mx = t.clone()
         dist.all_reduce(mx, op=dist.ReduceOp.MAX)
         dist.all_reduce(t, op=dist.ReduceOp.SUM)
         res["max_abs_err"] = float(mx[0])
         res["ok"] = bool(float(mx[1]) == 0.0)
         res["rows"], res["elements"] = int(t[2]), int(t[3])
-        if "need_condition_bound" in res:
-            res["need_condition_bound"] = int(t[4])
+        if "outside_plain_tolerance_vs_reference_order" in res:
+            res["outside_plain_tolerance_vs_reference_order"] = int(t[4])
+            res["kernel_outside_vs_float64_sum"], res["reference_order_outside_vs_float64_sum"] = int(t[5]), int(t[6])
         res["ranks_checked"] = world
     res["against"] = "oracle/fusedmm_oracle.c on the same inputs, sampled rows of the timed output"
+    res["criterion"] = ("max/min: out and arg bit-exact. sum/mean: every element inside 1e-6 + 1e-5*max(|ref|, sum|a_e x_e|) "
+                        "and the kernel's fp32 summation order no further from the float64 sum than the reference's "
+                        "sequential order (counts against the plain 1e-6 + 1e-5|ref| reported)")
     return res
 
 

@@ -160,6 +160,56 @@ int isplib_b200_spmm_csr_fused(int reduce, int64_t m, int64_t n, int64_t k, int6
                                const int32_t* edge_ids, int64_t arg_sentinel,
                                const isplib_b200_epilogue* epi, isplib_stream_t stream);
 
+/* ---- row-partitioned multi-GPU forward: gather of X fused INTO the SpMM -------------------
+ * New functionality (the reference is single-process).  Rank r owns a
+ * contiguous block of rows of A and the matching slice of X; its block's columns address the
+ * owner-major gathered matrix [world * slice_rows, k].  Instead of an all-gather collective
+ * followed by the SpMM, ONE kernel does both over NVLink peer memory: its first `copy_ctas` CTAs
+ * pull the peers' slices (group by group, `owner_group`), the rest multiply, each work item
+ * starting as soon as the slices of ITS arrival group have landed.  Needs a grouped plan.
+ *
+ * isplib_b200_plan_build_grouped: like isplib_b200_plan_build, but segments never cross the
+ * `n_runs` column runs [run_start[j], run_start[j+1]) and the work items are ordered by
+ * run_group[j] (0 .. n_groups-1); group_item_end[g] receives the end of group g's items.
+ * Usable with every forward entry point (the item order is free).                              */
+int isplib_b200_plan_grouped_bytes(int64_t m, int64_t nnz, int32_t seg_len, int32_t n_runs, size_t* bytes);
+int isplib_b200_plan_build_grouped(int64_t m, int64_t nnz, const int32_t* rowptr, const int32_t* col,
+                                   int32_t seg_len, int32_t n_runs, const int32_t* run_start,
+                                   const int32_t* run_group, int32_t n_groups,
+                                   void* plan_dev, size_t plan_dev_bytes, isplib_b200_plan_info* info,
+                                   int64_t* group_item_end, isplib_stream_t stream);
+
+typedef struct isplib_b200_gather_desc {
+    int32_t world, rank;
+    int32_t n_groups;               /* arrival groups incl. group 0 (the rank's own slice) */
+    int32_t copy_ctas;              /* CTAs that pull over NVLink; 0 = default (32) */
+    const void* const* peer_x;      /* [world] host array: rank q's gathered-x buffer as mapped into this
+                                       process (symmetric memory); slice q = rows [q*slice_rows, ...) of
+                                       EVERY buffer; peer_x[rank] == x */
+    void* const* peer_ready;        /* [world] host array: rank q's ready words, uint32[world], same mapping */
+    const int32_t* owner_group;     /* [world] host array: arrival group of each owner; owner_group[rank] == 0 */
+    int64_t slice_rows;             /* n == world * slice_rows */
+    uint32_t* flags;                /* device uint32[8], zeroed once, private to this rank */
+    uint32_t* status;               /* device uint32, zeroed once: 1 after a wait timed out (4 s) */
+    uint32_t epoch;                 /* 1, 2, 3, ... one per launch on this (flags, ready words) set; the
+                                       caller alternates two x buffers + ready-word sets by epoch parity */
+    uint32_t reserved;
+    const int64_t* group_item_end;  /* [n_groups] host array from isplib_b200_plan_build_grouped */
+} isplib_b200_gather_desc;
+/* x: the LOCAL gathered buffer [n = world * slice_rows, k] (row stride ldx, ldx % 4 == 0); its own
+ * slice must hold this step's rows before the call (stream order); the other slices are overwritten.
+ * Everything else as isplib_b200_spmm_csr_fused.  world == 1 degenerates to the plain kernel. */
+int isplib_b200_spmm_csr_gather(int reduce, int64_t m, int64_t n, int64_t k, int64_t nnz,
+                                const int32_t* rowptr, const int32_t* col, const float* val,
+                                float* x, int64_t ldx, float* out, int64_t ldo,
+                                int64_t* arg_out,
+                                const isplib_b200_plan_info* info, const void* plan_dev,
+                                void* workspace, size_t workspace_bytes,
+                                int variant, int flags, const float* row_divisor,
+                                const int32_t* edge_ids, int64_t arg_sentinel,
+                                const isplib_b200_epilogue* epi,
+                                const isplib_b200_gather_desc* gd, isplib_stream_t stream);
+
 /* ---- kernel variants + on-device selection: replaces autotuner/findbestk.py:29-41
  *      (an offline K sweep) by timing the eligible row-split / K-tile / unroll
  *      variants on the device, on the caller's own graph and buffers ------------ */

@@ -29,7 +29,8 @@ EXPORTS = [
     "isplib_b200_abi_version", "isplib_b200_status_string",
     "isplib_b200_plan_bytes", "isplib_b200_plan_build", "isplib_b200_spmm_workspace_bytes",
     "isplib_b200_spmm_csr", "isplib_b200_spmm_csr_ex", "isplib_b200_spmm_csr_fused",
-    "isplib_b200_spmm_arg_backward_aux",
+    "isplib_b200_spmm_arg_backward_aux", "isplib_b200_spmm_csr_gather",
+    "isplib_b200_plan_grouped_bytes", "isplib_b200_plan_build_grouped",
     "isplib_b200_variant_count", "isplib_b200_variant_name", "isplib_b200_variant_supported",
     "isplib_b200_variant_default", "isplib_b200_spmm_autotune",
     "isplib_b200_csr_transpose_workspace_bytes", "isplib_b200_csr_transpose",
@@ -58,6 +59,17 @@ class Epilogue(ctypes.Structure):
     ]
 
 
+class GatherDesc(ctypes.Structure):
+    """isplib_b200_gather_desc (include/isplib_b200.h)."""
+    _fields_ = [
+        ("world", ctypes.c_int32), ("rank", ctypes.c_int32), ("n_groups", ctypes.c_int32), ("copy_ctas", ctypes.c_int32),
+        ("peer_x", ctypes.POINTER(ctypes.c_void_p)), ("peer_ready", ctypes.POINTER(ctypes.c_void_p)),
+        ("owner_group", ctypes.POINTER(ctypes.c_int32)), ("slice_rows", ctypes.c_int64),
+        ("flags", ctypes.c_void_p), ("status", ctypes.c_void_p), ("epoch", ctypes.c_uint32), ("reserved", ctypes.c_uint32),
+        ("group_item_end", ctypes.POINTER(ctypes.c_int64)),
+    ]
+
+
 _lib: Optional[ctypes.CDLL] = None
 
 
@@ -82,6 +94,11 @@ def lib() -> ctypes.CDLL:
     L.isplib_b200_spmm_csr.argtypes = spmm_args + [ctypes.c_int, p]
     L.isplib_b200_spmm_csr_ex.argtypes = spmm_args + [ctypes.c_int, ctypes.c_int, p, p, i64, p]
     L.isplib_b200_spmm_csr_fused.argtypes = spmm_args + [ctypes.c_int, ctypes.c_int, p, p, i64, ctypes.POINTER(Epilogue), p]
+    L.isplib_b200_spmm_csr_gather.argtypes = spmm_args + [ctypes.c_int, ctypes.c_int, p, p, i64, ctypes.POINTER(Epilogue),
+                                                          ctypes.POINTER(GatherDesc), p]
+    L.isplib_b200_plan_grouped_bytes.argtypes = [i64, i64, i32, i32, ctypes.POINTER(sz)]
+    L.isplib_b200_plan_build_grouped.argtypes = [i64, i64, p, p, i32, i32, ctypes.POINTER(i32), ctypes.POINTER(i32), i32,
+                                                 p, sz, pinfo, ctypes.POINTER(i64), p]
     L.isplib_b200_spmm_arg_backward_aux.argtypes = [i64, i64, i64, p, p, i64, p, i64, p, i64, ctypes.c_int, p]
     L.isplib_b200_variant_count.restype = ctypes.c_int
     L.isplib_b200_variant_name.restype = ctypes.c_char_p
@@ -154,6 +171,80 @@ class Plan:
     @property
     def ptr(self) -> ctypes.c_void_p:
         return _aligned_ptr(self.buf)
+
+
+class GroupedPlan(Plan):
+    """A plan whose segments never cross the given column runs and whose work items are ordered by
+    the runs' arrival group (isplib_b200_plan_build_grouped): the plan of the fused gather + SpMM
+    kernel.  Usable with every forward entry point."""
+
+    def __init__(self, rowptr32: torch.Tensor, col32: torch.Tensor, run_start, run_group, n_groups: int, seg_len: int = 0):
+        assert rowptr32.is_cuda and rowptr32.dtype == torch.int32 and rowptr32.is_contiguous()
+        assert col32.dtype == torch.int32 and col32.is_contiguous()
+        self.m = rowptr32.numel() - 1
+        self.nnz = int(col32.numel())
+        n_runs = len(run_start)
+        assert n_runs == len(run_group) and n_runs >= 1
+        nbytes = ctypes.c_size_t(0)
+        check(lib().isplib_b200_plan_grouped_bytes(self.m, self.nnz, seg_len, n_runs, ctypes.byref(nbytes)), "plan_grouped_bytes")
+        self.buf = _dev_bytes(nbytes.value, rowptr32.device)
+        self.info = PlanInfo()
+        rs = (ctypes.c_int32 * n_runs)(*[int(v) for v in run_start])
+        rg = (ctypes.c_int32 * n_runs)(*[int(v) for v in run_group])
+        ends = (ctypes.c_int64 * int(n_groups))()
+        check(lib().isplib_b200_plan_build_grouped(self.m, self.nnz, _p(rowptr32), _p(col32), seg_len, n_runs, rs, rg,
+                                                   int(n_groups), _aligned_ptr(self.buf), nbytes.value,
+                                                   ctypes.byref(self.info), ends, _stream(rowptr32.device)),
+              "plan_build_grouped")
+        self.n_groups = int(n_groups)
+        self.group_item_end = [int(v) for v in ends]
+
+
+def spmm_csr_gather(reduce, rowptr32, col32, val, x_gathered, plan: "GroupedPlan", *, world: int, rank: int,
+                    peer_x, peer_ready, owner_group, slice_rows: int, flags, status, epoch: int,
+                    copy_ctas: int = 0, variant: int = VARIANT_AUTO, out=None, arg_out=None, row_divisor=None,
+                    edge_ids=None, arg_sentinel: Optional[int] = None, bias=None, addend=None,
+                    addend_scale: float = 1.0, relu: bool = False, spmm_flags: int = 0):
+    """Fused all-gather + SpMM (isplib_b200_spmm_csr_gather).  x_gathered: the LOCAL [world *
+    slice_rows, K] buffer whose own slice already holds this step's rows; peer_x / peer_ready: the
+    device addresses (ints) of every rank's buffer / ready words as mapped into this process."""
+    code = REDUCE_CODE[reduce] if isinstance(reduce, str) else int(reduce)
+    assert x_gathered.is_cuda and x_gathered.dtype == torch.float32 and x_gathered.dim() == 2 and x_gathered.stride(1) == 1
+    M, nnz = plan.m, plan.nnz
+    N, K = x_gathered.shape
+    is_arg = code in (MAX, MIN)
+    if out is None:
+        out = torch.empty((M, K), dtype=torch.float32, device=x_gathered.device)
+    if is_arg and arg_out is None:
+        arg_out = torch.empty((M, K), dtype=torch.int64, device=x_gathered.device)
+    ws_bytes = ctypes.c_size_t(0)
+    check(lib().isplib_b200_spmm_workspace_bytes(ctypes.byref(plan.info), K, code, ctypes.byref(ws_bytes)),
+          "spmm_workspace_bytes")
+    ws = _dev_bytes(ws_bytes.value, x_gathered.device)
+    gd = GatherDesc()
+    gd.world, gd.rank, gd.n_groups, gd.copy_ctas = world, rank, plan.n_groups, copy_ctas
+    px = (ctypes.c_void_p * world)(*[int(v) for v in peer_x])
+    pr = (ctypes.c_void_p * world)(*[int(v) for v in peer_ready])
+    og = (ctypes.c_int32 * world)(*[int(v) for v in owner_group])
+    gie = (ctypes.c_int64 * plan.n_groups)(*plan.group_item_end)
+    gd.peer_x, gd.peer_ready, gd.owner_group, gd.group_item_end = px, pr, og, gie
+    gd.slice_rows = slice_rows
+    gd.flags, gd.status, gd.epoch = flags.data_ptr(), status.data_ptr(), int(epoch) & 0xFFFFFFFF
+    epi = Epilogue()
+    epi.bias = None if bias is None else bias.data_ptr()
+    if addend is not None:
+        epi.addend = addend.data_ptr()
+        epi.ld_addend = addend.stride(0) if addend.size(0) > 1 else max(K, addend.stride(0))
+        epi.addend_scale = float(addend_scale)
+    ldx = x_gathered.stride(0) if N > 1 else max(K, x_gathered.stride(0))
+    ldo = out.stride(0) if M > 1 else max(K, out.stride(0))
+    st = lib().isplib_b200_spmm_csr_gather(
+        code, M, N, K, nnz, _p(rowptr32), _p(col32), _p(val), _p(x_gathered), ldx, _p(out), ldo,
+        _p(arg_out) if is_arg else None, ctypes.byref(plan.info), plan.ptr, _aligned_ptr(ws), ws_bytes.value,
+        variant, spmm_flags | (FLAG_RELU if relu else 0), _p(row_divisor), _p(edge_ids),
+        nnz if arg_sentinel is None else int(arg_sentinel), ctypes.byref(epi), ctypes.byref(gd), _stream(x_gathered.device))
+    check(st, "spmm_csr_gather")
+    return out, (arg_out if is_arg else None)
 
 
 def variant_names():

@@ -121,6 +121,7 @@ static int fill_params(SpmmParams& p, int reduce, int64_t m, int64_t n, int64_t 
     p.has_epilogue = (flags & ISPLIB_FLAG_RELU) ? 1 : 0;
     p.arg_col = nullptr;
     p.arg_val = nullptr;
+    memset(&p.gather, 0, sizeof(p.gather));
     return ISPLIB_SUCCESS;
 }
 
@@ -177,6 +178,89 @@ extern "C" int isplib_b200_spmm_csr_fused(int reduce, int64_t m, int64_t n, int6
     return launch_spmm(reduce, p, nnz, variant, (cudaStream_t)stream);
 }
 
+// --------------------------------------------------------------------------------------
+// row-partitioned multi-GPU forward: the SpMM pulls the peers' slices of x itself
+// --------------------------------------------------------------------------------------
+extern "C" int isplib_b200_spmm_csr_gather(int reduce, int64_t m, int64_t n, int64_t k, int64_t nnz,
+                                           const int32_t* rowptr, const int32_t* col, const float* val,
+                                           float* x, int64_t ldx, float* out, int64_t ldo,
+                                           int64_t* arg_out,
+                                           const isplib_b200_plan_info* info, const void* plan_dev,
+                                           void* workspace, size_t workspace_bytes,
+                                           int variant, int flags, const float* row_divisor,
+                                           const int32_t* edge_ids, int64_t arg_sentinel,
+                                           const isplib_b200_epilogue* epi,
+                                           const isplib_b200_gather_desc* gd, isplib_stream_t stream) {
+    if (!gd) return ISPLIB_INVALID_ARG;
+    if (gd->world < 1 || gd->world > kMaxPeers + 1 || gd->rank < 0 || gd->rank >= gd->world) return ISPLIB_INVALID_ARG;
+    if (gd->n_groups < 1 || gd->n_groups > kMaxArrivalGroups || !gd->owner_group || !gd->group_item_end) return ISPLIB_INVALID_ARG;
+    if (gd->slice_rows < 0 || gd->slice_rows * (int64_t)gd->world != n) return ISPLIB_INVALID_ARG;
+    if (gd->world > 1 && (!gd->peer_x || !gd->peer_ready || !gd->flags || !gd->status)) return ISPLIB_INVALID_ARG;
+    if (ldx % 4 != 0 || (reinterpret_cast<uintptr_t>(x) & 15u) != 0) return ISPLIB_INVALID_ARG;   // slices move as 16-byte vectors
+    SpmmParams p;
+    int st = fill_params(p, reduce, m, n, k, nnz, rowptr, col, val, x, ldx, out, ldo, arg_out, info,
+                         plan_dev, workspace, workspace_bytes, flags, row_divisor, edge_ids, arg_sentinel);
+    if (st) return st;
+    if (m == 0 || k == 0) return ISPLIB_SUCCESS;
+    if ((st = apply_epilogue_args(p, reduce, k, flags, epi))) return st;
+
+    GatherParams& G = p.gather;
+    G.n_groups = gd->n_groups;
+    G.copy_ctas = gd->world > 1 ? (gd->copy_ctas > 0 ? gd->copy_ctas : 32) : 0;
+    G.epoch = gd->epoch;
+    G.flags = gd->flags;
+    G.status = gd->status;
+    G.my_rank = gd->rank;
+    G.slice_vec4 = gd->slice_rows * ldx / 4;
+    G.ready_local = gd->world > 1 ? (unsigned*)gd->peer_ready[gd->rank] : nullptr;
+    for (int g = 0; g < kMaxArrivalGroups; ++g) {
+        const int64_t e = g < gd->n_groups ? gd->group_item_end[g] : info->num_items;
+        if (e < 0 || e > info->num_items || (g > 0 && g < gd->n_groups && e < gd->group_item_end[g - 1])) return ISPLIB_INVALID_ARG;
+        G.group_item_end[g] = (int)e;
+    }
+    if (gd->group_item_end[gd->n_groups - 1] != info->num_items) return ISPLIB_FAIL;   // not this plan's groups
+    // pull order: group after group, inside a group by ring distance from this rank, so that at any
+    // moment the ranks read from DIFFERENT peers (every NVSwitch port carries one stream)
+    int ns = 0;
+    if (gd->owner_group[gd->rank] != 0) return ISPLIB_INVALID_ARG;
+    for (int g = 1; g < gd->n_groups; ++g) {
+        for (int d = 1; d < gd->world; ++d) {
+            const int o = (gd->rank + d) % gd->world;
+            if (gd->owner_group[o] != g) continue;
+            if (!gd->peer_x[o] || !gd->peer_ready[o]) return ISPLIB_INVALID_ARG;
+            const size_t off = (size_t)o * (size_t)gd->slice_rows * (size_t)ldx;
+            G.src[ns] = (const float*)gd->peer_x[o] + off;
+            G.dst[ns] = x + off;
+            G.ready_peer[ns] = (unsigned*)gd->peer_ready[o];
+            G.src_group[ns] = g;
+            G.src_rank[ns] = o;
+            ++ns;
+        }
+    }
+    for (int o = 0; o < gd->world; ++o)
+        if (o != gd->rank && (gd->owner_group[o] < 1 || gd->owner_group[o] >= gd->n_groups)) return ISPLIB_INVALID_ARG;
+    G.n_src = ns;
+    if (ns != gd->world - 1) return ISPLIB_INVALID_ARG;
+
+    if (variant == ISPLIB_VARIANT_AUTO) {
+        // lean kernels only, one launch: 64-wide K tiles (grid.y) when they make the slab of x
+        // L2-resident, else untiled; 16-byte lean body for rows that are not 32-byte aligned
+        const double x_bytes = (double)n * (double)k * 4.0;
+        const int cands[3][2] = {{5, (x_bytes > 96.0 * 1024 * 1024 && k > 64 && (double)n * 256.0 <= 64.0 * 1024 * 1024) ? 64 : 0},
+                                 {5, 0}, {6, 0}};
+        variant = -1;
+        for (int c = 0; c < 3 && variant < 0; ++c)
+            for (int v = 0; v < variant_count(); ++v) {
+                const VariantDesc* d = variant_desc(v);
+                if (d->method == cands[c][0] && d->kt == cands[c][1] && !d->seq && d->warps == 4 &&
+                    spmm_variant_supported(v, reduce, k, ldx, ldo, x, out)) { variant = v; break; }
+            }
+        if (variant < 0) return ISPLIB_NO_OPT_IMPL;
+    }
+    if (!spmm_variant_supported(variant, reduce, k, ldx, ldo, x, out)) return ISPLIB_NO_OPT_IMPL;
+    return launch_spmm(reduce, p, nnz, variant, (cudaStream_t)stream);
+}
+
 extern "C" int isplib_b200_spmm_csr(int reduce, int64_t m, int64_t n, int64_t k, int64_t nnz,
                                     const int32_t* rowptr, const int32_t* col, const float* val,
                                     const float* x, int64_t ldx, float* out, int64_t ldo,
@@ -222,6 +306,7 @@ extern "C" int isplib_b200_spmm_autotune(int reduce, int64_t m, int64_t n, int64
         if (!spmm_variant_supported(v, reduce, k, ldx, ldo, x, out)) continue;
         const VariantDesc* d = variant_desc(v);
         if (d->method == 1 && !tune_bulk) continue;   // see the variant table
+        if (d->method == 7) continue;                 // reference-order parity mode, never a candidate
         // default candidate set = the family that wins on every measured shape (U=4; 4 warps/CTA
         // for every K tile, 8 warps only untiled); the rest only with ISPLIB_B200_TUNE_ALL=1
         if (d->method == 0 && !tune_all && !(d->unroll == 4 && (d->warps == 4 || d->kt == 0))) continue;

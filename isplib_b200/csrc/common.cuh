@@ -80,6 +80,31 @@ static inline PlanLayout plan_layout(int64_t m, int64_t nnz, int32_t seg_len) {
 
 enum PlanCounter { PC_ITEMS = 0, PC_SPLIT_ROWS = 1, PC_SPLIT_ITEMS = 2, PC_MAX_DEG = 3, PC_EMPTY = 4 };
 
+// ---- fused all-gather of x (row-partitioned multi-GPU forward) -------------------------
+// The lean SpMM kernels can pull the peers' slices of x over NVLink THEMSELVES while they
+// multiply: the first `copy_ctas` CTAs of the grid copy slice after slice from peer memory into the
+// local gathered x (group by group, in arrival order) and bump flags[g] when group g has landed;
+// the work items are ordered by arrival group (grouped plan) and an item of group g > 0 starts
+// only when flags[g] says its rows are there.  One launch = gather + SpMM, the transfer of group
+// g + 1 overlaps the multiply of group g, no NCCL call and no extra kernel in between.
+constexpr int kMaxPeers = 15;           // world <= 16
+constexpr int kMaxArrivalGroups = 8;
+struct GatherParams {
+    const float* src[kMaxPeers];        // peer slice (peer-mapped device address), in pull order
+    float* dst[kMaxPeers];              // where that slice lands in the local gathered x
+    unsigned* ready_peer[kMaxPeers];    // that peer's ready words: we store `epoch` at [my_rank]
+    int src_group[kMaxPeers];           // arrival group (1-based) of each pulled slice, non-decreasing
+    int src_rank[kMaxPeers];            // the peer's rank (index into ready_local)
+    int group_item_end[kMaxArrivalGroups];   // items [end[g-1], end[g]) gather from group g
+    unsigned* flags;                    // [kMaxArrivalGroups] local arrival counters, monotonic
+    unsigned* ready_local;              // [world]: ready_local[q] == epoch <=> peer q's slice of this step is readable
+    unsigned* status;                   // set to 1 if a wait timed out (a peer never arrived)
+    long long slice_vec4;               // 16-byte vectors per slice
+    unsigned epoch;                     // 1, 2, 3 ... per launch; flags[g] reaches epoch * copy_ctas
+    int n_src, n_groups, copy_ctas;     // copy_ctas == 0: plain kernel, nothing below is touched
+    int my_rank;
+};
+
 // ---- forward kernel parameter block --------------------------------------------------
 struct SpmmParams {
     const int32_t* __restrict__ rowptr;
@@ -112,6 +137,7 @@ struct SpmmParams {
     int has_epilogue;                   // bias || addend || ISPLIB_FLAG_RELU
     int32_t* __restrict__ arg_col;      // [m, k] stride ldo or null: col[arg] (-1 where no entry won)
     float* __restrict__ arg_val;        // [m, k] stride ldo or null: val[arg]
+    GatherParams gather;                // fused all-gather of x (copy_ctas == 0: off)
 };
 
 enum Op { OP_SUM = 0, OP_MAX = 1, OP_MIN = 2 };

@@ -145,6 +145,216 @@ extern "C" int isplib_b200_plan_build(int64_t m, int64_t nnz, const int32_t* row
     return ISPLIB_SUCCESS;
 }
 
+// ---------------------------------------------------------------------------------
+// grouped plan (row-partitioned multi-GPU forward, fused with the gather of X)
+// ---------------------------------------------------------------------------------
+// The columns of a rank's row block are laid out owner-major ([P * Rc] gathered rows of X).  Owner
+// ranges ("runs") are assigned to ARRIVAL GROUPS: group 0 = the rank's own slice, group g > 0 =
+// the peers whose slices land g-th.  Segments never cross a run boundary, and the work items are
+// ordered by group (all items of group 0 first, ...), so the kernel can start on a group as soon as
+// its slices have landed while later groups are still in flight.  Partial slots of split rows stay in
+// edge order, so the in-kernel merge (finish_item) is unchanged and max/min/arg stay bit-exact.
+namespace isplib {
+
+constexpr int kMaxRuns = 20;     // world <= 16: at most world + 1 contiguous owner runs
+constexpr int kMaxGroups = 8;
+struct RunTable { int n_runs; int n_groups; int start[kMaxRuns]; int group[kMaxRuns]; };
+
+__device__ __forceinline__ int lower_bound_i32(const int32_t* __restrict__ a, int lo, int hi, int key) {
+    while (lo < hi) {
+        const int mid = (lo + hi) >> 1;
+        if (a[mid] < key) lo = mid + 1; else hi = mid;
+    }
+    return lo;
+}
+
+// one thread per row: per-group item counts (group-major matrix cnt[g * m + row]), the row's total
+__global__ void plan_grouped_count_kernel(int m, int seg_len, const int32_t* __restrict__ rowptr,
+                                          const int32_t* __restrict__ col, const RunTable rt,
+                                          int32_t* __restrict__ grp_cnt, int32_t* __restrict__ seg_cnt,
+                                          int32_t* __restrict__ part_cnt, unsigned long long* __restrict__ counters) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    int deg = 0, pc = 0;
+    if (i < m) {
+        const int rb = rowptr[i], re = rowptr[i + 1];
+        deg = re - rb;
+        int cnt[kMaxGroups];
+#pragma unroll
+        for (int g = 0; g < kMaxGroups; ++g) cnt[g] = 0;
+        int total = 0, lo = rb;
+        for (int j = 0; j < rt.n_runs; ++j) {
+            const int hi = (j + 1 < rt.n_runs) ? lower_bound_i32(col, lo, re, rt.start[j + 1]) : re;
+            const int c = (hi - lo + seg_len - 1) / seg_len;
+#pragma unroll
+            for (int g = 0; g < kMaxGroups; ++g) if (g == rt.group[j]) cnt[g] += c;
+            total += c;
+            lo = hi;
+        }
+        if (total == 0) { cnt[0] = 1; total = 1; }     // an empty row still owns one item: it writes the row
+#pragma unroll
+        for (int g = 0; g < kMaxGroups; ++g) if (g < rt.n_groups) grp_cnt[(size_t)g * m + i] = cnt[g];
+        seg_cnt[i] = total;
+        pc = total > 1 ? total : 0;
+        part_cnt[i] = pc;
+    } else if (i == m) {
+        seg_cnt[i] = 0;
+        part_cnt[i] = 0;
+        grp_cnt[(size_t)rt.n_groups * m] = 0;          // scan sentinel: total item count lands here
+    }
+    typedef cub::BlockReduce<int, 256> BR;
+    __shared__ typename BR::TempStorage tmp;
+    const int max_deg = BR(tmp).Reduce(deg, cub::Max());
+    __syncthreads();
+    const int n_split = BR(tmp).Sum(pc > 0 ? 1 : 0);
+    __syncthreads();
+    const int n_empty = BR(tmp).Sum((i < m && deg == 0) ? 1 : 0);
+    if (threadIdx.x == 0) {
+        atomicMax(&counters[PC_MAX_DEG], (unsigned long long)max_deg);
+        if (n_split) atomicAdd(&counters[PC_SPLIT_ROWS], (unsigned long long)n_split);
+        if (n_empty) atomicAdd(&counters[PC_EMPTY], (unsigned long long)n_empty);
+    }
+}
+
+// one thread per row: emit the row's items, group by group in the item array, edge order in the slots
+__global__ void plan_grouped_fill_kernel(int m, int seg_len, const int32_t* __restrict__ rowptr,
+                                         const int32_t* __restrict__ col, const RunTable rt,
+                                         const int32_t* __restrict__ grp_off, const int32_t* __restrict__ seg_off,
+                                         const int32_t* __restrict__ part_off, int4* __restrict__ item_desc,
+                                         unsigned long long* __restrict__ counters) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= m) return;
+    const int rb = rowptr[i], re = rowptr[i + 1];
+    const int total = seg_off[i + 1] - seg_off[i];
+    const int pb = part_off[i];
+    int pos[kMaxGroups];
+#pragma unroll
+    for (int g = 0; g < kMaxGroups; ++g) pos[g] = (g < rt.n_groups) ? grp_off[(size_t)g * m + i] : 0;
+    if (re == rb) {
+        item_desc[pos[0]] = make_int4(i, rb, rb, -1);
+    } else {
+        int s = 0, lo = rb;
+        for (int j = 0; j < rt.n_runs; ++j) {
+            const int hi = (j + 1 < rt.n_runs) ? lower_bound_i32(col, lo, re, rt.start[j + 1]) : re;
+            const int g = rt.group[j];
+            for (int eb = lo; eb < hi; eb += seg_len) {
+                int w = 0;
+#pragma unroll
+                for (int q = 0; q < kMaxGroups; ++q) if (q == g) w = pos[q]++;
+                item_desc[w] = make_int4(i, eb, min(hi, eb + seg_len), total > 1 ? pb + s : -1);
+                ++s;
+            }
+            lo = hi;
+        }
+    }
+    if (i == m - 1) {
+        counters[PC_ITEMS] = (unsigned long long)grp_off[(size_t)rt.n_groups * m];
+        counters[PC_SPLIT_ITEMS] = (unsigned long long)part_off[m];
+    }
+}
+
+static inline int64_t grouped_wmax(int64_t m, int64_t nnz, int32_t S, int n_runs) {
+    return m * (int64_t)n_runs + nnz / S + 1;
+}
+
+}  // namespace isplib
+
+using namespace isplib;
+
+extern "C" int isplib_b200_plan_grouped_bytes(int64_t m, int64_t nnz, int32_t seg_len, int32_t n_runs, size_t* bytes) {
+    if (!bytes || m < 0 || nnz < 0 || n_runs < 1 || n_runs > kMaxRuns) return ISPLIB_INVALID_ARG;
+    if (m >= INT32_MAX - 1 || nnz >= INT32_MAX - 64) return ISPLIB_INVALID_ARG;
+    const int32_t S = effective_seg_len(seg_len);
+    const PlanLayout L = plan_layout(m, nnz, seg_len);
+    const int64_t wmax = grouped_wmax(m, nnz, S, n_runs);
+    if (wmax >= INT32_MAX || (int64_t)kMaxGroups * m + 1 >= INT32_MAX) return ISPLIB_INVALID_ARG;
+    size_t scan_tmp = 0;
+    cub::DeviceScan::ExclusiveSum(nullptr, scan_tmp, (const int32_t*)nullptr, (int32_t*)nullptr, (int)(kMaxGroups * m + 1));
+    size_t o = align_up(L.off_item_desc + (size_t)wmax * 16, 256);          // item_desc sized for the grouped bound
+    o = align_up(o + (size_t)(m + 1) * 4, 256);                             // seg_cnt
+    o = align_up(o + (size_t)(m + 1) * 4, 256);                             // part_cnt
+    o = align_up(o + (size_t)(kMaxGroups * m + 1) * 4, 256);                // grp_cnt
+    o = align_up(o + (size_t)(kMaxGroups * m + 1) * 4, 256);                // grp_off
+    o = align_up(o + scan_tmp, 256);
+    *bytes = o;
+    return ISPLIB_SUCCESS;
+}
+
+extern "C" int isplib_b200_plan_build_grouped(int64_t m, int64_t nnz, const int32_t* rowptr, const int32_t* col,
+                                              int32_t seg_len, int32_t n_runs, const int32_t* run_start,
+                                              const int32_t* run_group, int32_t n_groups,
+                                              void* plan_dev, size_t plan_dev_bytes, isplib_b200_plan_info* info,
+                                              int64_t* group_item_end, isplib_stream_t stream_) {
+    cudaStream_t stream = (cudaStream_t)stream_;
+    if (!info || !run_start || !run_group || !group_item_end || m < 0 || nnz < 0 || (m > 0 && !rowptr) || (nnz > 0 && !col))
+        return ISPLIB_INVALID_ARG;
+    if (n_groups < 1 || n_groups > kMaxGroups) return ISPLIB_INVALID_ARG;
+    size_t need = 0;
+    int st = isplib_b200_plan_grouped_bytes(m, nnz, seg_len, n_runs, &need);
+    if (st) return st;
+    if (!plan_dev || plan_dev_bytes < need) return ISPLIB_NOT_ENOUGH_MEM;
+    if ((reinterpret_cast<uintptr_t>(plan_dev) & 255u) != 0) return ISPLIB_INVALID_ARG;
+    RunTable rt;
+    rt.n_runs = n_runs;
+    rt.n_groups = n_groups;
+    for (int j = 0; j < n_runs; ++j) {
+        if (run_group[j] < 0 || run_group[j] >= n_groups) return ISPLIB_INVALID_ARG;
+        if (j > 0 && run_start[j] < run_start[j - 1]) return ISPLIB_INVALID_ARG;
+        rt.start[j] = run_start[j];
+        rt.group[j] = run_group[j];
+    }
+    const int32_t S = effective_seg_len(seg_len);
+    const PlanLayout L = plan_layout(m, nnz, seg_len);
+    const int64_t wmax = grouped_wmax(m, nnz, S, n_runs);
+    char* base = (char*)plan_dev;
+    unsigned long long* counters = (unsigned long long*)(base + L.off_counters);
+    int32_t* seg_off = (int32_t*)(base + L.off_seg_off);
+    int32_t* part_off = (int32_t*)(base + L.off_part_off);
+    int4* item_desc = (int4*)(base + L.off_item_desc);
+    size_t o = align_up(L.off_item_desc + (size_t)wmax * 16, 256);
+    const size_t persistent = o;
+    int32_t* seg_cnt = (int32_t*)(base + o);  o = align_up(o + (size_t)(m + 1) * 4, 256);
+    int32_t* part_cnt = (int32_t*)(base + o); o = align_up(o + (size_t)(m + 1) * 4, 256);
+    int32_t* grp_cnt = (int32_t*)(base + o);  o = align_up(o + (size_t)(kMaxGroups * m + 1) * 4, 256);
+    int32_t* grp_off = (int32_t*)(base + o);  o = align_up(o + (size_t)(kMaxGroups * m + 1) * 4, 256);
+    void* scan_tmp = base + o;
+    size_t scan_bytes = plan_dev_bytes - o;
+
+    ISPLIB_CUDA_TRY(cudaMemsetAsync(counters, 0, 8 * sizeof(int64_t), stream));
+    const int threads = 256;
+    plan_grouped_count_kernel<<<(int)((m + 1 + threads - 1) / threads), threads, 0, stream>>>(
+        (int)m, S, rowptr, col, rt, grp_cnt, seg_cnt, part_cnt, counters);
+    ISPLIB_LAUNCH_CHECK();
+    const int n_grp = (int)((int64_t)n_groups * m + 1);
+    ISPLIB_CUDA_TRY(cub::DeviceScan::ExclusiveSum(scan_tmp, scan_bytes, grp_cnt, grp_off, n_grp, stream));
+    ISPLIB_CUDA_TRY(cub::DeviceScan::ExclusiveSum(scan_tmp, scan_bytes, seg_cnt, seg_off, (int)(m + 1), stream));
+    ISPLIB_CUDA_TRY(cub::DeviceScan::ExclusiveSum(scan_tmp, scan_bytes, part_cnt, part_off, (int)(m + 1), stream));
+    if (m > 0) {
+        plan_grouped_fill_kernel<<<(int)((m + threads - 1) / threads), threads, 0, stream>>>(
+            (int)m, S, rowptr, col, rt, grp_off, seg_off, part_off, item_desc, counters);
+        ISPLIB_LAUNCH_CHECK();
+    }
+    unsigned long long h[8] = {0};
+    int32_t ends[kMaxGroups] = {0};
+    ISPLIB_CUDA_TRY(cudaMemcpyAsync(h, counters, sizeof(h), cudaMemcpyDeviceToHost, stream));
+    for (int g = 0; g < n_groups; ++g)
+        ISPLIB_CUDA_TRY(cudaMemcpyAsync(&ends[g], grp_off + (size_t)(g + 1) * m, 4, cudaMemcpyDeviceToHost, stream));
+    ISPLIB_CUDA_TRY(cudaStreamSynchronize(stream));
+    for (int g = 0; g < n_groups; ++g) group_item_end[g] = m > 0 ? (int64_t)ends[g] : 0;
+
+    info->m = m;
+    info->nnz = nnz;
+    info->seg_len = S;
+    info->reserved = 0;
+    info->num_items = m > 0 ? (int64_t)h[PC_ITEMS] : 0;
+    info->num_split_rows = (int64_t)h[PC_SPLIT_ROWS];
+    info->num_split_items = (int64_t)h[PC_SPLIT_ITEMS];
+    info->max_degree = (int64_t)h[PC_MAX_DEG];
+    info->num_empty_rows = (int64_t)h[PC_EMPTY];
+    info->plan_bytes = (uint64_t)persistent;
+    if (info->num_items > wmax) return ISPLIB_FAIL;
+    return ISPLIB_SUCCESS;
+}
+
 extern "C" int isplib_b200_spmm_workspace_bytes(const isplib_b200_plan_info* info, int64_t k,
                                                 int reduce, size_t* bytes) {
     if (reduce < 0 || reduce > 3) return ISPLIB_NO_OPT_IMPL;

@@ -73,6 +73,14 @@ static const VariantDesc kVariants[] = {
     {"lean128/w4/kfull", 6, 4, 4, 0, 0},
     {"lean128/w4/kt64", 6, 4, 4, 64, 0},
     {"lean128/w4/kt64/seq", 6, 4, 4, 64, 1},
+    // method 7: REFERENCE-ORDER sum.  The general kernel with scalar lanes (one lane group = the
+    // whole warp, so a warp takes ONE entry per step) adds a row's terms in CSR order with one FMA
+    // each -- exactly the recurrence of the CPU kernel it replaces (z[i,k] = fma(a_e, y[col_e,k],
+    // z[i,k]), e ascending; oracle/fusedmm_oracle.c).  With a plan whose seg_len >= the maximum
+    // degree (no row is split) sum / mean are BIT-IDENTICAL to the CPU path, which pins that the
+    // fast variants differ from it by re-association only.  4x the load instructions: a parity
+    // mode (never auto-selected, not in the autotune set), not a performance variant.
+    {"ordered/w4/u4/kfull", 7, 4, 4, 0, 0},
 };
 int variant_count() { return (int)(sizeof(kVariants) / sizeof(kVariants[0])); }
 const VariantDesc* variant_desc(int v) {
@@ -161,6 +169,7 @@ bool spmm_variant_supported(int variant, int reduce, int64_t k, int64_t ldx, int
         if (d->kt > 0 && d->kt >= k) return false;
         return tw >= 16 && tw <= 128 && tw % 4 == 0 && k % tw == 0;
     }
+    if (d->method == 7) return true;   // scalar lanes: any K, any alignment
     if (d->method == 3) {   // 32-byte gathers
         if (!vec8_ok(k, ldx, x)) return false;
         if (d->kt > 0 && (d->kt >= k || d->kt % 8 != 0)) return false;
@@ -200,11 +209,12 @@ int spmm_variant_default(int reduce, int64_t n, int64_t k, int64_t ldx, int64_t 
     const double x_bytes = (double)n * (double)k * 4.0;
     const bool slab64 = (double)n * 64.0 * 4.0 <= 64.0 * MB;
     const bool additive = (reduce == ISPLIB_REDUCE_SUM || reduce == ISPLIB_REDUCE_MEAN);
-    // max / min: the lean kernel (80 registers) is 3-20 % behind seg/* while x is L2-resident and
-    // ahead once x is far beyond L2 (Amazon-shape K=200: 36.0 vs 40.9 ms)
-    if (additive || x_bytes > 512.0 * MB) {
+    // max / min: since round 2 the 32-byte lean body is compiled for 32 warps/SM (64 registers) and
+    // leads from K = 64 up (Reddit-shape K=128 4.56 vs 5.0 ms, K=256 9.3 vs 10.1 ms for seg/*;
+    // profiles/r2_kbench_max_minb.txt); narrow rows (K < 64) stay with seg/* (K=32: 1.34 vs 1.46 ms)
+    if (additive || k >= 64 || x_bytes > 512.0 * MB) {
         int v = -1;
-        if (additive && x_bytes > 96.0 * MB && k > 64 && slab64) v = find_variant(5, 4, 4, 64, 1);   // one launch per 64-wide slab
+        if (x_bytes > 96.0 * MB && k > 64 && slab64) v = find_variant(5, 4, 4, 64, additive || k > 128 ? 1 : 0);   // 64-wide slabs of x, L2-resident
         else v = find_variant(5, 4, 4, 0);
         if (v >= 0 && spmm_variant_supported(v, reduce, k, ldx, ldo, x, out)) return v;
         v = find_variant(5, 4, 4, 0);
@@ -233,6 +243,7 @@ int launch_spmm(int reduce, const SpmmParams& base, int64_t nnz, int variant, cu
 
     SpmmParams p = base;
     int vec = pick_vec(p.k, p.ldx, p.x);
+    if (d->method == 7) vec = 1;
     if (d->method == 3) {
         if (!vec8_ok(p.k, p.ldx, p.x)) return ISPLIB_NO_OPT_IMPL;
         vec = 8;
@@ -288,10 +299,12 @@ int launch_spmm(int reduce, const SpmmParams& base, int64_t nnz, int variant, cu
         else kern = seg_kernel_min(t, d->unroll, partial);
     }
     if (!kern) return ISPLIB_NO_OPT_IMPL;
+    // fused all-gather: only the lean kernels carry the copy role, and the grid must be ONE launch
+    if (p.gather.copy_ctas > 0 && ((d->method != 5 && d->method != 6) || d->seq)) return ISPLIB_NO_OPT_IMPL;
 
     const int warps = d->warps;
     const dim3 block(warps * 32);
-    const dim3 grid((unsigned)((p.num_items + warps - 1) / warps), (unsigned)t.ntiles);
+    const dim3 grid((unsigned)((p.num_items + warps - 1) / warps) + (unsigned)max(p.gather.copy_ctas, 0), (unsigned)t.ntiles);
     if (t.ntiles > 65535) return ISPLIB_NO_OPT_IMPL;
     if (p.num_split_rows > 0) {
         // arrival counters of the split rows, one set per K tile (self-resetting, cleared

@@ -673,65 +673,126 @@ spmm_bulk_kernel(const __grid_constant__ SpmmParams p) {
 // 0, so no extra traffic) and keeps them out of the stores.  max/min carry VEC more registers
 // (arg): 80 with VEC = 8 (24 warps/SM), 56 with VEC = 4 (36 warps/SM).
 // ------------------------------------------------------------------------------------
-template <int OP> __device__ __forceinline__ float pick2(float a, float b) {
-    // NaN-dropping max / min (FMNMX): a NaN product never wins, like the strict compare of the oracle
-    return OP == OP_MAX ? fmaxf(a, b) : fminf(a, b);
+// ------------------------------------------------------------------------------------
+// fused all-gather (GatherParams, common.cuh): the copy role and the consumer-side wait
+// ------------------------------------------------------------------------------------
+__device__ __forceinline__ unsigned long long global_timer_ns() {
+    unsigned long long t;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+    return t;
 }
+__device__ __forceinline__ unsigned ld_acquire_sys(const unsigned* p) {
+    unsigned v;
+    asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+    return v;
+}
+__device__ __forceinline__ unsigned ld_acquire_gpu(const unsigned* p) {
+    unsigned v;
+    asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+    return v;
+}
+__device__ __forceinline__ void st_release_sys(unsigned* p, unsigned v) {
+    asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
+constexpr unsigned long long kGatherTimeoutNs = 4000000000ull;   // 4 s: a peer that never shows up must not hang the GPU
 
-// max / min in the lean body (the r1 body spent 4 instructions per gathered element: FMUL,
-// FSETP, 2 selects, and was issue-bound in the L2 regime).  Here the U entries of a step are
-// folded with FMUL + FMNMX only, and ONE compare + 2 selects per accumulator and step record the
-// step (its first entry id) in which the running extremum strictly improved.  `resolve_step_winner`
-// then re-reads the <= U entries of that one step per accumulator and takes the first whose product
-// equals the extremum -- the smallest edge id, and that entry's own product bit for bit (so the
-// -0.0 / +0.0 tie of the oracle's strict scan is reproduced too).  NOVAL: val == NULL (SAGE / GIN
-// drop the values), no multiply and no value shuffle at all.
-template <int OP, int VEC, int NG, int U, bool NOVAL>
-__device__ __forceinline__ void resolve_step_winner(const SpmmParams& p, const char* xlane, unsigned ldxb, int ee,
-                                                    float (&acc)[VEC], int (&arg)[VEC]) {
-#pragma unroll
-    for (int v = 0; v < VEC; ++v) {
-        const int base = arg[v];
-        if (base == kNoArg) continue;
-        float tt[U];
-#pragma unroll
-        for (int u = 0; u < U; ++u) {
-            const int e = base + u * NG;
-            if (u == 0 || e < ee) {
-                const unsigned cc = (unsigned)__ldg(p.col + e);
-                const float xx = __ldg(reinterpret_cast<const float*>(xlane + (unsigned long long)cc * ldxb) + v);
-                tt[u] = NOVAL ? xx : __fmul_rn(__ldg(p.val + e), xx);
-            } else {
-                tt[u] = OP == OP_MAX ? -INFINITY : INFINITY;   // never equal to a finite extremum
-            }
-        }
-        const float m = acc[v];
-        int win = base;
-        float wv = tt[0];
-        // first u whose product equals the extremum (u = 0 always does for exactly tracked entries)
-        bool found = (tt[0] == m);
-#pragma unroll
-        for (int u = 1; u < U; ++u) {
-            const bool hit = !found && (tt[u] == m);
-            if (hit) { win = base + u * NG; wv = tt[u]; }
-            found = found || hit;
-        }
-        arg[v] = win;
-        acc[v] = wv;
+// spin until *word has reached `target` (wrap-safe); false on timeout
+template <bool SYS>
+__device__ __forceinline__ bool wait_reached(const unsigned* word, unsigned target, unsigned* status) {
+    const unsigned long long t0 = global_timer_ns();
+    unsigned ns = 32;
+    while (true) {
+        const unsigned v = SYS ? ld_acquire_sys(word) : ld_acquire_gpu(word);
+        if ((int)(v - target) >= 0) return true;
+        __nanosleep(ns);
+        if (ns < 1024) ns <<= 1;
+        if (global_timer_ns() - t0 > kGatherTimeoutNs) { atomicExch(status, 1u); return false; }
     }
 }
 
+// The first copy_ctas CTAs: pull the peers' slices, group after group, 8 x 16 bytes in flight per
+// thread (NVLink latency is a few microseconds: bytes in flight, not threads, set the rate).
+static __device__ __noinline__ void gather_copy_role(const GatherParams& G) {
+    const int cta = blockIdx.x, nc = G.copy_ctas, tid = threadIdx.x, nt = blockDim.x;
+    // my own slice of this step was written by earlier work on this stream: tell every peer
+    if (cta == 0 && tid < G.n_src) st_release_sys(G.ready_peer[tid] + G.my_rank, G.epoch);
+    const long long n = G.slice_vec4;
+    const long long chunk = ((n + nc - 1) / nc + 7) & ~7ll;
+    const long long b = min(n, (long long)cta * chunk), e = min(n, b + chunk);
+    int s = 0;
+    for (int g = 1; g < G.n_groups; ++g) {
+        for (; s < G.n_src && G.src_group[s] == g; ++s) {
+            if (tid == 0) wait_reached<true>(G.ready_local + G.src_rank[s], G.epoch, G.status);
+            __syncthreads();
+            const float4* __restrict__ src = reinterpret_cast<const float4*>(G.src[s]);
+            float4* __restrict__ dst = reinterpret_cast<float4*>(G.dst[s]);
+            for (long long i = b + tid; i < e; i += (long long)nt * 8) {
+                float4 v[8];
+#pragma unroll
+                for (int u = 0; u < 8; ++u) {
+                    const long long j = i + (long long)u * nt;
+                    if (j < e) v[u] = __ldcg(src + j);          // L2 only: the line is not reused by this SM
+                }
+#pragma unroll
+                for (int u = 0; u < 8; ++u) {
+                    const long long j = i + (long long)u * nt;
+                    if (j < e) dst[j] = v[u];
+                }
+            }
+        }
+        __threadfence();                 // this thread's stores are visible device-wide ...
+        __syncthreads();                 // ... for every thread of the CTA ...
+        if (tid == 0) atomicAdd(G.flags + g, 1u);   // ... before the arrival is published
+    }
+}
+
+// consumer side: the arrival group of a work item, and the wait for it
+__device__ __forceinline__ void gather_wait_for_item(const GatherParams& G, int item, int lane) {
+    int g = 0;
+    while (g < G.n_groups - 1 && item >= G.group_item_end[g]) ++g;
+    if (g > 0) {
+        if (lane == 0) wait_reached<false>(G.flags + g, G.epoch * (unsigned)G.copy_ctas, G.status);
+        __syncwarp();
+    }
+}
+
+// NOVAL (max / min only): val == NULL (SAGE / GIN drop the values) -- no multiply and no value
+// shuffle at all in the hot loop.
+//
+// Tried in round 2 and removed again (profiles/r2_kbench_max_stepid.txt): tracking only the STEP in
+// which the running extremum improved (FMUL + FMNMX per element and one compare + 2 selects per
+// accumulator and step: 2.25 instead of 4 instructions per element) and re-reading that step's U
+// entries at the end of the item to find the winning entry.  Bit-exact, but the re-read costs
+// VEC x U scattered 4-byte loads per lane and item = +25 % L2 sectors on a kernel that is bound by
+// L2 gather bandwidth, not by issue slots: Reddit-shape K=128 max 5.4 -> 6.3 ms (lean256),
+// 5.1 -> 5.3-5.6 ms (lean128).
+#ifndef ISPLIB_LEANMAX_MINB
+// CTAs/SM the 32-byte max/min body is compiled for.  8 (64 registers, ~50 bytes of spills outside
+// the gather loop, 32 warps/SM) beats 6 (80 registers, 24 warps/SM) and 7 on Reddit-shape:
+// K=128 4.56 vs 4.93 / 4.75 ms, K=256 9.28 vs 9.67 / 9.41 ms (profiles/r2_kbench_max_minb.txt)
+#define ISPLIB_LEANMAX_MINB 8
+#endif
 template <int OP, int VEC, int G, bool RAGGED, bool NOVAL>
-__global__ void __launch_bounds__(128, VEC == 8 ? (OP == OP_SUM ? 8 : 6) : (OP == OP_SUM ? 10 : 9))
+__global__ void __launch_bounds__(128, VEC == 8 ? (OP == OP_SUM ? 8 : ISPLIB_LEANMAX_MINB) : (OP == OP_SUM ? 10 : 9))
 spmm_lean_kernel(const __grid_constant__ SpmmParams p) {
     constexpr int U = 4;
     constexpr int NG = 32 / G;
     constexpr unsigned FULL = 0xffffffffu;
     const int lane = threadIdx.x & 31;
-    const int item = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    int bx = blockIdx.x;
+    if (p.gather.copy_ctas > 0) {
+        // fused all-gather: the first CTAs of the grid pull the peers' slices of x over NVLink
+        if (bx < p.gather.copy_ctas) {
+            if (blockIdx.y == 0) gather_copy_role(p.gather);
+            return;
+        }
+        bx -= p.gather.copy_ctas;
+    }
+    const int item = bx * (blockDim.x >> 5) + (threadIdx.x >> 5);
     if (item >= p.num_items) return;
     const int4 desc = __ldg(p.item_desc + item);
     const int eb = desc.y, ee = desc.z;
+    if (p.gather.copy_ctas > 0) gather_wait_for_item(p.gather, item, lane);   // rows of this item's arrival group landed?
     const int g = lane / G;
     const bool lane_ok = !RAGGED || (lane % G) * VEC < p.tile_w;
     const int k0 = (blockIdx.y + p.tile_base) * p.tile_w + (lane_ok ? (lane % G) * VEC : 0);
@@ -778,29 +839,19 @@ spmm_lean_kernel(const __grid_constant__ SpmmParams p) {
                     const unsigned cc = __shfl_sync(FULL, c, t + u * NG + g);
                     load_vec<VEC>(reinterpret_cast<const float*>(xlane + (unsigned long long)cc * ldxb), xv[u]);
                 }
-                if constexpr (OP == OP_SUM) {
 #pragma unroll
-                    for (int u = 0; u < U; ++u) {
-                        const float aa = __shfl_sync(FULL, a, t + u * NG + g);
+                for (int u = 0; u < U; ++u) {
+                    float aa = 1.f;
+                    if constexpr (!NOVAL) aa = __shfl_sync(FULL, a, t + u * NG + g);
 #pragma unroll
-                        for (int v = 0; v < VEC; ++v) acc[0][v] = fmaf(aa, xv[u][v], acc[0][v]);
-                    }
-                } else {
-                    float m[VEC];
-#pragma unroll
-                    for (int u = 0; u < U; ++u) {
-                        float aa = 1.f;
-                        if constexpr (!NOVAL) aa = __shfl_sync(FULL, a, t + u * NG + g);
-#pragma unroll
-                        for (int v = 0; v < VEC; ++v) {
+                    for (int v = 0; v < VEC; ++v) {
+                        if constexpr (OP == OP_SUM) {
+                            acc[0][v] = fmaf(aa, xv[u][v], acc[0][v]);
+                        } else {
                             const float tt = NOVAL ? xv[u][v] : __fmul_rn(aa, xv[u][v]);
-                            m[v] = (u == 0) ? tt : pick2<OP>(m[v], tt);
+                            if (better<OP>(tt, acc[0][v])) { acc[0][v] = tt; arg[0][v] = e0 + t + u * NG + g; }
                         }
                     }
-                    const int base = e0 + t + g;   // first entry of this lane group's step
-#pragma unroll
-                    for (int v = 0; v < VEC; ++v)
-                        if (better<OP>(m[v], acc[0][v])) { acc[0][v] = m[v]; arg[0][v] = base; }
                 }
             }
         } else {
@@ -820,7 +871,6 @@ spmm_lean_kernel(const __grid_constant__ SpmmParams p) {
                             acc[0][v] = fmaf(aa, xv[v], acc[0][v]);
                         } else {
                             const float tt = NOVAL ? xv[v] : __fmul_rn(aa, xv[v]);
-                            // an exactly tracked entry: resolve_step_winner finds it at u = 0
                             if (better<OP>(tt, acc[0][v])) { acc[0][v] = tt; arg[0][v] = e0 + idx; }
                         }
                     }
@@ -828,7 +878,6 @@ spmm_lean_kernel(const __grid_constant__ SpmmParams p) {
             }
         }
     }
-    if constexpr (OP != OP_SUM) resolve_step_winner<OP, VEC, NG, U, NOVAL>(p, xlane, ldxb, ee, acc[0], arg[0]);
     const int koff[1] = {k0};
     const bool kok[1] = {lane_ok};
     finish_item<OP, VEC, G, 1>(p, lane, desc.x, eb, ee, desc.w, koff, kok, acc, arg);

@@ -305,7 +305,7 @@ DenseOperand dense_operand(const Tensor& mat_in, bool cacheable) {
     {
         std::lock_guard<std::mutex> lk(g_pad_mu);
         for (auto& e : g_pad_cache)
-            if (e.id.matches(key) && e.padded.size(0) == N && e.padded.size(1) == Kp) return {e.padded, Kp};
+            if (e.id.matches(key) && e.padded.size(0) == N && e.padded.size(1) == Kp) return {e.padded.narrow(1, 0, K), Kp};
     }
     Tensor padded = at::constant_pad_nd(mat_in, {0, Kp - K}, 0);
     if (cacheable) {
@@ -318,7 +318,7 @@ DenseOperand dense_operand(const Tensor& mat_in, bool cacheable) {
         e.padded = padded;
         g_pad_cache.push_back(std::move(e));
     }
-    return {padded, Kp};
+    return {padded.narrow(1, 0, K), Kp};
 }
 
 // ---------------------------------------------------------------------------------------

@@ -25,6 +25,16 @@ One process per GPU (``torchrun``), ``torch.distributed`` over NCCL/NVLink.
   backward (max/min): local arg-scatter into a zeroed [P*R, K] partial, then
   reduce-scatter(sum).
 
+* ``mode="fused"`` (the default on CUDA with more than one rank): NO collective call at all.  The
+  rank's whole row block is ONE CSR over the owner-major gathered columns with a *grouped* plan
+  (work items ordered by the arrival group of their columns), X lives in a double-buffered
+  symmetric-memory allocation, and ONE kernel (``isplib_b200_spmm_csr_gather``) pulls the peers'
+  slices over NVLink with its first CTAs while the others multiply -- each item as soon as the
+  slices of its group have landed.  Peers are told "my slice is readable" by a release store into
+  their ready words at kernel start; nobody waits for a barrier kernel.  max/min/mean need no
+  cross-block merge any more (a row is one CSR row again), so results equal the 1-GPU kernel's.
+  ``mode="nccl"`` keeps the all-gather + two-block path below.
+
 The block SpMM is injectable (``block_spmm``) so the partitioning / merge logic can be
 tested on CPU with gloo; the default is the CUDA C ABI (isplib_b200.capi) and there is no
 CPU fallback in the product path.
@@ -169,6 +179,80 @@ def split_row_block_by_owner(rowptr: torch.Tensor, col: torch.Tensor, val: Optio
     return blocks, full_deg, R
 
 
+def owner_groups(world: int, rank: int, n_remote_groups: int):
+    """Arrival group of every owner's slice for `rank`: 0 for its own, 1..G for the peers by ring
+    distance (rank+1 first), split as evenly as possible.  Ring order makes the ranks read from
+    different peers at any moment."""
+    n_remote = world - 1
+    G = max(1, min(n_remote_groups, n_remote)) if n_remote > 0 else 0
+    groups = [0] * world
+    for d in range(1, world):
+        groups[(rank + d) % world] = 1 + ((d - 1) * G) // n_remote
+    return groups, G + 1
+
+
+def group_runs(groups, slice_rows: int):
+    """Contiguous owner runs of equal group in absolute (owner-major) column order:
+    (run_start[], run_group[]) for isplib_b200_plan_build_grouped."""
+    starts, grp = [], []
+    for o, g in enumerate(groups):
+        if not grp or grp[-1] != g:
+            starts.append(o * slice_rows)
+            grp.append(g)
+    return starts, grp
+
+
+class _PeerBuffers:
+    """The double-buffered gathered-X allocation of one feature width, visible to every rank.
+
+    Layout (fp32 words): [buf 0: world*Rc*Kp][buf 1: world*Rc*Kp][ready words: 2 x 64 uint32].
+    Real ranks: torch symmetric memory (CUDA VMM peer mappings over NVLink), rendezvoused once per
+    width.  ``emulated``: a dict shared by the emulated ranks of ONE process (tests on one GPU): the
+    "peers" are ordinary local tensors, the kernel's pulls are local copies."""
+
+    READY_WORDS = 64
+
+    def __init__(self, world, rank, Rc, K, device, group, emulated=None):
+        self.world, self.rank, self.Rc, self.K = world, rank, Rc, K
+        self.Kp = (K + 7) // 8 * 8
+        self.buf_words = world * Rc * self.Kp
+        n_words = 2 * self.buf_words + 2 * self.READY_WORDS
+        if emulated is None:
+            import torch.distributed._symmetric_memory as symm
+            g = group if group is not None else dist.group.WORLD
+            try:
+                if not symm.is_symm_mem_enabled_for_group(g.group_name):
+                    symm.enable_symm_mem_for_group(g.group_name)
+            except Exception:
+                pass                               # newer torch enables it inside rendezvous()
+            self.t = symm.empty(n_words, dtype=torch.float32, device=device)
+            self.t.zero_()
+            torch.cuda.synchronize(device)
+            self.hdl = symm.rendezvous(self.t, g)
+            dist.barrier(group=g)                  # nobody publishes into ready words that are not zeroed yet
+            self.ptrs = [int(p) for p in self.hdl.buffer_ptrs]
+        else:
+            ts = emulated.setdefault(("bufs", K), [torch.zeros(n_words, dtype=torch.float32, device=device)
+                                                   for _ in range(world)])
+            self.t = ts[rank]
+            self.all = ts
+            self.ptrs = [int(t.data_ptr()) for t in ts]
+        self.bufs = [self.t[b * self.buf_words:(b + 1) * self.buf_words].view(world * Rc, self.Kp) for b in (0, 1)]
+
+    def peer_x(self, b):
+        return [p + 4 * b * self.buf_words for p in self.ptrs]
+
+    def peer_ready(self, b):
+        return [p + 4 * (2 * self.buf_words + b * self.READY_WORDS) for p in self.ptrs]
+
+    def ready_words(self, b):
+        off = 2 * self.buf_words + b * self.READY_WORDS
+        return self.t[off:off + self.READY_WORDS].view(torch.int32)
+
+    def own_slice(self, b):
+        return self.bufs[b][self.rank * self.Rc:(self.rank + 1) * self.Rc, :self.K]
+
+
 def _cuda_block_spmm(reduce_code, block: CsrBlock, x, out, arg_out, flags, row_divisor, arg_sentinel, variant=-1):
     from . import capi
     if block.plan is None:
@@ -183,10 +267,15 @@ class RowPartitionedSpMM:
 
     def __init__(self, rowptr: torch.Tensor, col: torch.Tensor, value: Optional[torch.Tensor], n_cols: int,
                  group=None, device=None, block_spmm: Optional[Callable] = None, overlap: bool = True,
-                 pipelined: Optional[bool] = None, balance: str = "rows", row_bounds=None, col_bounds=None):
+                 pipelined: Optional[bool] = None, balance: str = "nnz", row_bounds=None, col_bounds=None,
+                 mode: Optional[str] = None, emulate=None):
         self.group = group
-        self.world = dist.get_world_size(group) if dist.is_initialized() else 1
-        self.rank = dist.get_rank(group) if dist.is_initialized() else 0
+        if emulate is not None:       # (world, rank, shared dict): several ranks emulated in one process
+            self.world, self.rank, self._emulated = int(emulate[0]), int(emulate[1]), emulate[2]
+        else:
+            self.world = dist.get_world_size(group) if dist.is_initialized() else 1
+            self.rank = dist.get_rank(group) if dist.is_initialized() else 0
+            self._emulated = None
         self.m = rowptr.numel() - 1
         self.n = int(n_cols)
         self.nnz = int(col.numel())
@@ -228,6 +317,30 @@ class RowPartitionedSpMM:
             self.owner_blocks = [mv(b) for b in blocks]
         self.k_chunk = None        # feature-chunk width of the all-gather/SpMM pipeline (None = auto)
         self._gather_bufs = {}     # persistent all-gather receive buffers, keyed by (K, dtype, device)
+        # fused gather + SpMM (one kernel, no collective): the default wherever it can run
+        if mode is None:
+            mode = os.environ.get("ISPLIB_B200_DIST_MODE") or (
+                "fused" if (self.world > 1 and self.device.type == "cuda" and block_spmm is None and not self.pipelined)
+                else "nccl")
+        if mode not in ("fused", "nccl"):
+            raise ValueError(f"mode must be 'fused' or 'nccl', got {mode!r}")
+        self.mode = mode
+        if mode == "fused":
+            r0, r1 = self.row_bounds[self.rank], self.row_bounds[self.rank + 1]
+            e0, e1 = int(rowptr[r0]), int(rowptr[r1])
+            rp = torch.zeros(self.R + 1, dtype=torch.int64, device=rowptr.device)
+            rp[1:r1 - r0 + 1] = rowptr[r0 + 1:r1 + 1] - e0
+            rp[r1 - r0 + 1:] = e1 - e0
+            pos = slice_position(col[e0:e1].to(torch.int64), self.col_bounds, self.Rc)   # monotone per row: owner-major keeps the order
+            self.full = CsrBlock(rp.to(torch.int32).to(self.device), pos.to(torch.int32).to(self.device),
+                                 None if value is None else value[e0:e1].contiguous().to(self.device),
+                                 torch.arange(e0, e1, dtype=torch.int32, device=self.device))
+            n_remote_groups = int(os.environ.get("ISPLIB_B200_DIST_GROUPS", "3"))
+            self.owner_group, self.n_groups = owner_groups(self.world, self.rank, n_remote_groups)
+            self.copy_ctas = int(os.environ.get("ISPLIB_B200_DIST_COPY_CTAS", "64"))
+            self._peer = {}            # K -> _PeerBuffers
+            self._epoch = {}           # K -> launches so far on that buffer set
+            self._gflags = {}          # K -> (flags uint32[8], status uint32[1])
 
     # rows this rank owns (without padding)
     @property
@@ -287,6 +400,9 @@ class RowPartitionedSpMM:
             self.block_spmm(inner, self.local, x_slice, out, arg, 0, div, self.nnz, self.variant)
             return out, arg
 
+        if self.mode == "fused":
+            return self._forward_fused(x_slice, code, out, arg)
+
         if self.pipelined:
             return self._forward_pipelined(x_slice, inner, div, out, arg)
 
@@ -320,6 +436,60 @@ class RowPartitionedSpMM:
         self.block_spmm(inner, self.local, x_slice, out, arg, 0, None, self.nnz, self.variant)
         self.block_spmm(inner, self.remote, gathered, out, arg, FLAG_ACCUMULATE, div, self.nnz, self.variant)
         return out, arg
+
+    def _fused_plan(self):
+        from . import capi
+        if self.full.plan is None:
+            starts, grp = group_runs(self.owner_group, self.Rc)
+            self.full.plan = capi.GroupedPlan(self.full.rowptr, self.full.col, starts, grp, self.n_groups)
+        return self.full.plan
+
+    def peer_buffers(self, K: int) -> "_PeerBuffers":
+        """The symmetric gathered-X allocation for feature width K (collective on first use per K)."""
+        pb = self._peer.get(K)
+        if pb is None:
+            pb = _PeerBuffers(self.world, self.rank, self.Rc, K, self.device, self.group, self._emulated)
+            self._peer[K] = pb
+            self._epoch[K] = 0
+            self._gflags[K] = (torch.zeros(8, dtype=torch.int32, device=self.device),
+                               torch.zeros(1, dtype=torch.int32, device=self.device))
+        return pb
+
+    def next_input_slice(self, K: int) -> torch.Tensor:
+        """The [Rc, K] view the NEXT forward of width K reads this rank's slice from: a producer that
+        writes there (instead of handing forward() a separate tensor) saves the staging copy."""
+        pb = self.peer_buffers(K)
+        return pb.own_slice((self._epoch[K] + 1) & 1)
+
+    def _forward_fused(self, x_slice, code, out, arg, bias=None, relu=False):
+        from . import capi
+        K = x_slice.size(1)
+        pb = self.peer_buffers(K)
+        self._epoch[K] += 1
+        epoch = self._epoch[K]
+        b = epoch & 1
+        own = pb.own_slice(b)
+        if x_slice.data_ptr() != own.data_ptr():
+            own.copy_(x_slice)                     # staging copy into the peer-visible buffer (Rc x K)
+        flags, status = self._gflags[K]
+        if self._emulated is not None:
+            # one process plays every rank in turn: the "peers" published their slices before this call
+            pb.ready_words(b)[: self.world] = epoch
+        full = self.full
+        capi.spmm_csr_gather(code, full.rowptr, full.col, full.val, pb.bufs[b][:, :K], self._fused_plan(),
+                             world=self.world, rank=self.rank, peer_x=pb.peer_x(b), peer_ready=pb.peer_ready(b),
+                             owner_group=self.owner_group, slice_rows=self.Rc, flags=flags, status=status,
+                             epoch=epoch, copy_ctas=self.copy_ctas, variant=self.variant, out=out, arg_out=arg,
+                             edge_ids=full.edge_ids, arg_sentinel=self.nnz, bias=bias, relu=relu)
+        return out, arg
+
+    def check_status(self):
+        """Raises if a fused-gather kernel gave up waiting for a peer (4 s timeout inside the kernel).
+        Synchronises; call it outside hot loops."""
+        if self.mode == "fused":
+            for K, (_, status) in self._gflags.items():
+                if int(status.item()) != 0:
+                    raise RuntimeError(f"isplib_b200: fused gather (K={K}) timed out waiting for a peer's slice")
 
     def _forward_pipelined(self, x_slice, inner, div, out, arg):
         """X slices travel peer-to-peer over NVLink by the copy engines (torch symmetric memory,
@@ -370,6 +540,8 @@ class RowPartitionedSpMM:
 
     def launches_per_forward(self) -> int:
         """how many of OUR kernels one forward launches (for bench.py's gpu_launches)."""
+        if self.world > 1 and self.mode == "fused":
+            return 1                      # gather + SpMM are one kernel
         n = 1 if self.world == 1 else 2   # one spmm_seg_kernel per column block (x feature chunks)
         return n
 
@@ -410,11 +582,12 @@ class DistSpMM:
     machinery as the forward), max/min through a local arg-scatter + reduce-scatter."""
 
     def __init__(self, rowptr, col, value, n_cols, group=None, device=None, block_spmm=None,
-                 arg_backward=None, overlap=True, pipelined=None, balance="rows"):
+                 arg_backward=None, overlap=True, pipelined=None, balance="nnz", mode=None, emulate=None):
         self.rowptr, self.col, self.value = rowptr, col, value
         self.m, self.n = rowptr.numel() - 1, int(n_cols)
         self.group, self.device = group, device
-        self._kw = dict(group=group, device=device, block_spmm=block_spmm, overlap=overlap, pipelined=pipelined)
+        self._kw = dict(group=group, device=device, block_spmm=block_spmm, overlap=overlap, pipelined=pipelined,
+                        mode=mode, emulate=emulate)
         self.fwd = RowPartitionedSpMM(rowptr, col, value, n_cols, balance=balance, **self._kw)
         self._bwd = {}
         self._arg_backward = arg_backward or _cuda_arg_backward

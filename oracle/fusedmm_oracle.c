@@ -237,6 +237,37 @@ int oracle_sddmm(const INDEXTYPE m, const INDEXTYPE k, const INDEXTYPE *rowptr, 
     return O_SUCCESS;
 }
 
+/* Not the reference's arithmetic: the same sum / mean with a float64 accumulator, rounded to
+ * float once at the end.  Used by the full-size tests as the yardstick for "how far is a given
+ * fp32 summation ORDER from the exact sum": the reference order (fusedMM_csr above) and the GPU
+ * kernel's order are both measured against it. */
+int oracle_spmm_sum_f64(const INDEXTYPE m, const INDEXTYPE k, const VALUETYPE *val /* nullable */,
+                        const INDEXTYPE *indx, const INDEXTYPE *rowptr, const VALUETYPE *y,
+                        const int mean, VALUETYPE *z)
+{
+#pragma omp parallel
+    {
+        double acc[1024];
+#pragma omp for schedule(dynamic, 16)
+        for (INDEXTYPE i = 0; i < m; ++i) {
+            for (INDEXTYPE k0 = 0; k0 < k; k0 += 1024) {
+                const INDEXTYPE kw = (k - k0 < 1024) ? (k - k0) : 1024;
+                for (INDEXTYPE kk = 0; kk < kw; ++kk) acc[kk] = 0.0;
+                for (INDEXTYPE j = rowptr[i]; j < rowptr[i + 1]; ++j) {
+                    const double a = val ? (double)val[j] : 1.0;
+                    const VALUETYPE *yr = y + indx[j] * k + k0;
+                    for (INDEXTYPE kk = 0; kk < kw; ++kk) acc[kk] += a * (double)yr[kk];
+                }
+                INDEXTYPE deg = rowptr[i + 1] - rowptr[i];
+                if (deg < 1) deg = 1;
+                for (INDEXTYPE kk = 0; kk < kw; ++kk)
+                    z[i * k + k0 + kk] = (VALUETYPE)(mean ? acc[kk] / (double)deg : acc[kk]);
+            }
+        }
+    }
+    return O_SUCCESS;
+}
+
 int oracle_num_threads(void)
 {
 #ifdef _OPENMP

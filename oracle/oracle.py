@@ -75,6 +75,8 @@ def load_c() -> ctypes.CDLL:
         lib.oracle_sddmm.restype = ctypes.c_int
         lib.oracle_sddmm.argtypes = [i64, i64, p, p, p, p, ctypes.c_int, p]
         lib.oracle_num_threads.restype = ctypes.c_int
+        lib.oracle_spmm_sum_f64.restype = ctypes.c_int
+        lib.oracle_spmm_sum_f64.argtypes = [i64, i64, p, p, p, p, ctypes.c_int, p]
         _lib = lib
     return _lib
 
@@ -240,6 +242,21 @@ def arg_backward(col, value, mat, arg, grad_out, N: int, need_grad_value: bool =
     if st != 0:
         raise RuntimeError(f"oracle_arg_backward status {st}")
     return grad_mat, grad_value
+
+
+def spmm_sum_f64(rowptr, col, value, mat, mean: bool = False) -> np.ndarray:
+    """sum / mean with a float64 accumulator (rounded to fp32 once): the yardstick both fp32
+    summation orders -- the reference's sequential one and the GPU kernel's -- are measured against."""
+    rowptr = np.ascontiguousarray(rowptr, dtype=np.int64)
+    col = np.ascontiguousarray(col, dtype=np.int64)
+    mat = np.ascontiguousarray(mat, dtype=np.float32)
+    val = None if value is None else np.ascontiguousarray(value, dtype=np.float32)
+    M, K = rowptr.shape[0] - 1, mat.shape[1]
+    out = np.zeros((M, K), dtype=np.float32)
+    st = load_c().oracle_spmm_sum_f64(M, K, _ptr(val), _ptr(col), _ptr(rowptr), _ptr(mat), 1 if mean else 0, _ptr(out))
+    if st != 0:
+        raise RuntimeError(f"oracle_spmm_sum_f64 status {st}")
+    return out
 
 
 def num_threads() -> int:

@@ -87,7 +87,7 @@ def test_variant_ids_quoted_in_profiles_and_bench_stay_valid():
 def test_variant_default_follows_the_measured_rules():
     """Shape-only default (no GPU needed, pointers are only checked for alignment):
     sum/mean -> lean 256-bit kernel, 64-wide sequential slabs once X exceeds L2; rows that are
-    only 16-byte aligned -> lean128; max/min -> seg while X can be L2-resident, lean256 beyond."""
+    only 16-byte aligned -> lean128; max/min -> the same lean kernels from K = 64 up, seg below."""
     from isplib_b200 import capi
     L = capi.lib()
     names = capi.variant_names()
@@ -103,6 +103,8 @@ def test_variant_default_follows_the_measured_rules():
     assert default(SUM, 2449029, 100) == "lean128/w4/kfull"          # rows only 16-byte aligned
     assert default(SUM, 2449029, 47, ldx=48) == "lean256/w4/kfull"   # padded odd width
     assert default(SUM, 1000, 64, x=ptr + 16) == "lean128/w4/kfull"  # operand only 16-byte aligned
-    assert default(MAX, 232965, 128).startswith("seg/")
+    assert default(MAX, 232965, 128) == "lean256/w4/kt64"            # since r2: lean body at 32 warps/SM
+    assert default(MAX, 232965, 256) == "lean256/w4/kt64/seq"
+    assert default(MAX, 232965, 32).startswith("seg/")               # narrow rows stay with seg/*
     assert default(MAX, 1569960, 200) == "lean256/w4/kfull"
     assert default(SUM, 1000, 7).startswith("seg/")                  # scalar rows

@@ -111,7 +111,8 @@ def test_arg_aux_outputs_and_streamed_backward(capi, oracle, K, reduce, with_val
             want_val = np.where(has, val[np.minimum(a, nnz - 1)], np.float32(1))
             assert np.array_equal(arg_val.cpu().numpy(), want_val)
         gx = capi.spmm_arg_backward_aux(arg_col, arg_val, torch.from_numpy(go).to(DEV), N)
-        np.testing.assert_allclose(gx.cpu().numpy(), rgx, rtol=1e-5, atol=1e-6)
+        # float atomics add in arrival order: tolerance, not bit-exact
+        np.testing.assert_allclose(gx.cpu().numpy(), rgx, rtol=1e-5, atol=1e-5)
 
 
 @pytest.mark.parametrize("K", [8, 32, 64, 104, 128, 256])
@@ -240,7 +241,7 @@ def test_op_arg_backward_through_aux_equals_general(isplib, oracle, reduce, with
         assert np.array_equal(out.detach().cpu().numpy(), ref) and np.array_equal(arg.cpu().numpy(), ref_arg)
         out.backward(torch.from_numpy(go).to(DEV))
         grads.append(x.grad.cpu().numpy())
-        np.testing.assert_allclose(grads[-1], rgx, rtol=1e-5, atol=1e-6)
+        np.testing.assert_allclose(grads[-1], rgx, rtol=1e-5, atol=1e-5)
 
 
 # ------------------------------------------------------------------- padded operands (zero copy)
@@ -285,21 +286,29 @@ def test_value_permutation_cache_survives_address_reuse(isplib, oracle):
     rp, co = torch.from_numpy(rowptr).to(DEV), torch.from_numpy(col).to(DEV)
     nnz = col.shape[0]
     go = rng.standard_normal((M, K)).astype(np.float32)
-    ptrs = set()
-    for step in range(4):
+    go_d = torch.from_numpy(go).to(DEV)
+
+    def one_step(step):
         val = rng.standard_normal(nnz).astype(np.float32)
-        v = torch.from_numpy(val).to(DEV)              # a fresh tensor each step, like learned edge weights
-        ptrs.add(v.data_ptr())
-        for reduce, op in (("sum", lambda x: torch.ops.isplib.fusedmm_spmm(None, rp, co, v, None, None, x)),
-                           ("mean", lambda x: torch.ops.isplib.fusedmm_spmm_mean(None, rp, co, v, None, None, None, x))):
+        v = torch.empty(nnz, device=DEV)            # a fresh tensor each step, like learned edge weights
+        v.copy_(torch.from_numpy(val))
+        ptr = v.data_ptr()
+        for reduce in ("sum", "mean"):
             x = torch.randn(N, K, device=DEV, requires_grad=True)
-            op(x).backward(torch.from_numpy(go).to(DEV))
+            if reduce == "sum":
+                out = torch.ops.isplib.fusedmm_spmm(None, rp, co, v, None, None, x)
+            else:
+                out = torch.ops.isplib.fusedmm_spmm_mean(None, rp, co, v, None, None, None, x)
+            out.backward(go_d)
             bw = oracle.spmm_backward_sum if reduce == "sum" else oracle.spmm_backward_mean
             want = bw(rowptr, col, val, go, N)
             np.testing.assert_allclose(x.grad.cpu().numpy(), want, rtol=1e-4, atol=1e-5,
                                        err_msg=f"step {step} {reduce}: stale permuted values")
-        del v
-    assert len(ptrs) < 4, "the allocator did not reuse the address; the test did not exercise the hazard"
+            del out, x
+        return ptr          # every local dies here: the block goes back to the caching allocator
+
+    ptrs = [one_step(i) for i in range(6)]
+    assert len(set(ptrs)) < len(ptrs), "the allocator never reused the address; the test did not exercise the hazard"
 
 
 def test_failed_graph_build_is_not_cached(isplib):
