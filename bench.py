@@ -262,18 +262,18 @@ def cpu_baseline_leg(args, budget_s):
             "ms": round(dt * 1e3, 2), "gflops": round(2.0 * g.nnz * K / dt / 1e9, 2)}
 
 
-def parity_check(torch, dist, world, g, x, out, arg, row0, reduce, n_rows=2000):
+def parity_check(torch, dist, world, g, x, out, arg, row0, row1, reduce, n_rows=2000):
     """Outside the timed region: `n_rows` sampled output rows (spread over all ranks' row ranges)
     of the output the timed kernel produced, against the CPU oracle on the same inputs
     (oracle/fusedmm_oracle.c, the restated fusedMM_csr driven like csrc/fusedmm.cpp:113-203).
     sum/mean: |a-b| <= 1e-6 + 1e-5|b|, elements that miss it must sit inside the
     condition-aware bound (conftest.assert_sum_close) and be < 0.1 %; max/min: bit-exact incl. arg.
-    `out` holds this rank's rows [row0, row0 + out.size(0)) (padding rows beyond M ignored)."""
+    `out` holds this rank's rows [row0, row1) (further rows of `out` are padding and ignored)."""
     import numpy as np
     from oracle import oracle
     dev = x.device
     M = g.m
-    r1 = min(M, row0 + out.size(0))
+    r1 = min(M, row1)
     per_rank = max(16, n_rows // world)
     gen = torch.Generator(device="cpu").manual_seed(1234 + row0)
     if r1 <= row0:
@@ -400,6 +400,72 @@ def configs_table(torch, capi, synth, g, rp32, co32, plan, peak):
     return rows
 
 
+def e2e_legs(torch, dev, run, x_host, out_hosts, in_shape, n_e2e, barrier):
+    """(serial ms, pipelined ms) per step of `run(x_dev) -> out_dev` fed from pinned host memory and
+    drained to pinned host memory every step.
+    serial: H2D -> run -> D2H on one stream.  pipelined: as a training / inference loop would
+    prefetch -- the H2D of step i+1 and the D2H of step i-1 run on their own streams (separate copy
+    engines) while step i computes; every step still moves its own X in and its own result out inside
+    the timed region."""
+    def serial_step(i):
+        xd = x_host[i & 1].to(dev, non_blocking=True)
+        o = run(xd)
+        out_hosts[0].copy_(o, non_blocking=True)
+    for i in range(3):
+        serial_step(i)
+    barrier()
+    a0, a1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    a0.record()
+    for i in range(n_e2e):
+        serial_step(i)
+    a1.record()
+    barrier()
+    ms_serial = a0.elapsed_time(a1) / n_e2e
+
+    cur = torch.cuda.current_stream(dev)
+    s_in, s_out = torch.cuda.Stream(dev), torch.cuda.Stream(dev)
+    xd = [torch.empty(in_shape, device=dev), torch.empty(in_shape, device=dev)]
+    ev_in = [torch.cuda.Event(), torch.cuda.Event()]
+    ev_used = [torch.cuda.Event(), torch.cuda.Event()]
+    ev_out = [torch.cuda.Event(), torch.cuda.Event()]
+    for e in ev_used + ev_out:
+        e.record(cur)
+
+    def h2d(i):
+        b = i & 1
+        with torch.cuda.stream(s_in):
+            s_in.wait_event(ev_used[b])           # the step that last read xd[b] is done
+            xd[b].copy_(x_host[b], non_blocking=True)
+            ev_in[b].record(s_in)
+
+    def run_pipeline(n):
+        h2d(0)
+        for i in range(n):
+            b = i & 1
+            if i + 1 < n:
+                h2d(i + 1)
+            cur.wait_event(ev_in[b])
+            o = run(xd[b])
+            ev_used[b].record(cur)
+            done = torch.cuda.Event()
+            done.record(cur)
+            with torch.cuda.stream(s_out):
+                s_out.wait_event(done)
+                s_out.wait_event(ev_out[b])        # previous D2H into out_hosts[b] finished
+                out_hosts[b].copy_(o, non_blocking=True)
+                o.record_stream(s_out)
+                ev_out[b].record(s_out)
+        cur.wait_stream(s_out)
+
+    run_pipeline(4)
+    barrier()
+    a0.record()
+    run_pipeline(n_e2e)
+    a1.record()
+    barrier()
+    return ms_serial, a0.elapsed_time(a1) / n_e2e
+
+
 def run_ours(args):
     import torch
     import torch.distributed as dist
@@ -442,7 +508,7 @@ def run_ours(args):
 
         def step(i):
             capi.spmm_csr(reduce, rp32, co32, g.value, xs[i & 1], plan, best, out=out, arg_out=arg)
-            return out, arg, 0
+            return out, arg, 0, M
         variant_name = capi.variant_names()[best]
         # one kernel per SpMM (split rows are merged inside it); */seq variants launch once per K tile
         launches_per_step = 1
@@ -451,18 +517,23 @@ def run_ours(args):
             launches_per_step = K // kt
         tune = {capi.variant_names()[v]: round(t, 3) for v, t in enumerate(times) if t >= 0}
     else:
-        op = RowPartitionedSpMM(g.rowptr, g.col, g.value, N, device=dev)
+        op = RowPartitionedSpMM(g.rowptr, g.col, g.value, N, device=dev)     # default: fused gather + SpMM, nnz-balanced rows
         c0, c1 = op.col_range()
         slices = [op.pad_x(x[c0:c1]) for x in xs]
         if args.variant is not None:
             op.variant = args.variant
+        elif op.mode == "fused":
+            op.variant = op.fused_variant(K, reduce)       # the id the C ABI's AUTO rule picks, so the line can name it
 
         def step(i):
             o, a = op.forward(slices[i & 1], reduce)
-            return o, a, op.row_range()[0]
+            return (o, a) + op.row_range()
         step(0)
         launches_per_step = op.launches_per_forward() * len(op._k_chunks(K))
-        variant_name = "auto" if args.variant is None else capi.variant_names()[args.variant]
+        inner = "auto" if op.variant < 0 else capi.variant_names()[op.variant]
+        if op.mode == "fused" and op.variant < 0:
+            inner = "lean256/w4/kt64 (K-tile arrival groups)"     # what RowPartitionedSpMM._tile_variant picked
+        variant_name = (f"fused-gather/{inner}" if op.mode == "fused" else inner)
         tune = {}
 
     def barrier():
@@ -499,9 +570,9 @@ def run_ours(args):
     parity = None
     if not args.no_parity:
         try:
-            o_chk, a_chk, row0 = step(0)
+            o_chk, a_chk, row0, row1 = step(0)
             torch.cuda.synchronize()
-            parity = parity_check(torch, dist, world, g, xs[0], o_chk, a_chk, row0, reduce)
+            parity = parity_check(torch, dist, world, g, xs[0], o_chk, a_chk, row0, row1, reduce)
         except Exception as ex:
             parity = {"ok": False, "error": repr(ex)[:300]}
 
@@ -515,75 +586,16 @@ def run_ours(args):
 
     # --- e2e: through the plugin (torch_sparse.matmul) with HOST buffers ---------------------
     e2e = None
+    phases = None
     if world == 1:
         adj = g.sparse_tensor()
         x_host = [x.cpu().pin_memory() for x in xs]
-        out_host = torch.empty((M, K), dtype=torch.float32).pin_memory()
-        out_hosts = [out_host, torch.empty((M, K), dtype=torch.float32).pin_memory()]
+        out_hosts = [torch.empty((M, K), dtype=torch.float32).pin_memory() for _ in range(2)]
+        n_e2e = max(4, min(args.steps, 20))
         iSpLibPlugin.patch_pyg()
         try:
-            # (a) serial: H2D -> matmul -> D2H on one stream
-            def e2e_step(i):
-                xd = x_host[i & 1].to(dev, non_blocking=True)
-                o = torch_sparse.matmul(adj, xd, reduce)
-                out_host.copy_(o, non_blocking=True)
-            for i in range(3):
-                e2e_step(i)
-            torch.cuda.synchronize()
-            n_e2e = max(4, min(args.steps, 20))
-            a0, a1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-            a0.record()
-            for i in range(n_e2e):
-                e2e_step(i)
-            a1.record()
-            torch.cuda.synchronize()
-            ms_serial = a0.elapsed_time(a1) / n_e2e
-
-            # (b) pipelined, as a training/inference loop would prefetch: the H2D of step i+1 and the
-            # D2H of step i-1 run on their own streams (separate copy engines) while step i computes.
-            # Every step still copies its own X in and its own result out inside the timed region.
-            cur = torch.cuda.current_stream(dev)
-            s_in, s_out = torch.cuda.Stream(dev), torch.cuda.Stream(dev)
-            xd = [torch.empty((N, K), device=dev), torch.empty((N, K), device=dev)]
-            ev_in = [torch.cuda.Event(), torch.cuda.Event()]
-            ev_used = [torch.cuda.Event(), torch.cuda.Event()]
-            ev_out = [torch.cuda.Event(), torch.cuda.Event()]
-            for e in ev_used + ev_out:
-                e.record(cur)
-
-            def h2d(i):
-                b = i & 1
-                with torch.cuda.stream(s_in):
-                    s_in.wait_event(ev_used[b])           # the SpMM that last read xd[b] is done
-                    xd[b].copy_(x_host[b], non_blocking=True)
-                    ev_in[b].record(s_in)
-
-            def run_pipeline(n):
-                h2d(0)
-                for i in range(n):
-                    b = i & 1
-                    if i + 1 < n:
-                        h2d(i + 1)
-                    cur.wait_event(ev_in[b])
-                    o = torch_sparse.matmul(adj, xd[b], reduce)
-                    ev_used[b].record(cur)
-                    done = torch.cuda.Event()
-                    done.record(cur)
-                    with torch.cuda.stream(s_out):
-                        s_out.wait_event(done)
-                        s_out.wait_event(ev_out[b])        # previous D2H into out_hosts[b] finished
-                        out_hosts[b].copy_(o, non_blocking=True)
-                        o.record_stream(s_out)
-                        ev_out[b].record(s_out)
-                cur.wait_stream(s_out)
-
-            run_pipeline(4)
-            torch.cuda.synchronize()
-            a0.record()
-            run_pipeline(n_e2e)
-            a1.record()
-            torch.cuda.synchronize()
-            ms_e2e = a0.elapsed_time(a1) / n_e2e
+            ms_serial, ms_e2e = e2e_legs(torch, dev, lambda xd: torch_sparse.matmul(adj, xd, reduce), x_host, out_hosts,
+                                         (N, K), n_e2e, torch.cuda.synchronize)
         finally:
             iSpLibPlugin.unpatch_pyg()
         e2e = {"value": round(b_alg / (ms_e2e * 1e-3) / 1e9, 2), "unit": "GB/s",
@@ -597,36 +609,29 @@ def run_ours(args):
                        "on the device (uploaded once per graph, as the plugin caches per graph)"}
         del adj
     else:
-        # N > 1: every rank copies ITS row slice of X from pinned host memory, runs the
-        # row-partitioned forward (all-gather + SpMM) and copies its slice of the result back
-        from isplib_b200.dist import DistSpMM  # noqa: F401  (same operator as the timed loop)
+        # N > 1: every rank copies ITS row slice of X from pinned host memory, runs the row-partitioned
+        # forward (gather + SpMM) and copies its slice of the result back -- the same two legs as N = 1
         x_host = [s_.cpu().pin_memory() for s_ in slices]
-        out_host = torch.empty((op.R, K), dtype=torch.float32).pin_memory()
-
-        def e2e_step(i):
-            xd = x_host[i & 1].to(dev, non_blocking=True)
-            o, _ = op.forward(xd, reduce)
-            out_host.copy_(o, non_blocking=True)
-        for i in range(3):
-            e2e_step(i)
-        barrier()
+        out_hosts = [torch.empty((op.R, K), dtype=torch.float32).pin_memory() for _ in range(2)]
         n_e2e = max(4, min(args.steps, 20))
-        a0, a1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        a0.record()
-        for i in range(n_e2e):
-            e2e_step(i)
-        a1.record()
-        barrier()
-        ms_e2e = a0.elapsed_time(a1) / n_e2e
-        t = torch.tensor([ms_e2e], device=dev, dtype=torch.float64)
+        ms_serial, ms_e2e = e2e_legs(torch, dev, lambda xd: op.forward(xd, reduce)[0], x_host, out_hosts,
+                                     (op.Rc, K), n_e2e, barrier)
+        t = torch.tensor([ms_e2e, ms_serial], device=dev, dtype=torch.float64)
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        ms_e2e = float(t.item())
+        ms_e2e, ms_serial = float(t[0]), float(t[1])
         e2e = {"value": round(b_alg / (ms_e2e * 1e-3) / 1e9, 2), "unit": "GB/s",
                "h2d_bytes_per_step": world * op.Rc * K * 4, "d2h_bytes_per_step": world * op.R * K * 4,
-               "ms_per_step": round(ms_e2e, 3),
+               "ms_per_step": round(ms_e2e, 3), "serial_ms_per_step": round(ms_serial, 3),
+               "serial_value": round(b_alg / (ms_serial * 1e-3) / 1e9, 2),
                "path": "isplib_b200.dist.RowPartitionedSpMM.forward per rank: X row slice from pinned host memory -> "
-                       "NCCL all-gather + local/remote block SpMM -> result slice back to pinned host memory, every "
-                       "step, one stream per rank; max over ranks"}
+                       "fused gather + SpMM kernel -> result slice back to pinned host memory, every step; `value` "
+                       "prefetches the next slice / drains the previous result on separate streams exactly like the "
+                       "N = 1 leg, `serial_*` is one stream per rank; max over ranks"}
+        # where the step goes: the same kernel with X already gathered (no pulls, no waits) vs the fused forward
+        try:
+            phases = op.phase_split(slices[0], reduce)
+        except Exception as ex:
+            phases = {"error": repr(ex)[:200]}
 
     # --- secondary: the other half of BASELINE.json's metric, a 2-layer GCN training epoch
     # (hidden 256) on the ogbn-products-shaped graph via patch_pyg(), same N GPUs ---------------
@@ -653,7 +658,8 @@ def run_ours(args):
         return 0
 
     peak, peak_src = peaks()
-    kernel_name = ("isplib::spmm_fused_gather_kernel" if variant_name.startswith("fused-gather")
+    kernel_name = ("isplib::spmm_lean_kernel (its first CTAs pull the peers' X slices over NVLink: gather + SpMM in one launch)"
+                   if variant_name.startswith("fused-gather")
                    else "isplib::spmm_lean_kernel" if variant_name.startswith("lean")
                    else "isplib::spmm_bulk_kernel" if variant_name.startswith("bulk")
                    else "isplib::spmm_seg_kernel")
@@ -688,8 +694,12 @@ def run_ours(args):
                    "reduce": reduce, "K": K, "variant": variant_name, "max_degree": g_max_degree,
                    "degree_gini": round(g_gini, 3),
                    "l2": "inputs 1.04 GB (col+val+X) > 126 MB L2 and two X buffers rotated between steps; no flush",
-                   "parallelism": "single GPU" if world == 1 else f"1-D row partition x{world}, X all-gathered per step "
-                                                                   f"over NCCL with local-block overlap"},
+                   "parallelism": "single GPU" if world == 1 else (
+                       f"1-D row partition x{world} (nnz-balanced), X pulled from the peers over NVLink INSIDE the SpMM "
+                       f"kernel (symmetric memory, {op.copy_ctas} copy CTAs, arrival groups = "
+                       f"{'K tiles' if op.variant < 0 else 'column owners'}), no collective"
+                       if op.mode == "fused" else
+                       f"1-D row partition x{world}, X all-gathered per step over NCCL with local-block overlap")},
         "gflops": round(2.0 * nnz * K / (ms_step * 1e-3) / 1e9, 1),
         "roofline": roofline,
         "gpu_launches": launches_per_step * args.steps,
@@ -703,6 +713,8 @@ def run_ours(args):
         line["autotune_ms"] = tune
     if e2e is not None:
         line["e2e"] = e2e
+    if phases is not None:
+        line["phases_ms"] = phases
     if gcn is not None:
         line["gcn_epoch"] = gcn
     if world == 1 and not args.no_cpu_baseline:

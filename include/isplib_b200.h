@@ -182,7 +182,7 @@ int isplib_b200_plan_build_grouped(int64_t m, int64_t nnz, const int32_t* rowptr
 typedef struct isplib_b200_gather_desc {
     int32_t world, rank;
     int32_t n_groups;               /* arrival groups incl. group 0 (the rank's own slice) */
-    int32_t copy_ctas;              /* CTAs that pull over NVLink; 0 = default (32) */
+    int32_t copy_ctas;              /* CTAs that pull over NVLink; 0 = default (64) */
     const void* const* peer_x;      /* [world] host array: rank q's gathered-x buffer as mapped into this
                                        process (symmetric memory); slice q = rows [q*slice_rows, ...) of
                                        EVERY buffer; peer_x[rank] == x */
@@ -193,8 +193,14 @@ typedef struct isplib_b200_gather_desc {
     uint32_t* status;               /* device uint32, zeroed once: 1 after a wait timed out (4 s) */
     uint32_t epoch;                 /* 1, 2, 3, ... one per launch on this (flags, ready words) set; the
                                        caller alternates two x buffers + ready-word sets by epoch parity */
-    uint32_t reserved;
+    uint32_t tile_mode;             /* 0: arrival groups = column owners (grouped plan, rows split per group).
+                                       1: arrival groups = the K TILES of the launch: every slice is pulled one
+                                          K tile at a time, the items of tile t wait for tile t; rows stay whole,
+                                          any plan works; n_groups / owner_group / group_item_end are ignored */
     const int64_t* group_item_end;  /* [n_groups] host array from isplib_b200_plan_build_grouped */
+    uint32_t flag_epoch;            /* launches on THIS flags array including this one (0 = same as epoch); a
+                                       flags array must always be used with the same copy_ctas and mode */
+    uint32_t reserved;
 } isplib_b200_gather_desc;
 /* x: the LOCAL gathered buffer [n = world * slice_rows, k] (row stride ldx, ldx % 4 == 0); its own
  * slice must hold this step's rows before the call (stream order); the other slices are overwritten.

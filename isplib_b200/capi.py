@@ -65,8 +65,8 @@ class GatherDesc(ctypes.Structure):
         ("world", ctypes.c_int32), ("rank", ctypes.c_int32), ("n_groups", ctypes.c_int32), ("copy_ctas", ctypes.c_int32),
         ("peer_x", ctypes.POINTER(ctypes.c_void_p)), ("peer_ready", ctypes.POINTER(ctypes.c_void_p)),
         ("owner_group", ctypes.POINTER(ctypes.c_int32)), ("slice_rows", ctypes.c_int64),
-        ("flags", ctypes.c_void_p), ("status", ctypes.c_void_p), ("epoch", ctypes.c_uint32), ("reserved", ctypes.c_uint32),
-        ("group_item_end", ctypes.POINTER(ctypes.c_int64)),
+        ("flags", ctypes.c_void_p), ("status", ctypes.c_void_p), ("epoch", ctypes.c_uint32), ("tile_mode", ctypes.c_uint32),
+        ("group_item_end", ctypes.POINTER(ctypes.c_int64)), ("flag_epoch", ctypes.c_uint32), ("reserved", ctypes.c_uint32),
     ]
 
 
@@ -200,8 +200,9 @@ class GroupedPlan(Plan):
         self.group_item_end = [int(v) for v in ends]
 
 
-def spmm_csr_gather(reduce, rowptr32, col32, val, x_gathered, plan: "GroupedPlan", *, world: int, rank: int,
-                    peer_x, peer_ready, owner_group, slice_rows: int, flags, status, epoch: int,
+def spmm_csr_gather(reduce, rowptr32, col32, val, x_gathered, plan, *, world: int, rank: int,
+                    peer_x, peer_ready, owner_group, slice_rows: int, flags, status, epoch: int, tile_mode: bool = False,
+                    flag_epoch: int = 0,
                     copy_ctas: int = 0, variant: int = VARIANT_AUTO, out=None, arg_out=None, row_divisor=None,
                     edge_ids=None, arg_sentinel: Optional[int] = None, bias=None, addend=None,
                     addend_scale: float = 1.0, relu: bool = False, spmm_flags: int = 0):
@@ -222,14 +223,17 @@ def spmm_csr_gather(reduce, rowptr32, col32, val, x_gathered, plan: "GroupedPlan
           "spmm_workspace_bytes")
     ws = _dev_bytes(ws_bytes.value, x_gathered.device)
     gd = GatherDesc()
-    gd.world, gd.rank, gd.n_groups, gd.copy_ctas = world, rank, plan.n_groups, copy_ctas
+    n_groups = 1 if tile_mode else plan.n_groups
+    gd.world, gd.rank, gd.n_groups, gd.copy_ctas = world, rank, n_groups, copy_ctas
+    gd.tile_mode = 1 if tile_mode else 0
     px = (ctypes.c_void_p * world)(*[int(v) for v in peer_x])
     pr = (ctypes.c_void_p * world)(*[int(v) for v in peer_ready])
     og = (ctypes.c_int32 * world)(*[int(v) for v in owner_group])
-    gie = (ctypes.c_int64 * plan.n_groups)(*plan.group_item_end)
+    gie = (ctypes.c_int64 * n_groups)(*(plan.group_item_end if not tile_mode else [plan.info.num_items]))
     gd.peer_x, gd.peer_ready, gd.owner_group, gd.group_item_end = px, pr, og, gie
     gd.slice_rows = slice_rows
     gd.flags, gd.status, gd.epoch = flags.data_ptr(), status.data_ptr(), int(epoch) & 0xFFFFFFFF
+    gd.flag_epoch = int(flag_epoch) & 0xFFFFFFFF
     epi = Epilogue()
     epi.bias = None if bias is None else bias.data_ptr()
     if addend is not None:

@@ -193,7 +193,9 @@ extern "C" int isplib_b200_spmm_csr_gather(int reduce, int64_t m, int64_t n, int
                                            const isplib_b200_gather_desc* gd, isplib_stream_t stream) {
     if (!gd) return ISPLIB_INVALID_ARG;
     if (gd->world < 1 || gd->world > kMaxPeers + 1 || gd->rank < 0 || gd->rank >= gd->world) return ISPLIB_INVALID_ARG;
-    if (gd->n_groups < 1 || gd->n_groups > kMaxArrivalGroups || !gd->owner_group || !gd->group_item_end) return ISPLIB_INVALID_ARG;
+    const bool tile_mode = gd->tile_mode != 0;
+    if (!tile_mode && (gd->n_groups < 1 || gd->n_groups > kMaxArrivalGroups || !gd->owner_group || !gd->group_item_end))
+        return ISPLIB_INVALID_ARG;
     if (gd->slice_rows < 0 || gd->slice_rows * (int64_t)gd->world != n) return ISPLIB_INVALID_ARG;
     if (gd->world > 1 && (!gd->peer_x || !gd->peer_ready || !gd->flags || !gd->status)) return ISPLIB_INVALID_ARG;
     if (ldx % 4 != 0 || (reinterpret_cast<uintptr_t>(x) & 15u) != 0) return ISPLIB_INVALID_ARG;   // slices move as 16-byte vectors
@@ -205,28 +207,36 @@ extern "C" int isplib_b200_spmm_csr_gather(int reduce, int64_t m, int64_t n, int
     if ((st = apply_epilogue_args(p, reduce, k, flags, epi))) return st;
 
     GatherParams& G = p.gather;
-    G.n_groups = gd->n_groups;
-    G.copy_ctas = gd->world > 1 ? (gd->copy_ctas > 0 ? gd->copy_ctas : 32) : 0;
+    G.n_groups = tile_mode ? 1 : gd->n_groups;
+    G.copy_ctas = gd->world > 1 ? (gd->copy_ctas > 0 ? gd->copy_ctas : 64) : 0;
     G.epoch = gd->epoch;
+    G.flag_epoch = gd->flag_epoch ? gd->flag_epoch : gd->epoch;
     G.flags = gd->flags;
     G.status = gd->status;
     G.my_rank = gd->rank;
     G.slice_vec4 = gd->slice_rows * ldx / 4;
+    G.slice_rows = gd->slice_rows;
+    G.row_vec4 = (int)(ldx / 4);
+    G.tile_vec4 = tile_mode ? -1 : 0;      // -1: launch_spmm fills in the variant's K tile
     G.ready_local = gd->world > 1 ? (unsigned*)gd->peer_ready[gd->rank] : nullptr;
-    for (int g = 0; g < kMaxArrivalGroups; ++g) {
-        const int64_t e = g < gd->n_groups ? gd->group_item_end[g] : info->num_items;
-        if (e < 0 || e > info->num_items || (g > 0 && g < gd->n_groups && e < gd->group_item_end[g - 1])) return ISPLIB_INVALID_ARG;
-        G.group_item_end[g] = (int)e;
+    if (!tile_mode) {
+        for (int g = 0; g < kMaxArrivalGroups; ++g) {
+            const int64_t e = g < gd->n_groups ? gd->group_item_end[g] : info->num_items;
+            if (e < 0 || e > info->num_items || (g > 0 && g < gd->n_groups && e < gd->group_item_end[g - 1])) return ISPLIB_INVALID_ARG;
+            G.group_item_end[g] = (int)e;
+        }
+        if (gd->group_item_end[gd->n_groups - 1] != info->num_items) return ISPLIB_FAIL;   // not this plan's groups
+        if (gd->owner_group[gd->rank] != 0) return ISPLIB_INVALID_ARG;
+        for (int o = 0; o < gd->world; ++o)
+            if (o != gd->rank && (gd->owner_group[o] < 1 || gd->owner_group[o] >= gd->n_groups)) return ISPLIB_INVALID_ARG;
     }
-    if (gd->group_item_end[gd->n_groups - 1] != info->num_items) return ISPLIB_FAIL;   // not this plan's groups
-    // pull order: group after group, inside a group by ring distance from this rank, so that at any
-    // moment the ranks read from DIFFERENT peers (every NVSwitch port carries one stream)
+    // pull order: (group after group,) by ring distance from this rank, so that at any moment the
+    // ranks read from DIFFERENT peers (every NVSwitch port carries one stream)
     int ns = 0;
-    if (gd->owner_group[gd->rank] != 0) return ISPLIB_INVALID_ARG;
-    for (int g = 1; g < gd->n_groups; ++g) {
+    for (int g = 1; g < (tile_mode ? 2 : gd->n_groups); ++g) {
         for (int d = 1; d < gd->world; ++d) {
             const int o = (gd->rank + d) % gd->world;
-            if (gd->owner_group[o] != g) continue;
+            if (!tile_mode && gd->owner_group[o] != g) continue;
             if (!gd->peer_x[o] || !gd->peer_ready[o]) return ISPLIB_INVALID_ARG;
             const size_t off = (size_t)o * (size_t)gd->slice_rows * (size_t)ldx;
             G.src[ns] = (const float*)gd->peer_x[o] + off;
@@ -237,8 +247,6 @@ extern "C" int isplib_b200_spmm_csr_gather(int reduce, int64_t m, int64_t n, int
             ++ns;
         }
     }
-    for (int o = 0; o < gd->world; ++o)
-        if (o != gd->rank && (gd->owner_group[o] < 1 || gd->owner_group[o] >= gd->n_groups)) return ISPLIB_INVALID_ARG;
     G.n_src = ns;
     if (ns != gd->world - 1) return ISPLIB_INVALID_ARG;
 

@@ -100,9 +100,18 @@ struct GatherParams {
     unsigned* ready_local;              // [world]: ready_local[q] == epoch <=> peer q's slice of this step is readable
     unsigned* status;                   // set to 1 if a wait timed out (a peer never arrived)
     long long slice_vec4;               // 16-byte vectors per slice
-    unsigned epoch;                     // 1, 2, 3 ... per launch; flags[g] reaches epoch * copy_ctas
+    unsigned epoch;                     // 1, 2, 3 ... per launch on this buffer set (ready words)
+    unsigned flag_epoch;                // launches on this flags array incl. this one: flags[g] reaches flag_epoch * copy_ctas
     int n_src, n_groups, copy_ctas;     // copy_ctas == 0: plain kernel, nothing below is touched
     int my_rank;
+    // tile mode (tile_vec4 > 0): the arrival groups are the K TILES of the launch instead of column
+    // owners -- every slice is pulled tile_vec4 16-byte vectors (one K tile) of each row at a time,
+    // flags[t] says "tile t of every peer's slice has landed", and the items of tile t (blockIdx.y)
+    // wait for it.  Rows stay whole (plain plan, no partial merges); the gather of tile t + 1
+    // overlaps the multiply of tile t.
+    int tile_vec4;                      // 16-byte vectors per row and K tile; 0 = owner-group mode
+    int row_vec4;                       // 16-byte vectors per row of x (ldx / 4)
+    long long slice_rows;
 };
 
 // ---- forward kernel parameter block --------------------------------------------------

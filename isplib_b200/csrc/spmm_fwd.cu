@@ -301,6 +301,13 @@ int launch_spmm(int reduce, const SpmmParams& base, int64_t nnz, int variant, cu
     if (!kern) return ISPLIB_NO_OPT_IMPL;
     // fused all-gather: only the lean kernels carry the copy role, and the grid must be ONE launch
     if (p.gather.copy_ctas > 0 && ((d->method != 5 && d->method != 6) || d->seq)) return ISPLIB_NO_OPT_IMPL;
+    if (p.gather.copy_ctas > 0 && p.gather.tile_vec4 < 0) {
+        // tile mode: the arrival groups are this variant's K tiles (whole rows when untiled)
+        if (t.ntiles > kMaxArrivalGroups) return ISPLIB_NO_OPT_IMPL;
+        p.gather.n_groups = t.ntiles;
+        p.gather.tile_vec4 = t.ntiles > 1 ? t.tile_w / 4 : p.gather.row_vec4;
+        if (t.ntiles > 1 && t.tile_w % 4 != 0) return ISPLIB_NO_OPT_IMPL;
+    }
 
     const int warps = d->warps;
     const dim3 block(warps * 32);

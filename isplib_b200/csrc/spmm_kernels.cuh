@@ -716,6 +716,44 @@ static __device__ __noinline__ void gather_copy_role(const GatherParams& G) {
     const int cta = blockIdx.x, nc = G.copy_ctas, tid = threadIdx.x, nt = blockDim.x;
     // my own slice of this step was written by earlier work on this stream: tell every peer
     if (cta == 0 && tid < G.n_src) st_release_sys(G.ready_peer[tid] + G.my_rank, G.epoch);
+    if (G.tile_vec4 > 0) {
+        // ---- tile mode: K tile after K tile, each tile from every peer (a [slice_rows x tile] block,
+        // row pitch row_vec4)
+        const long long n = G.slice_rows * (long long)G.tile_vec4;            // vectors per slice and tile
+        const long long chunk = ((n + nc - 1) / nc + 7) & ~7ll;
+        const long long b = min(n, (long long)cta * chunk), e = min(n, b + chunk);
+        const int tv = G.tile_vec4, rv = G.row_vec4;
+        for (int t = 0; t < G.n_groups; ++t) {
+            for (int s = 0; s < G.n_src; ++s) {
+                if (t == 0) {
+                    if (tid == 0) wait_reached<true>(G.ready_local + G.src_rank[s], G.epoch, G.status);
+                    __syncthreads();
+                }
+                const float4* __restrict__ src = reinterpret_cast<const float4*>(G.src[s]) + (long long)t * tv;
+                float4* __restrict__ dst = reinterpret_cast<float4*>(G.dst[s]) + (long long)t * tv;
+                for (long long i = b + tid; i < e; i += (long long)nt * 8) {
+                    float4 v[8];
+                    long long off[8];
+#pragma unroll
+                    for (int u = 0; u < 8; ++u) {
+                        const long long j = i + (long long)u * nt;
+                        const long long r = j / tv;
+                        off[u] = r * rv + (j - r * tv);
+                        if (j < e) v[u] = __ldcg(src + off[u]);
+                    }
+#pragma unroll
+                    for (int u = 0; u < 8; ++u) {
+                        const long long j = i + (long long)u * nt;
+                        if (j < e) dst[off[u]] = v[u];
+                    }
+                }
+            }
+            __threadfence();
+            __syncthreads();
+            if (tid == 0) atomicAdd(G.flags + t, 1u);
+        }
+        return;
+    }
     const long long n = G.slice_vec4;
     const long long chunk = ((n + nc - 1) / nc + 7) & ~7ll;
     const long long b = min(n, (long long)cta * chunk), e = min(n, b + chunk);
@@ -747,11 +785,18 @@ static __device__ __noinline__ void gather_copy_role(const GatherParams& G) {
 }
 
 // consumer side: the arrival group of a work item, and the wait for it
-__device__ __forceinline__ void gather_wait_for_item(const GatherParams& G, int item, int lane) {
+__device__ __forceinline__ void gather_wait_for_item(const GatherParams& G, int item, int tile, int lane) {
     int g = 0;
+    if (G.tile_vec4 > 0) {
+        // tile mode: every item gathers remote rows; its arrival group is its K tile.  The local slice
+        // needs no wait, but an item does not know which of its columns are local.
+        if (lane == 0) wait_reached<false>(G.flags + tile, G.flag_epoch * (unsigned)G.copy_ctas, G.status);
+        __syncwarp();
+        return;
+    }
     while (g < G.n_groups - 1 && item >= G.group_item_end[g]) ++g;
     if (g > 0) {
-        if (lane == 0) wait_reached<false>(G.flags + g, G.epoch * (unsigned)G.copy_ctas, G.status);
+        if (lane == 0) wait_reached<false>(G.flags + g, G.flag_epoch * (unsigned)G.copy_ctas, G.status);
         __syncwarp();
     }
 }
@@ -792,7 +837,6 @@ spmm_lean_kernel(const __grid_constant__ SpmmParams p) {
     if (item >= p.num_items) return;
     const int4 desc = __ldg(p.item_desc + item);
     const int eb = desc.y, ee = desc.z;
-    if (p.gather.copy_ctas > 0) gather_wait_for_item(p.gather, item, lane);   // rows of this item's arrival group landed?
     const int g = lane / G;
     const bool lane_ok = !RAGGED || (lane % G) * VEC < p.tile_w;
     const int k0 = (blockIdx.y + p.tile_base) * p.tile_w + (lane_ok ? (lane % G) * VEC : 0);
@@ -813,6 +857,9 @@ spmm_lean_kernel(const __grid_constant__ SpmmParams p) {
         if (has_val) a_next = __ldcs(p.val + eb + lane);
     }
 #endif
+    // fused all-gather: have the rows of this item's arrival group landed?  (checked here, with the
+    // first index chunk already in flight, so the flag's round trip hides behind it)
+    if (p.gather.copy_ctas > 0) gather_wait_for_item(p.gather, item, blockIdx.y + p.tile_base, lane);
     for (int e0 = eb; e0 < ee; e0 += 32) {
         const int cnt = min(32, ee - e0);
 #if ISPLIB_LEAN_PREFETCH

@@ -337,7 +337,12 @@ class RowPartitionedSpMM:
                                  torch.arange(e0, e1, dtype=torch.int32, device=self.device))
             n_remote_groups = int(os.environ.get("ISPLIB_B200_DIST_GROUPS", "3"))
             self.owner_group, self.n_groups = owner_groups(self.world, self.rank, n_remote_groups)
-            self.copy_ctas = int(os.environ.get("ISPLIB_B200_DIST_COPY_CTAS", "64"))
+            self.copy_ctas = int(os.environ.get("ISPLIB_B200_DIST_COPY_CTAS", "128"))
+            # what the arrival groups of the fused kernel are: "tiles" = the K tiles of the launch
+            # (rows stay whole, plain plan; needs >= 2 tiles, i.e. K >= 128 in 64-wide tiles) or
+            # "owners" = column owners (grouped plan, rows split per group); "auto" = tiles when possible
+            self.gather_groups = os.environ.get("ISPLIB_B200_DIST_GATHER", "auto")
+            self._plain_plan = None
             self._peer = {}            # K -> _PeerBuffers
             self._epoch = {}           # K -> launches so far on that buffer set
             self._gflags = {}          # K -> (flags uint32[8], status uint32[1])
@@ -451,8 +456,10 @@ class RowPartitionedSpMM:
             pb = _PeerBuffers(self.world, self.rank, self.Rc, K, self.device, self.group, self._emulated)
             self._peer[K] = pb
             self._epoch[K] = 0
-            self._gflags[K] = (torch.zeros(8, dtype=torch.int32, device=self.device),
-                               torch.zeros(1, dtype=torch.int32, device=self.device))
+            # arrival counters + timeout status per (K, mode), with their own launch count
+            for tm in (False, True):
+                self._gflags[(K, tm)] = [torch.zeros(8, dtype=torch.int32, device=self.device),
+                                         torch.zeros(1, dtype=torch.int32, device=self.device), 0]
         return pb
 
     def next_input_slice(self, K: int) -> torch.Tensor:
@@ -460,6 +467,16 @@ class RowPartitionedSpMM:
         writes there (instead of handing forward() a separate tensor) saves the staging copy."""
         pb = self.peer_buffers(K)
         return pb.own_slice((self._epoch[K] + 1) & 1)
+
+    def _tile_variant(self, K: int, code: int, x) -> int:
+        """Variant id of the 64-wide-K-tile lean kernel if the fused forward can run in tile mode at
+        this width (>= 2 whole tiles), else -1."""
+        from . import capi
+        if self.gather_groups == "owners" or K < 128 or K % 64 != 0 or K // 64 > 8:
+            return -1
+        v = capi.variant_names().index("lean256/w4/kt64")
+        ok = capi.lib().isplib_b200_variant_supported(v, code, K, x.stride(0), K, x.data_ptr(), x.data_ptr())
+        return v if ok else -1
 
     def _forward_fused(self, x_slice, code, out, arg, bias=None, relu=False):
         from . import capi
@@ -471,25 +488,104 @@ class RowPartitionedSpMM:
         own = pb.own_slice(b)
         if x_slice.data_ptr() != own.data_ptr():
             own.copy_(x_slice)                     # staging copy into the peer-visible buffer (Rc x K)
-        flags, status = self._gflags[K]
         if self._emulated is not None:
             # one process plays every rank in turn: the "peers" published their slices before this call
             pb.ready_words(b)[: self.world] = epoch
         full = self.full
-        capi.spmm_csr_gather(code, full.rowptr, full.col, full.val, pb.bufs[b][:, :K], self._fused_plan(),
+        xg = pb.bufs[b][:, :K]
+        tv = self._tile_variant(K, code, xg) if self.variant < 0 else -1
+        tile_mode = tv >= 0
+        if tile_mode:
+            if self._plain_plan is None:
+                self._plain_plan = capi.Plan(full.rowptr, full.nnz)
+            plan, variant = self._plain_plan, tv
+        else:
+            plan, variant = self._fused_plan(), self.variant
+        fl = self._gflags[(K, tile_mode)]
+        fl[2] += 1
+        capi.spmm_csr_gather(code, full.rowptr, full.col, full.val, xg, plan,
                              world=self.world, rank=self.rank, peer_x=pb.peer_x(b), peer_ready=pb.peer_ready(b),
-                             owner_group=self.owner_group, slice_rows=self.Rc, flags=flags, status=status,
-                             epoch=epoch, copy_ctas=self.copy_ctas, variant=self.variant, out=out, arg_out=arg,
-                             edge_ids=full.edge_ids, arg_sentinel=self.nnz, bias=bias, relu=relu)
+                             owner_group=self.owner_group, slice_rows=self.Rc, flags=fl[0], status=fl[1],
+                             epoch=epoch, flag_epoch=fl[2], tile_mode=tile_mode, copy_ctas=self.copy_ctas, variant=variant, out=out,
+                             arg_out=arg, edge_ids=full.edge_ids, arg_sentinel=self.nnz, bias=bias, relu=relu)
         return out, arg
+
+    def fused_variant(self, K: int, reduce: str = "sum") -> int:
+        """The kernel variant the C ABI's AUTO rule picks for the fused forward at width K (lean
+        kernels, one launch: 64-wide K tiles when they make the slab of X L2-resident), as an id."""
+        from . import capi
+        names = capi.variant_names()
+        n = self.world * self.Rc
+        x_bytes = n * K * 4.0
+        pb = self.peer_buffers(K)
+        x = pb.bufs[0][:, :K]
+        cands = []
+        if self._tile_variant(K, capi.REDUCE_CODE[reduce], x) >= 0:
+            return -1        # tile mode picks lean256/w4/kt64 itself (forward sets it per call)
+        if x_bytes > 96 * 2**20 and K > 64 and n * 256.0 <= 64 * 2**20:
+            cands.append("lean256/w4/kt64")
+        cands += ["lean256/w4/kfull", "lean128/w4/kfull"]
+        L = capi.lib()
+        for nm in cands:
+            v = names.index(nm)
+            if L.isplib_b200_variant_supported(v, capi.REDUCE_CODE[reduce], K, x.stride(0), K, x.data_ptr(), x.data_ptr()):
+                return v
+        return -1
+
+    def phase_split(self, x_slice, reduce: str = "sum", steps: int = 10):
+        """{'forward', 'multiply_only'} ms (max over ranks): the fused forward vs the same kernel and
+        plan on an already gathered X (no pulls, no waits); the difference is what the gather costs."""
+        from . import capi
+        assert self.mode == "fused"
+        K = x_slice.size(1)
+        dev = x_slice.device
+
+        def timed(fn):
+            fn()
+            if dist.is_initialized() and self._emulated is None:
+                dist.barrier(group=self.group)
+            torch.cuda.synchronize(dev)
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            for _ in range(steps):
+                fn()
+            e1.record()
+            torch.cuda.synchronize(dev)
+            t = torch.tensor([e0.elapsed_time(e1) / steps], device=dev, dtype=torch.float64)
+            if dist.is_initialized() and self._emulated is None:
+                dist.all_reduce(t, op=dist.ReduceOp.MAX, group=self.group)
+            return round(float(t.item()), 4)
+
+        fwd = timed(lambda: self.forward(x_slice, reduce))
+        pb = self.peer_buffers(K)
+        xg = pb.bufs[self._epoch[K] & 1][:, :K]
+        full = self.full
+        plan, variant, groups = self.fused_plan_and_variant(K, reduce)
+        out = torch.empty((self.R, K), device=dev)
+        arg = torch.empty((self.R, K), dtype=torch.int64, device=dev) if reduce in ("max", "min") else None
+        mul = timed(lambda: capi.spmm_csr(reduce, full.rowptr, full.col, full.val, xg, plan, variant, out=out,
+                                          arg_out=arg, edge_ids=full.edge_ids, arg_sentinel=self.nnz))
+        return {"forward": fwd, "multiply_only": mul, "gather_exposed": round(max(0.0, fwd - mul), 4),
+                "arrival_groups": groups}
+
+    def fused_plan_and_variant(self, K: int, reduce: str = "sum"):
+        """(plan, variant id, 'K tiles' | 'column owners') the fused forward uses at width K."""
+        from . import capi
+        pb = self.peer_buffers(K)
+        tv = self._tile_variant(K, capi.REDUCE_CODE[reduce], pb.bufs[0][:, :K]) if self.variant < 0 else -1
+        if tv >= 0:
+            if self._plain_plan is None:
+                self._plain_plan = capi.Plan(self.full.rowptr, self.full.nnz)
+            return self._plain_plan, tv, "K tiles"
+        return self._fused_plan(), self.variant, "column owners"
 
     def check_status(self):
         """Raises if a fused-gather kernel gave up waiting for a peer (4 s timeout inside the kernel).
         Synchronises; call it outside hot loops."""
         if self.mode == "fused":
-            for K, (_, status) in self._gflags.items():
+            for key, (_, status, _n) in self._gflags.items():
                 if int(status.item()) != 0:
-                    raise RuntimeError(f"isplib_b200: fused gather (K={K}) timed out waiting for a peer's slice")
+                    raise RuntimeError(f"isplib_b200: fused gather (K, tile mode)={key} timed out waiting for a peer's slice")
 
     def _forward_pipelined(self, x_slice, inner, div, out, arg):
         """X slices travel peer-to-peer over NVLink by the copy engines (torch symmetric memory,

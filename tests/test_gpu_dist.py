@@ -1,4 +1,4 @@
-"""2-GPU NCCL test of the row-partitioned path with the real CUDA kernels (skipped on boxes
+"""2-GPU tests of the row-partitioned path with the real CUDA kernels (skipped on boxes
 with fewer than 2 GPUs; run with `gpurun --gpus 2 -- python -m pytest tests/test_gpu_dist.py -m gpu`).
 Forward and backward of every reduction against the single-process oracle."""
 import os
@@ -14,7 +14,7 @@ pytestmark = pytest.mark.gpu
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 
 
-def worker(rank, world, port, results, pipelined=False):
+def worker(rank, world, port, results, mode="fused"):
     sys.path.insert(0, ROOT)
     os.environ["MASTER_ADDR"] = "127.0.0.1"
     os.environ["MASTER_PORT"] = str(port)
@@ -30,8 +30,10 @@ def worker(rank, world, port, results, pipelined=False):
         K = 32
         x = torch.randint(-3, 4, (g.n, K), generator=torch.Generator().manual_seed(1)).float()
         go = torch.randn(g.m, K, generator=torch.Generator().manual_seed(2))
-        op = DistSpMM(g.rowptr.to(dev), g.col.to(dev), val.to(dev), g.n, device=dev, pipelined=pipelined)
-        assert op.fwd.pipelined == pipelined
+        pipelined = mode == "pipelined"
+        op = DistSpMM(g.rowptr.to(dev), g.col.to(dev), val.to(dev), g.n, device=dev, pipelined=pipelined,
+                      mode="fused" if mode == "fused" else "nccl")
+        assert op.fwd.pipelined == pipelined and op.fwd.mode == ("fused" if mode == "fused" else "nccl")
         f = op.fwd
         r0, r1 = f.row_range()
         c0, c1 = f.col_range()
@@ -55,9 +57,27 @@ def worker(rank, world, port, results, pipelined=False):
                 bw = oracle.spmm_backward_sum if reduce == "sum" else oracle.spmm_backward_mean
                 gref = bw(rp, co, va, go.numpy(), g.n)
             ok[reduce + "_bwd"] = bool(np.allclose(xs.grad.cpu().numpy()[: c1 - c0], gref[c0:c1], rtol=1e-3, atol=1e-3))
+            if reduce in ("max", "min"):
+                # arg_out carries GLOBAL edge ids, bit-identical to the single-GPU answer
+                _, a = f.forward(f.pad_x(x[c0:c1].to(dev)), reduce)
+                ok[reduce + "_arg"] = bool(np.array_equal(a.cpu().numpy()[: r1 - r0], ref_arg[r0:r1]))
+        f.check_status()
         results[rank] = ok
     finally:
         dist.destroy_process_group()
+
+
+def test_row_partitioned_spmm_two_gpus_fused_gather():
+    """The default multi-GPU path: ONE kernel pulls the peer's slice of X over NVLink (symmetric
+    memory) and multiplies; no collective call in the forward or in the sum/mean backward."""
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs 2 GPUs")
+    mgr = mp.Manager()
+    results = mgr.dict()
+    mp.spawn(worker, args=(2, 29350 + os.getpid() % 300, results, "fused"), nprocs=2, join=True)
+    for rank in range(2):
+        bad = [k for k, v in results[rank].items() if not v]
+        assert not bad, f"rank {rank}: {bad}"
 
 
 def test_row_partitioned_spmm_two_gpus_nccl():
@@ -65,7 +85,7 @@ def test_row_partitioned_spmm_two_gpus_nccl():
         pytest.skip("needs 2 GPUs")
     mgr = mp.Manager()
     results = mgr.dict()
-    mp.spawn(worker, args=(2, 29650 + os.getpid() % 300, results), nprocs=2, join=True)
+    mp.spawn(worker, args=(2, 29650 + os.getpid() % 300, results, "nccl"), nprocs=2, join=True)
     for rank in range(2):
         bad = [k for k, v in results[rank].items() if not v]
         assert not bad, f"rank {rank}: {bad}"
@@ -78,7 +98,7 @@ def test_row_partitioned_spmm_two_gpus_pipelined_p2p():
         pytest.skip("needs 2 GPUs")
     mgr = mp.Manager()
     results = mgr.dict()
-    mp.spawn(worker, args=(2, 29950 + os.getpid() % 300, results, True), nprocs=2, join=True)
+    mp.spawn(worker, args=(2, 29950 + os.getpid() % 300, results, "pipelined"), nprocs=2, join=True)
     for rank in range(2):
         bad = [k for k, v in results[rank].items() if not v]
         assert not bad, f"rank {rank}: {bad}"

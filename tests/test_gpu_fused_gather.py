@@ -57,10 +57,13 @@ def test_grouped_plan_with_the_plain_kernels(capi, oracle, reduce):
 
 @pytest.mark.parametrize("world", [2, 4, 8])
 @pytest.mark.parametrize("reduce", ["sum", "mean", "max", "min"])
-@pytest.mark.parametrize("K", [32, 47, 128])
-def test_fused_gather_emulated_ranks_match_oracle(capi, oracle, world, reduce, K, monkeypatch):
+@pytest.mark.parametrize("K,groups", [(32, "auto"), (47, "auto"), (128, "auto"), (128, "owners"), (256, "auto")])
+def test_fused_gather_emulated_ranks_match_oracle(capi, oracle, world, reduce, K, groups, monkeypatch):
+    """K = 128 / 256 with "auto": arrival groups = the 64-wide K tiles (rows whole, plain plan);
+    narrower K or "owners": arrival groups = column owners (grouped plan, rows split per group)."""
     from isplib_b200.dist import RowPartitionedSpMM
     monkeypatch.setenv("ISPLIB_B200_DIST_COPY_CTAS", "8")
+    monkeypatch.setenv("ISPLIB_B200_DIST_GATHER", groups)
     M = N = 1500 + world          # not a multiple of world: padded slices
     rng, rowptr, col, val = _graph(10 + world, M, N, 60, long_rows=[(5, 1400), (M - 2, 700)])
     rp_t, co_t, va_t = torch.from_numpy(rowptr).to(DEV), torch.from_numpy(col).to(DEV), torch.from_numpy(val).to(DEV)
@@ -88,6 +91,8 @@ def test_fused_gather_emulated_ranks_match_oracle(capi, oracle, world, reduce, K
                 arg[r0:r1] = a[: r1 - r0]
         for op in ops:
             op.check_status()
+            used_tiles = any(n > 0 for (k_, tm), (_, _, n) in op._gflags.items() if tm)
+            assert used_tiles == (groups == "auto" and K >= 128)
         ref, ref_arg = oracle.spmm_c(rowptr, col, val, mat, code)
         if reduce in ("max", "min"):
             assert np.array_equal(out.cpu().numpy(), ref), f"step {step}"
