@@ -522,19 +522,23 @@ def run_ours(args):
         slices = [op.pad_x(x[c0:c1]) for x in xs]
         if args.variant is not None:
             op.variant = args.variant
-        elif op.mode == "fused":
-            op.variant = op.fused_variant(K, reduce)       # the id the C ABI's AUTO rule picks, so the line can name it
 
         def step(i):
             o, a = op.forward(slices[i & 1], reduce)
             return (o, a) + op.row_range()
-        step(0)
-        launches_per_step = op.launches_per_forward() * len(op._k_chunks(K))
-        inner = "auto" if op.variant < 0 else capi.variant_names()[op.variant]
-        if op.mode == "fused" and op.variant < 0:
-            inner = "lean256/w4/kt64 (K-tile arrival groups)"     # what RowPartitionedSpMM._tile_variant picked
-        variant_name = (f"fused-gather/{inner}" if op.mode == "fused" else inner)
+        step(0)                                   # mode='auto': times the fused kernel against the NCCL path here
+        dist_mode = op.mode_for(K, reduce)
+        launches_per_step = op.launches_per_forward(K, reduce) * (1 if dist_mode == "fused" else len(op._k_chunks(K)))
+        if dist_mode == "fused":
+            _plan, v_id, groups = op.fused_plan_and_variant(K, reduce)
+            inner = "auto" if v_id < 0 else capi.variant_names()[v_id]
+            variant_name = f"fused-gather/{inner} (arrival groups: {groups})"
+        else:
+            variant_name = "auto" if op.variant < 0 else capi.variant_names()[op.variant]
         tune = {}
+        choice = op._mode_choice.get((K, reduce in ("max", "min")))
+        if choice is not None and len(choice) == 3:
+            tune = {"fused gather+SpMM kernel": choice[1], "NCCL all-gather + 2 block kernels": choice[2]}
 
     def barrier():
         if world > 1:
@@ -622,16 +626,20 @@ def run_ours(args):
         e2e = {"value": round(b_alg / (ms_e2e * 1e-3) / 1e9, 2), "unit": "GB/s",
                "h2d_bytes_per_step": world * op.Rc * K * 4, "d2h_bytes_per_step": world * op.R * K * 4,
                "ms_per_step": round(ms_e2e, 3), "serial_ms_per_step": round(ms_serial, 3),
+               "host_link_gbs_per_direction": round(world * op.Rc * K * 4 / (ms_e2e * 1e-3) / 1e9, 1),
                "serial_value": round(b_alg / (ms_serial * 1e-3) / 1e9, 2),
                "path": "isplib_b200.dist.RowPartitionedSpMM.forward per rank: X row slice from pinned host memory -> "
-                       "fused gather + SpMM kernel -> result slice back to pinned host memory, every step; `value` "
+                       "row-partitioned forward -> result slice back to pinned host memory, every step; the N ranks "
+                       "together move the SAME total bytes over the host link as N = 1 does, so this leg is bound by "
+                       "the box's host link (host_link_gbs_per_direction), not by the GPUs; `value` "
                        "prefetches the next slice / drains the previous result on separate streams exactly like the "
                        "N = 1 leg, `serial_*` is one stream per rank; max over ranks"}
-        # where the step goes: the same kernel with X already gathered (no pulls, no waits) vs the fused forward
-        try:
-            phases = op.phase_split(slices[0], reduce)
-        except Exception as ex:
-            phases = {"error": repr(ex)[:200]}
+        # where the step goes: the same kernel with X already gathered (no pushes, no waits) vs the fused forward
+        if dist_mode == "fused":
+            try:
+                phases = op.phase_split(slices[0], reduce)
+            except Exception as ex:
+                phases = {"error": repr(ex)[:200]}
 
     # --- secondary: the other half of BASELINE.json's metric, a 2-layer GCN training epoch
     # (hidden 256) on the ogbn-products-shaped graph via patch_pyg(), same N GPUs ---------------
@@ -695,11 +703,12 @@ def run_ours(args):
                    "degree_gini": round(g_gini, 3),
                    "l2": "inputs 1.04 GB (col+val+X) > 126 MB L2 and two X buffers rotated between steps; no flush",
                    "parallelism": "single GPU" if world == 1 else (
-                       f"1-D row partition x{world} (nnz-balanced), X pulled from the peers over NVLink INSIDE the SpMM "
-                       f"kernel (symmetric memory, {op.copy_ctas} copy CTAs, arrival groups = "
-                       f"{'K tiles' if op.variant < 0 else 'column owners'}), no collective"
-                       if op.mode == "fused" else
-                       f"1-D row partition x{world}, X all-gathered per step over NCCL with local-block overlap")},
+                       f"1-D row partition x{world} (nnz-balanced), every rank's X slice pushed to its peers over NVLink "
+                       f"INSIDE the SpMM kernel (symmetric memory, {op.copy_ctas} copy CTAs), no collective; chosen over "
+                       f"the NCCL path by on-device timing"
+                       if dist_mode == "fused" else
+                       f"1-D row partition x{world} (nnz-balanced), X all-gathered per step over NCCL with local-block "
+                       f"overlap; chosen over the fused gather kernel by on-device timing")},
         "gflops": round(2.0 * nnz * K / (ms_step * 1e-3) / 1e9, 1),
         "roofline": roofline,
         "gpu_launches": launches_per_step * args.steps,

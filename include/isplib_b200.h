@@ -165,8 +165,10 @@ int isplib_b200_spmm_csr_fused(int reduce, int64_t m, int64_t n, int64_t k, int6
  * contiguous block of rows of A and the matching slice of X; its block's columns address the
  * owner-major gathered matrix [world * slice_rows, k].  Instead of an all-gather collective
  * followed by the SpMM, ONE kernel does both over NVLink peer memory: its first `copy_ctas` CTAs
- * pull the peers' slices (group by group, `owner_group`), the rest multiply, each work item
- * starting as soon as the slices of ITS arrival group have landed.  Needs a grouped plan.
+ * PUSH the rank's own slice into every peer's buffer (posted stores, then a release-add on the peer's
+ * arrival counter), the rest multiply, each work item starting as soon as the rows of ITS arrival
+ * group have landed.  Flow control is by credits (a rank tells its peers when it has started a step),
+ * x is double-buffered by step parity; no collective, no barrier kernel.
  *
  * isplib_b200_plan_build_grouped: like isplib_b200_plan_build, but segments never cross the
  * `n_runs` column runs [run_start[j], run_start[j+1]) and the work items are ordered by
@@ -181,29 +183,32 @@ int isplib_b200_plan_build_grouped(int64_t m, int64_t nnz, const int32_t* rowptr
 
 typedef struct isplib_b200_gather_desc {
     int32_t world, rank;
-    int32_t n_groups;               /* arrival groups incl. group 0 (the rank's own slice) */
-    int32_t copy_ctas;              /* CTAs that pull over NVLink; 0 = default (64) */
-    const void* const* peer_x;      /* [world] host array: rank q's gathered-x buffer as mapped into this
-                                       process (symmetric memory); slice q = rows [q*slice_rows, ...) of
+    int32_t n_groups;               /* owner mode: arrival groups incl. group 0 (the rank's own slice) */
+    int32_t copy_ctas;              /* CTAs that push over NVLink; 0 = default (64); the same on every rank */
+    void* const* peer_x;            /* [world] host array: rank q's gathered-x buffer OF THIS STEP'S PARITY as mapped
+                                       into this process (symmetric memory); slice q = rows [q*slice_rows, ...) of
                                        EVERY buffer; peer_x[rank] == x */
-    void* const* peer_ready;        /* [world] host array: rank q's ready words, uint32[world], same mapping */
-    const int32_t* owner_group;     /* [world] host array: arrival group of each owner; owner_group[rank] == 0 */
+    void* const* peer_arrive;       /* [world] host array: rank q's arrival counters of this parity, uint32[8] */
+    void* const* peer_credit;       /* [world] host array: rank q's credit words, uint32[world] */
+    const int32_t* owner_group;     /* owner mode, [world]: arrival group of each owner's slice HERE; [rank] == 0 */
+    const int32_t* my_group_at_peer;/* owner mode, [world]: the group THIS rank's slice belongs to at peer q */
     int64_t slice_rows;             /* n == world * slice_rows */
-    uint32_t* flags;                /* device uint32[8], zeroed once, private to this rank */
     uint32_t* status;               /* device uint32, zeroed once: 1 after a wait timed out (4 s) */
-    uint32_t epoch;                 /* 1, 2, 3, ... one per launch on this (flags, ready words) set; the
-                                       caller alternates two x buffers + ready-word sets by epoch parity */
+    uint32_t epoch;                 /* 1, 2, 3, ... one per step on this buffer set; parity = epoch & 1 selects
+                                       which of the two x buffers / arrival-counter sets the step uses */
     uint32_t tile_mode;             /* 0: arrival groups = column owners (grouped plan, rows split per group).
-                                       1: arrival groups = the K TILES of the launch: every slice is pulled one
-                                          K tile at a time, the items of tile t wait for tile t; rows stay whole,
-                                          any plan works; n_groups / owner_group / group_item_end are ignored */
-    const int64_t* group_item_end;  /* [n_groups] host array from isplib_b200_plan_build_grouped */
-    uint32_t flag_epoch;            /* launches on THIS flags array including this one (0 = same as epoch); a
-                                       flags array must always be used with the same copy_ctas and mode */
-    uint32_t reserved;
+                                       1: arrival groups = the K TILES of the launch: the slice is pushed one K tile
+                                          at a time, the items of tile t wait for tile t of every peer; rows stay
+                                          whole, any plan works; the owner-mode members are ignored */
+    const int64_t* group_item_end;  /* owner mode: [n_groups] host array from isplib_b200_plan_build_grouped */
+    uint32_t parity_launch;         /* steps that have used this parity's arrival counters, including this one */
+    uint32_t phase;                 /* 0: push + multiply (the product path).  1: push only, 2: multiply only
+                                       (still waits for arrivals): the two halves of a step when several ranks are
+                                       emulated on ONE GPU, where a rank's kernel cannot wait for kernels that have
+                                       not been launched yet */
 } isplib_b200_gather_desc;
 /* x: the LOCAL gathered buffer [n = world * slice_rows, k] (row stride ldx, ldx % 4 == 0); its own
- * slice must hold this step's rows before the call (stream order); the other slices are overwritten.
+ * slice must hold this step's rows before the call (stream order); the peers write the other slices.
  * Everything else as isplib_b200_spmm_csr_fused.  world == 1 degenerates to the plain kernel. */
 int isplib_b200_spmm_csr_gather(int reduce, int64_t m, int64_t n, int64_t k, int64_t nnz,
                                 const int32_t* rowptr, const int32_t* col, const float* val,

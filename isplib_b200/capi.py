@@ -63,10 +63,12 @@ class GatherDesc(ctypes.Structure):
     """isplib_b200_gather_desc (include/isplib_b200.h)."""
     _fields_ = [
         ("world", ctypes.c_int32), ("rank", ctypes.c_int32), ("n_groups", ctypes.c_int32), ("copy_ctas", ctypes.c_int32),
-        ("peer_x", ctypes.POINTER(ctypes.c_void_p)), ("peer_ready", ctypes.POINTER(ctypes.c_void_p)),
-        ("owner_group", ctypes.POINTER(ctypes.c_int32)), ("slice_rows", ctypes.c_int64),
-        ("flags", ctypes.c_void_p), ("status", ctypes.c_void_p), ("epoch", ctypes.c_uint32), ("tile_mode", ctypes.c_uint32),
-        ("group_item_end", ctypes.POINTER(ctypes.c_int64)), ("flag_epoch", ctypes.c_uint32), ("reserved", ctypes.c_uint32),
+        ("peer_x", ctypes.POINTER(ctypes.c_void_p)), ("peer_arrive", ctypes.POINTER(ctypes.c_void_p)),
+        ("peer_credit", ctypes.POINTER(ctypes.c_void_p)),
+        ("owner_group", ctypes.POINTER(ctypes.c_int32)), ("my_group_at_peer", ctypes.POINTER(ctypes.c_int32)),
+        ("slice_rows", ctypes.c_int64), ("status", ctypes.c_void_p), ("epoch", ctypes.c_uint32),
+        ("tile_mode", ctypes.c_uint32), ("group_item_end", ctypes.POINTER(ctypes.c_int64)),
+        ("parity_launch", ctypes.c_uint32), ("phase", ctypes.c_uint32),
     ]
 
 
@@ -201,14 +203,15 @@ class GroupedPlan(Plan):
 
 
 def spmm_csr_gather(reduce, rowptr32, col32, val, x_gathered, plan, *, world: int, rank: int,
-                    peer_x, peer_ready, owner_group, slice_rows: int, flags, status, epoch: int, tile_mode: bool = False,
-                    flag_epoch: int = 0,
+                    peer_x, peer_arrive, peer_credit, owner_group, my_group_at_peer, slice_rows: int, status,
+                    epoch: int, parity_launch: int, tile_mode: bool = False, phase: int = 0,
                     copy_ctas: int = 0, variant: int = VARIANT_AUTO, out=None, arg_out=None, row_divisor=None,
                     edge_ids=None, arg_sentinel: Optional[int] = None, bias=None, addend=None,
                     addend_scale: float = 1.0, relu: bool = False, spmm_flags: int = 0):
     """Fused all-gather + SpMM (isplib_b200_spmm_csr_gather).  x_gathered: the LOCAL [world *
-    slice_rows, K] buffer whose own slice already holds this step's rows; peer_x / peer_ready: the
-    device addresses (ints) of every rank's buffer / ready words as mapped into this process."""
+    slice_rows, K] buffer of this step's parity whose own slice already holds this step's rows;
+    peer_x / peer_arrive / peer_credit: the device addresses (ints) of every rank's buffer / arrival
+    counters / credit words as mapped into this process."""
     code = REDUCE_CODE[reduce] if isinstance(reduce, str) else int(reduce)
     assert x_gathered.is_cuda and x_gathered.dtype == torch.float32 and x_gathered.dim() == 2 and x_gathered.stride(1) == 1
     M, nnz = plan.m, plan.nnz
@@ -225,15 +228,16 @@ def spmm_csr_gather(reduce, rowptr32, col32, val, x_gathered, plan, *, world: in
     gd = GatherDesc()
     n_groups = 1 if tile_mode else plan.n_groups
     gd.world, gd.rank, gd.n_groups, gd.copy_ctas = world, rank, n_groups, copy_ctas
-    gd.tile_mode = 1 if tile_mode else 0
-    px = (ctypes.c_void_p * world)(*[int(v) for v in peer_x])
-    pr = (ctypes.c_void_p * world)(*[int(v) for v in peer_ready])
+    gd.tile_mode, gd.phase = (1 if tile_mode else 0), int(phase)
+    arrs = [(ctypes.c_void_p * world)(*[int(v) for v in a]) for a in (peer_x, peer_arrive, peer_credit)]
+    gd.peer_x, gd.peer_arrive, gd.peer_credit = arrs
     og = (ctypes.c_int32 * world)(*[int(v) for v in owner_group])
+    mg = (ctypes.c_int32 * world)(*[int(v) for v in my_group_at_peer])
     gie = (ctypes.c_int64 * n_groups)(*(plan.group_item_end if not tile_mode else [plan.info.num_items]))
-    gd.peer_x, gd.peer_ready, gd.owner_group, gd.group_item_end = px, pr, og, gie
+    gd.owner_group, gd.my_group_at_peer, gd.group_item_end = og, mg, gie
     gd.slice_rows = slice_rows
-    gd.flags, gd.status, gd.epoch = flags.data_ptr(), status.data_ptr(), int(epoch) & 0xFFFFFFFF
-    gd.flag_epoch = int(flag_epoch) & 0xFFFFFFFF
+    gd.status, gd.epoch = status.data_ptr(), int(epoch) & 0xFFFFFFFF
+    gd.parity_launch = int(parity_launch) & 0xFFFFFFFF
     epi = Epilogue()
     epi.bias = None if bias is None else bias.data_ptr()
     if addend is not None:

@@ -179,7 +179,7 @@ extern "C" int isplib_b200_spmm_csr_fused(int reduce, int64_t m, int64_t n, int6
 }
 
 // --------------------------------------------------------------------------------------
-// row-partitioned multi-GPU forward: the SpMM pulls the peers' slices of x itself
+// row-partitioned multi-GPU forward: the SpMM kernel moves the slices of x itself
 // --------------------------------------------------------------------------------------
 extern "C" int isplib_b200_spmm_csr_gather(int reduce, int64_t m, int64_t n, int64_t k, int64_t nnz,
                                            const int32_t* rowptr, const int32_t* col, const float* val,
@@ -194,10 +194,13 @@ extern "C" int isplib_b200_spmm_csr_gather(int reduce, int64_t m, int64_t n, int
     if (!gd) return ISPLIB_INVALID_ARG;
     if (gd->world < 1 || gd->world > kMaxPeers + 1 || gd->rank < 0 || gd->rank >= gd->world) return ISPLIB_INVALID_ARG;
     const bool tile_mode = gd->tile_mode != 0;
-    if (!tile_mode && (gd->n_groups < 1 || gd->n_groups > kMaxArrivalGroups || !gd->owner_group || !gd->group_item_end))
+    const bool multi = gd->world > 1;
+    if (!tile_mode && (gd->n_groups < 1 || gd->n_groups > kMaxArrivalGroups || !gd->owner_group ||
+                       !gd->my_group_at_peer || !gd->group_item_end))
         return ISPLIB_INVALID_ARG;
     if (gd->slice_rows < 0 || gd->slice_rows * (int64_t)gd->world != n) return ISPLIB_INVALID_ARG;
-    if (gd->world > 1 && (!gd->peer_x || !gd->peer_ready || !gd->flags || !gd->status)) return ISPLIB_INVALID_ARG;
+    if (multi && (!gd->peer_x || !gd->peer_arrive || !gd->peer_credit || !gd->status)) return ISPLIB_INVALID_ARG;
+    if (gd->phase > 2) return ISPLIB_INVALID_ARG;
     if (ldx % 4 != 0 || (reinterpret_cast<uintptr_t>(x) & 15u) != 0) return ISPLIB_INVALID_ARG;   // slices move as 16-byte vectors
     SpmmParams p;
     int st = fill_params(p, reduce, m, n, k, nnz, rowptr, col, val, x, ldx, out, ldo, arg_out, info,
@@ -208,47 +211,60 @@ extern "C" int isplib_b200_spmm_csr_gather(int reduce, int64_t m, int64_t n, int
 
     GatherParams& G = p.gather;
     G.n_groups = tile_mode ? 1 : gd->n_groups;
-    G.copy_ctas = gd->world > 1 ? (gd->copy_ctas > 0 ? gd->copy_ctas : 64) : 0;
+    G.copy_ctas = multi ? (gd->copy_ctas > 0 ? gd->copy_ctas : 64) : 0;
     G.epoch = gd->epoch;
-    G.flag_epoch = gd->flag_epoch ? gd->flag_epoch : gd->epoch;
-    G.flags = gd->flags;
     G.status = gd->status;
     G.my_rank = gd->rank;
     G.slice_vec4 = gd->slice_rows * ldx / 4;
     G.slice_rows = gd->slice_rows;
     G.row_vec4 = (int)(ldx / 4);
     G.tile_vec4 = tile_mode ? -1 : 0;      // -1: launch_spmm fills in the variant's K tile
-    G.ready_local = gd->world > 1 ? (unsigned*)gd->peer_ready[gd->rank] : nullptr;
+    G.phase = (int)gd->phase;
+    const size_t own_off = (size_t)gd->rank * (size_t)gd->slice_rows * (size_t)ldx;
+    G.own = x + own_off;
+    if (multi) {
+        if ((const void*)gd->peer_x[gd->rank] != (const void*)x) return ISPLIB_INVALID_ARG;
+        G.arrive_local = (unsigned*)gd->peer_arrive[gd->rank];
+        G.credit_local = (unsigned*)gd->peer_credit[gd->rank];
+    }
+    const unsigned per_source = gd->parity_launch * (unsigned)G.copy_ctas;
+    for (int g = 0; g < kMaxArrivalGroups; ++g) { G.arrive_target[g] = 0; G.group_item_end[g] = (int)info->num_items; }
     if (!tile_mode) {
-        for (int g = 0; g < kMaxArrivalGroups; ++g) {
-            const int64_t e = g < gd->n_groups ? gd->group_item_end[g] : info->num_items;
-            if (e < 0 || e > info->num_items || (g > 0 && g < gd->n_groups && e < gd->group_item_end[g - 1])) return ISPLIB_INVALID_ARG;
+        for (int g = 0; g < gd->n_groups; ++g) {
+            const int64_t e = gd->group_item_end[g];
+            if (e < 0 || e > info->num_items || (g > 0 && e < gd->group_item_end[g - 1])) return ISPLIB_INVALID_ARG;
             G.group_item_end[g] = (int)e;
         }
         if (gd->group_item_end[gd->n_groups - 1] != info->num_items) return ISPLIB_FAIL;   // not this plan's groups
         if (gd->owner_group[gd->rank] != 0) return ISPLIB_INVALID_ARG;
-        for (int o = 0; o < gd->world; ++o)
-            if (o != gd->rank && (gd->owner_group[o] < 1 || gd->owner_group[o] >= gd->n_groups)) return ISPLIB_INVALID_ARG;
+        for (int o = 0; o < gd->world; ++o) {
+            if (o == gd->rank) continue;
+            const int g = gd->owner_group[o], gp = gd->my_group_at_peer[o];
+            if (g < 1 || g >= gd->n_groups || gp < 1 || gp >= kMaxArrivalGroups) return ISPLIB_INVALID_ARG;
+            G.arrive_target[g] += per_source;          // every source of group g adds copy_ctas arrivals per step
+        }
+    } else {
+        for (int g = 0; g < kMaxArrivalGroups; ++g) G.arrive_target[g] = per_source * (unsigned)(gd->world - 1);
     }
-    // pull order: (group after group,) by ring distance from this rank, so that at any moment the
-    // ranks read from DIFFERENT peers (every NVSwitch port carries one stream)
-    int ns = 0;
-    for (int g = 1; g < (tile_mode ? 2 : gd->n_groups); ++g) {
+    // push order: owner mode -- the peers at which my slice is in the EARLIEST group first (the peer
+    // just before me in the ring gathers from me first); inside a group, and in tile mode, by ring
+    // distance, so that at any moment the ranks write to DIFFERENT peers
+    int nd = 0;
+    for (int g = 1; g < (tile_mode ? 2 : kMaxArrivalGroups); ++g) {
         for (int d = 1; d < gd->world; ++d) {
-            const int o = (gd->rank + d) % gd->world;
-            if (!tile_mode && gd->owner_group[o] != g) continue;
-            if (!gd->peer_x[o] || !gd->peer_ready[o]) return ISPLIB_INVALID_ARG;
-            const size_t off = (size_t)o * (size_t)gd->slice_rows * (size_t)ldx;
-            G.src[ns] = (const float*)gd->peer_x[o] + off;
-            G.dst[ns] = x + off;
-            G.ready_peer[ns] = (unsigned*)gd->peer_ready[o];
-            G.src_group[ns] = g;
-            G.src_rank[ns] = o;
-            ++ns;
+            const int q = (gd->rank - d + gd->world) % gd->world;
+            if (!tile_mode && gd->my_group_at_peer[q] != g) continue;
+            if (!gd->peer_x[q] || !gd->peer_arrive[q] || !gd->peer_credit[q]) return ISPLIB_INVALID_ARG;
+            G.dst[nd] = (float*)gd->peer_x[q] + own_off;
+            G.peer_arrive[nd] = (unsigned*)gd->peer_arrive[q];
+            G.peer_credit[nd] = (unsigned*)gd->peer_credit[q];
+            G.dst_group[nd] = tile_mode ? 0 : g;
+            G.dst_rank[nd] = q;
+            ++nd;
         }
     }
-    G.n_src = ns;
-    if (ns != gd->world - 1) return ISPLIB_INVALID_ARG;
+    G.n_dst = nd;
+    if (nd != gd->world - 1) return ISPLIB_INVALID_ARG;
 
     if (variant == ISPLIB_VARIANT_AUTO) {
         // lean kernels only, one launch: 64-wide K tiles (grid.y) when they make the slab of x

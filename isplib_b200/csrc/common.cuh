@@ -81,37 +81,39 @@ static inline PlanLayout plan_layout(int64_t m, int64_t nnz, int32_t seg_len) {
 enum PlanCounter { PC_ITEMS = 0, PC_SPLIT_ROWS = 1, PC_SPLIT_ITEMS = 2, PC_MAX_DEG = 3, PC_EMPTY = 4 };
 
 // ---- fused all-gather of x (row-partitioned multi-GPU forward) -------------------------
-// The lean SpMM kernels can pull the peers' slices of x over NVLink THEMSELVES while they
-// multiply: the first `copy_ctas` CTAs of the grid copy slice after slice from peer memory into the
-// local gathered x (group by group, in arrival order) and bump flags[g] when group g has landed;
-// the work items are ordered by arrival group (grouped plan) and an item of group g > 0 starts
-// only when flags[g] says its rows are there.  One launch = gather + SpMM, the transfer of group
-// g + 1 overlaps the multiply of group g, no NCCL call and no extra kernel in between.
+// The lean SpMM kernels move the slices of x over NVLink THEMSELVES while they multiply: the first
+// `copy_ctas` CTAs of the grid PUSH this rank's own slice into every peer's gathered x (posted
+// stores into peer-mapped memory: no round trip per request, unlike pulling) and then bump that
+// peer's arrival counter; the other CTAs multiply, each work item starting as soon as the arrival
+// counter of ITS group says the rows it gathers have landed.  One launch = all-gather + SpMM, the
+// transfer of group g + 1 overlaps the multiply of group g, no NCCL call, no barrier kernel.
+//   arrival groups = the K TILES of the launch (tile mode: rows stay whole, any plan), or
+//                  = column owners (owner mode: grouped plan, rows split per group).
+//   flow control   = credits: a rank announces "I have started step e" to every peer at kernel start;
+//                    a peer pushes step e + 1 into this rank's buffer of that parity only after that
+//                    (double-buffered x, so step e + 1 never overwrites rows step e still reads).
 constexpr int kMaxPeers = 15;           // world <= 16
 constexpr int kMaxArrivalGroups = 8;
 struct GatherParams {
-    const float* src[kMaxPeers];        // peer slice (peer-mapped device address), in pull order
-    float* dst[kMaxPeers];              // where that slice lands in the local gathered x
-    unsigned* ready_peer[kMaxPeers];    // that peer's ready words: we store `epoch` at [my_rank]
-    int src_group[kMaxPeers];           // arrival group (1-based) of each pulled slice, non-decreasing
-    int src_rank[kMaxPeers];            // the peer's rank (index into ready_local)
-    int group_item_end[kMaxArrivalGroups];   // items [end[g-1], end[g]) gather from group g
-    unsigned* flags;                    // [kMaxArrivalGroups] local arrival counters, monotonic
-    unsigned* ready_local;              // [world]: ready_local[q] == epoch <=> peer q's slice of this step is readable
+    float* dst[kMaxPeers];              // peer q's gathered x (this step's parity) at MY slice's rows, peer-mapped
+    unsigned* peer_arrive[kMaxPeers];   // peer q's arrival counters of this parity: [kMaxArrivalGroups]
+    unsigned* peer_credit[kMaxPeers];   // peer q's credit words: we store `epoch` at [my_rank] at kernel start
+    int dst_group[kMaxPeers];           // owner mode: the arrival group my slice belongs to AT that peer
+    int dst_rank[kMaxPeers];            // the peer's rank (index into credit_local)
+    int group_item_end[kMaxArrivalGroups];      // owner mode: items [end[g-1], end[g]) gather from group g
+    unsigned arrive_target[kMaxArrivalGroups];  // value arrive_local[g] reaches when group g of THIS step has landed
+    const float* own;                   // my own slice inside my gathered x (what gets pushed)
+    unsigned* arrive_local;             // my arrival counters of this parity, bumped by the peers' copy CTAs
+    unsigned* credit_local;             // [world]: credit_local[q] >= epoch - 1 <=> peer q's buffer of this parity is free
     unsigned* status;                   // set to 1 if a wait timed out (a peer never arrived)
     long long slice_vec4;               // 16-byte vectors per slice
-    unsigned epoch;                     // 1, 2, 3 ... per launch on this buffer set (ready words)
-    unsigned flag_epoch;                // launches on this flags array incl. this one: flags[g] reaches flag_epoch * copy_ctas
-    int n_src, n_groups, copy_ctas;     // copy_ctas == 0: plain kernel, nothing below is touched
-    int my_rank;
-    // tile mode (tile_vec4 > 0): the arrival groups are the K TILES of the launch instead of column
-    // owners -- every slice is pulled tile_vec4 16-byte vectors (one K tile) of each row at a time,
-    // flags[t] says "tile t of every peer's slice has landed", and the items of tile t (blockIdx.y)
-    // wait for it.  Rows stay whole (plain plan, no partial merges); the gather of tile t + 1
-    // overlaps the multiply of tile t.
-    int tile_vec4;                      // 16-byte vectors per row and K tile; 0 = owner-group mode
-    int row_vec4;                       // 16-byte vectors per row of x (ldx / 4)
     long long slice_rows;
+    unsigned epoch;                     // 1, 2, 3 ... per step on this buffer set
+    int n_dst, n_groups, copy_ctas;     // copy_ctas == 0: plain kernel, nothing here is touched
+    int my_rank;
+    int tile_vec4;                      // tile mode: 16-byte vectors per row and K tile; 0 = owner mode
+    int row_vec4;                       // 16-byte vectors per row of x (ldx / 4)
+    int phase;                          // 0 fused; 1 push only; 2 multiply only (still waits) -- 1/2: single-GPU emulation
 };
 
 // ---- forward kernel parameter block --------------------------------------------------

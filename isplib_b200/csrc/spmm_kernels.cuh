@@ -674,7 +674,7 @@ spmm_bulk_kernel(const __grid_constant__ SpmmParams p) {
 // (arg): 80 with VEC = 8 (24 warps/SM), 56 with VEC = 4 (36 warps/SM).
 // ------------------------------------------------------------------------------------
 // ------------------------------------------------------------------------------------
-// fused all-gather (GatherParams, common.cuh): the copy role and the consumer-side wait
+// fused all-gather (GatherParams, common.cuh): the push role and the consumer-side wait
 // ------------------------------------------------------------------------------------
 __device__ __forceinline__ unsigned long long global_timer_ns() {
     unsigned long long t;
@@ -686,23 +686,20 @@ __device__ __forceinline__ unsigned ld_acquire_sys(const unsigned* p) {
     asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
     return v;
 }
-__device__ __forceinline__ unsigned ld_acquire_gpu(const unsigned* p) {
-    unsigned v;
-    asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
-    return v;
-}
 __device__ __forceinline__ void st_release_sys(unsigned* p, unsigned v) {
     asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
+__device__ __forceinline__ void red_release_sys_add(unsigned* p, unsigned v) {
+    asm volatile("red.release.sys.global.add.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
 }
 constexpr unsigned long long kGatherTimeoutNs = 4000000000ull;   // 4 s: a peer that never shows up must not hang the GPU
 
 // spin until *word has reached `target` (wrap-safe); false on timeout
-template <bool SYS>
 __device__ __forceinline__ bool wait_reached(const unsigned* word, unsigned target, unsigned* status) {
     const unsigned long long t0 = global_timer_ns();
     unsigned ns = 32;
     while (true) {
-        const unsigned v = SYS ? ld_acquire_sys(word) : ld_acquire_gpu(word);
+        const unsigned v = ld_acquire_sys(word);
         if ((int)(v - target) >= 0) return true;
         __nanosleep(ns);
         if (ns < 1024) ns <<= 1;
@@ -710,95 +707,80 @@ __device__ __forceinline__ bool wait_reached(const unsigned* word, unsigned targ
     }
 }
 
-// The first copy_ctas CTAs: pull the peers' slices, group after group, 8 x 16 bytes in flight per
-// thread (NVLink latency is a few microseconds: bytes in flight, not threads, set the rate).
-static __device__ __noinline__ void gather_copy_role(const GatherParams& G) {
+// The first copy_ctas CTAs: push my slice to every peer.  Each vector is loaded ONCE (local, L2) and
+// stored to all peers (posted NVLink writes); 4 vectors per thread in flight.
+static __device__ __noinline__ void gather_push_role(const GatherParams& G) {
     const int cta = blockIdx.x, nc = G.copy_ctas, tid = threadIdx.x, nt = blockDim.x;
-    // my own slice of this step was written by earlier work on this stream: tell every peer
-    if (cta == 0 && tid < G.n_src) st_release_sys(G.ready_peer[tid] + G.my_rank, G.epoch);
+    // credit: "I have started step `epoch`" -- the step before has released my buffer of the OTHER
+    // parity, so peers may push step epoch + 1 into it
+    if (cta == 0 && tid < G.n_dst) st_release_sys(G.peer_credit[tid] + G.my_rank, G.epoch);
+    if (G.phase == 2) return;
+    // nobody may overwrite a buffer its owner still reads: wait for every peer's credit (steady state: long there)
+    if (tid < G.n_dst) wait_reached(G.credit_local + G.dst_rank[tid], G.epoch - 1u, G.status);
+    __syncthreads();
+    const float4* __restrict__ own = reinterpret_cast<const float4*>(G.own);
+    const int nd = G.n_dst;
     if (G.tile_vec4 > 0) {
-        // ---- tile mode: K tile after K tile, each tile from every peer (a [slice_rows x tile] block,
-        // row pitch row_vec4)
-        const long long n = G.slice_rows * (long long)G.tile_vec4;            // vectors per slice and tile
-        const long long chunk = ((n + nc - 1) / nc + 7) & ~7ll;
+        // ---- tile mode: K tile after K tile (a [slice_rows x tile] block, row pitch row_vec4), to every peer
+        const long long n = G.slice_rows * (long long)G.tile_vec4;
+        const long long chunk = ((n + nc - 1) / nc + 3) & ~3ll;
         const long long b = min(n, (long long)cta * chunk), e = min(n, b + chunk);
         const int tv = G.tile_vec4, rv = G.row_vec4;
         for (int t = 0; t < G.n_groups; ++t) {
-            for (int s = 0; s < G.n_src; ++s) {
-                if (t == 0) {
-                    if (tid == 0) wait_reached<true>(G.ready_local + G.src_rank[s], G.epoch, G.status);
-                    __syncthreads();
+            for (long long i = b + tid; i < e; i += (long long)nt * 4) {
+                float4 v[4];
+                long long off[4];
+#pragma unroll
+                for (int u = 0; u < 4; ++u) {
+                    const long long j = i + (long long)u * nt;
+                    const long long r = j / tv;
+                    off[u] = r * rv + (j - r * tv) + (long long)t * tv;
+                    if (j < e) v[u] = __ldg(own + off[u]);
                 }
-                const float4* __restrict__ src = reinterpret_cast<const float4*>(G.src[s]) + (long long)t * tv;
-                float4* __restrict__ dst = reinterpret_cast<float4*>(G.dst[s]) + (long long)t * tv;
-                for (long long i = b + tid; i < e; i += (long long)nt * 8) {
-                    float4 v[8];
-                    long long off[8];
+                for (int s = 0; s < nd; ++s) {
+                    float4* __restrict__ dst = reinterpret_cast<float4*>(G.dst[s]);
 #pragma unroll
-                    for (int u = 0; u < 8; ++u) {
-                        const long long j = i + (long long)u * nt;
-                        const long long r = j / tv;
-                        off[u] = r * rv + (j - r * tv);
-                        if (j < e) v[u] = __ldcg(src + off[u]);
-                    }
-#pragma unroll
-                    for (int u = 0; u < 8; ++u) {
-                        const long long j = i + (long long)u * nt;
-                        if (j < e) dst[off[u]] = v[u];
-                    }
+                    for (int u = 0; u < 4; ++u)
+                        if (i + (long long)u * nt < e) dst[off[u]] = v[u];
                 }
             }
-            __threadfence();
-            __syncthreads();
-            if (tid == 0) atomicAdd(G.flags + t, 1u);
+            __threadfence_system();          // my stores have reached the peers ...
+            __syncthreads();                 // ... for every thread of the CTA ...
+            if (tid < nd) red_release_sys_add(G.peer_arrive[tid] + t, 1u);   // ... before the arrival is published there
         }
         return;
     }
+    // ---- owner mode: the whole slice, peer after peer in the order of the group it belongs to THERE
     const long long n = G.slice_vec4;
-    const long long chunk = ((n + nc - 1) / nc + 7) & ~7ll;
+    const long long chunk = ((n + nc - 1) / nc + 3) & ~3ll;
     const long long b = min(n, (long long)cta * chunk), e = min(n, b + chunk);
-    int s = 0;
-    for (int g = 1; g < G.n_groups; ++g) {
-        for (; s < G.n_src && G.src_group[s] == g; ++s) {
-            if (tid == 0) wait_reached<true>(G.ready_local + G.src_rank[s], G.epoch, G.status);
-            __syncthreads();
-            const float4* __restrict__ src = reinterpret_cast<const float4*>(G.src[s]);
-            float4* __restrict__ dst = reinterpret_cast<float4*>(G.dst[s]);
-            for (long long i = b + tid; i < e; i += (long long)nt * 8) {
-                float4 v[8];
+    for (int s = 0; s < nd; ++s) {
+        float4* __restrict__ dst = reinterpret_cast<float4*>(G.dst[s]);
+        for (long long i = b + tid; i < e; i += (long long)nt * 8) {
+            float4 v[8];
 #pragma unroll
-                for (int u = 0; u < 8; ++u) {
-                    const long long j = i + (long long)u * nt;
-                    if (j < e) v[u] = __ldcg(src + j);          // L2 only: the line is not reused by this SM
-                }
+            for (int u = 0; u < 8; ++u)
+                if (i + (long long)u * nt < e) v[u] = __ldg(own + i + (long long)u * nt);
 #pragma unroll
-                for (int u = 0; u < 8; ++u) {
-                    const long long j = i + (long long)u * nt;
-                    if (j < e) dst[j] = v[u];
-                }
-            }
+            for (int u = 0; u < 8; ++u)
+                if (i + (long long)u * nt < e) dst[i + (long long)u * nt] = v[u];
         }
-        __threadfence();                 // this thread's stores are visible device-wide ...
-        __syncthreads();                 // ... for every thread of the CTA ...
-        if (tid == 0) atomicAdd(G.flags + g, 1u);   // ... before the arrival is published
+        __threadfence_system();
+        __syncthreads();
+        if (tid == 0) red_release_sys_add(G.peer_arrive[s] + G.dst_group[s], 1u);
     }
 }
 
 // consumer side: the arrival group of a work item, and the wait for it
 __device__ __forceinline__ void gather_wait_for_item(const GatherParams& G, int item, int tile, int lane) {
-    int g = 0;
-    if (G.tile_vec4 > 0) {
-        // tile mode: every item gathers remote rows; its arrival group is its K tile.  The local slice
-        // needs no wait, but an item does not know which of its columns are local.
-        if (lane == 0) wait_reached<false>(G.flags + tile, G.flag_epoch * (unsigned)G.copy_ctas, G.status);
-        __syncwarp();
-        return;
+    int g = tile;                        // tile mode: the item's K tile (every item gathers remote rows)
+    if (G.tile_vec4 <= 0) {              // owner mode: group 0 = the rank's own slice, nothing to wait for
+        g = 0;
+        while (g < G.n_groups - 1 && item >= G.group_item_end[g]) ++g;
+        if (g == 0) return;
     }
-    while (g < G.n_groups - 1 && item >= G.group_item_end[g]) ++g;
-    if (g > 0) {
-        if (lane == 0) wait_reached<false>(G.flags + g, G.flag_epoch * (unsigned)G.copy_ctas, G.status);
-        __syncwarp();
-    }
+    if (lane == 0) wait_reached(G.arrive_local + g, G.arrive_target[g], G.status);
+    __syncwarp();
 }
 
 // NOVAL (max / min only): val == NULL (SAGE / GIN drop the values) -- no multiply and no value
@@ -826,12 +808,13 @@ spmm_lean_kernel(const __grid_constant__ SpmmParams p) {
     const int lane = threadIdx.x & 31;
     int bx = blockIdx.x;
     if (p.gather.copy_ctas > 0) {
-        // fused all-gather: the first CTAs of the grid pull the peers' slices of x over NVLink
+        // fused all-gather: the first CTAs of the grid push this rank's slice of x to the peers over NVLink
         if (bx < p.gather.copy_ctas) {
-            if (blockIdx.y == 0) gather_copy_role(p.gather);
+            if (blockIdx.y == 0) gather_push_role(p.gather);
             return;
         }
         bx -= p.gather.copy_ctas;
+        if (p.gather.phase == 1) return;          // push-only launch (single-GPU emulation of the ranks)
     }
     const int item = bx * (blockDim.x >> 5) + (threadIdx.x >> 5);
     if (item >= p.num_items) return;

@@ -205,52 +205,64 @@ def group_runs(groups, slice_rows: int):
 class _PeerBuffers:
     """The double-buffered gathered-X allocation of one feature width, visible to every rank.
 
-    Layout (fp32 words): [buf 0: world*Rc*Kp][buf 1: world*Rc*Kp][ready words: 2 x 64 uint32].
+    Layout (fp32 words): [buf 0: world*Rc*Kp][buf 1: world*Rc*Kp][credit: 64 uint32]
+    [arrive parity 0: 16 uint32][arrive parity 1: 16 uint32].
     Real ranks: torch symmetric memory (CUDA VMM peer mappings over NVLink), rendezvoused once per
     width.  ``emulated``: a dict shared by the emulated ranks of ONE process (tests on one GPU): the
-    "peers" are ordinary local tensors, the kernel's pulls are local copies."""
+    "peers" are ordinary local tensors, the kernel's pushes are local copies."""
 
-    READY_WORDS = 64
+    CREDIT_WORDS, ARRIVE_WORDS = 64, 16
 
     def __init__(self, world, rank, Rc, K, device, group, emulated=None):
         self.world, self.rank, self.Rc, self.K = world, rank, Rc, K
         self.Kp = (K + 7) // 8 * 8
         self.buf_words = world * Rc * self.Kp
-        n_words = 2 * self.buf_words + 2 * self.READY_WORDS
+        n_words = 2 * self.buf_words + self.CREDIT_WORDS + 2 * self.ARRIVE_WORDS
         if emulated is None:
             import torch.distributed._symmetric_memory as symm
             g = group if group is not None else dist.group.WORLD
-            try:
-                if not symm.is_symm_mem_enabled_for_group(g.group_name):
-                    symm.enable_symm_mem_for_group(g.group_name)
-            except Exception:
-                pass                               # newer torch enables it inside rendezvous()
             self.t = symm.empty(n_words, dtype=torch.float32, device=device)
             self.t.zero_()
             torch.cuda.synchronize(device)
             self.hdl = symm.rendezvous(self.t, g)
-            dist.barrier(group=g)                  # nobody publishes into ready words that are not zeroed yet
+            dist.barrier(group=g)                  # nobody pushes into words that are not zeroed yet
             self.ptrs = [int(p) for p in self.hdl.buffer_ptrs]
         else:
             ts = emulated.setdefault(("bufs", K), [torch.zeros(n_words, dtype=torch.float32, device=device)
                                                    for _ in range(world)])
             self.t = ts[rank]
-            self.all = ts
             self.ptrs = [int(t.data_ptr()) for t in ts]
         self.bufs = [self.t[b * self.buf_words:(b + 1) * self.buf_words].view(world * Rc, self.Kp) for b in (0, 1)]
 
     def peer_x(self, b):
         return [p + 4 * b * self.buf_words for p in self.ptrs]
 
-    def peer_ready(self, b):
-        return [p + 4 * (2 * self.buf_words + b * self.READY_WORDS) for p in self.ptrs]
+    def peer_credit(self):
+        return [p + 4 * 2 * self.buf_words for p in self.ptrs]
 
-    def ready_words(self, b):
-        off = 2 * self.buf_words + b * self.READY_WORDS
-        return self.t[off:off + self.READY_WORDS].view(torch.int32)
+    def peer_arrive(self, b):
+        return [p + 4 * (2 * self.buf_words + self.CREDIT_WORDS + b * self.ARRIVE_WORDS) for p in self.ptrs]
 
     def own_slice(self, b):
         return self.bufs[b][self.rank * self.Rc:(self.rank + 1) * self.Rc, :self.K]
+
+
+def emulated_step(ops, xs, reduce: str = "sum"):
+    """One forward of several ranks emulated in ONE process / on ONE GPU (tests): every rank pushes
+    its slice first (phase 1), then every rank multiplies (phase 2, still waiting on the arrival
+    counters the pushes bumped).  Real ranks do both in one launch (phase 0).  Returns [(out, arg)]."""
+    code = REDUCE_CODE[reduce]
+    is_arg = code in (MAX, MIN)
+    outs = []
+    for op, x in zip(ops, xs):
+        K = x.size(1)
+        out = torch.empty((op.R, K), dtype=torch.float32, device=x.device)
+        arg = torch.empty((op.R, K), dtype=torch.int64, device=x.device) if is_arg else None
+        op._forward_fused(x, code, out, arg, phase=1)
+        outs.append((out, arg))
+    for op, x, (out, arg) in zip(ops, xs, outs):
+        op._forward_fused(x, code, out, arg, phase=2)
+    return outs
 
 
 def _cuda_block_spmm(reduce_code, block: CsrBlock, x, out, arg_out, flags, row_divisor, arg_sentinel, variant=-1):
@@ -317,15 +329,21 @@ class RowPartitionedSpMM:
             self.owner_blocks = [mv(b) for b in blocks]
         self.k_chunk = None        # feature-chunk width of the all-gather/SpMM pipeline (None = auto)
         self._gather_bufs = {}     # persistent all-gather receive buffers, keyed by (K, dtype, device)
-        # fused gather + SpMM (one kernel, no collective): the default wherever it can run
+        # "fused": gather + SpMM in one kernel, no collective.  "nccl": all-gather on a side stream +
+        # local / remote block kernels.  "auto" (the default wherever the fused kernel can run): both
+        # are built and the faster one is MEASURED per feature width on first use (on-device selection,
+        # like the single-GPU variants): the all-gather hides completely behind the local block while
+        # that block is a large share of the work (2-4 ranks), the fused kernel wins beyond
         if mode is None:
             mode = os.environ.get("ISPLIB_B200_DIST_MODE") or (
-                "fused" if (self.world > 1 and self.device.type == "cuda" and block_spmm is None and not self.pipelined)
-                else "nccl")
-        if mode not in ("fused", "nccl"):
-            raise ValueError(f"mode must be 'fused' or 'nccl', got {mode!r}")
+                "auto" if (self.world > 1 and self.device.type == "cuda" and block_spmm is None and not self.pipelined
+                           and self._emulated is None)
+                else ("fused" if self._emulated is not None else "nccl"))
+        if mode not in ("auto", "fused", "nccl"):
+            raise ValueError(f"mode must be 'auto', 'fused' or 'nccl', got {mode!r}")
         self.mode = mode
-        if mode == "fused":
+        self._mode_choice = {}      # (K, is_arg) -> "fused" | "nccl" (+ the two measured times)
+        if mode in ("auto", "fused"):
             r0, r1 = self.row_bounds[self.rank], self.row_bounds[self.rank + 1]
             e0, e1 = int(rowptr[r0]), int(rowptr[r1])
             rp = torch.zeros(self.R + 1, dtype=torch.int64, device=rowptr.device)
@@ -337,12 +355,16 @@ class RowPartitionedSpMM:
                                  torch.arange(e0, e1, dtype=torch.int32, device=self.device))
             n_remote_groups = int(os.environ.get("ISPLIB_B200_DIST_GROUPS", "3"))
             self.owner_group, self.n_groups = owner_groups(self.world, self.rank, n_remote_groups)
-            self.copy_ctas = int(os.environ.get("ISPLIB_B200_DIST_COPY_CTAS", "128"))
+            # the arrival group THIS rank's slice belongs to at every peer (the pusher needs it)
+            self.my_group_at_peer = [owner_groups(self.world, q, n_remote_groups)[0][self.rank] for q in range(self.world)]
+            # the pushes are NVLink-bound, not CTA-bound: 32, 64 and 128 CTAs measure the same (profiles/r2_dist_probe_n8.json)
+            self.copy_ctas = int(os.environ.get("ISPLIB_B200_DIST_COPY_CTAS", "32"))
             # what the arrival groups of the fused kernel are: "tiles" = the K tiles of the launch
             # (rows stay whole, plain plan; needs >= 2 tiles, i.e. K >= 128 in 64-wide tiles) or
             # "owners" = column owners (grouped plan, rows split per group); "auto" = tiles when possible
             self.gather_groups = os.environ.get("ISPLIB_B200_DIST_GATHER", "auto")
             self._plain_plan = None
+            self._fpv_cache = {}
             self._peer = {}            # K -> _PeerBuffers
             self._epoch = {}           # K -> launches so far on that buffer set
             self._gflags = {}          # K -> (flags uint32[8], status uint32[1])
@@ -405,7 +427,7 @@ class RowPartitionedSpMM:
             self.block_spmm(inner, self.local, x_slice, out, arg, 0, div, self.nnz, self.variant)
             return out, arg
 
-        if self.mode == "fused":
+        if self.mode_for(K, reduce, x_slice) == "fused":
             return self._forward_fused(x_slice, code, out, arg)
 
         if self.pipelined:
@@ -442,6 +464,38 @@ class RowPartitionedSpMM:
         self.block_spmm(inner, self.remote, gathered, out, arg, FLAG_ACCUMULATE, div, self.nnz, self.variant)
         return out, arg
 
+    def mode_for(self, K: int, reduce: str = "sum", x_slice: Optional[torch.Tensor] = None) -> str:
+        """'fused' or 'nccl' for this feature width.  mode='auto' times both once per (K, arg/additive)
+        -- 1 warm-up + 3 forwards each, max over ranks, every rank takes the same decision."""
+        if self.mode != "auto":
+            return self.mode
+        code = REDUCE_CODE[reduce]
+        key = (K, code in (MAX, MIN))
+        hit = self._mode_choice.get(key)
+        if hit is not None:
+            return hit[0]
+        if x_slice is None:
+            return "fused"
+        times = {}
+        dev = x_slice.device
+        for m in ("fused", "nccl"):
+            self._mode_choice[key] = (m,)
+            self.forward(x_slice, reduce)
+            dist.barrier(group=self.group)
+            torch.cuda.synchronize(dev)
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            for _ in range(3):
+                self.forward(x_slice, reduce)
+            e1.record()
+            torch.cuda.synchronize(dev)
+            t = torch.tensor([e0.elapsed_time(e1) / 3.0], device=dev, dtype=torch.float64)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX, group=self.group)
+            times[m] = float(t.item())
+        best = min(times, key=times.get)
+        self._mode_choice[key] = (best, round(times["fused"], 4), round(times["nccl"], 4))
+        return best
+
     def _fused_plan(self):
         from . import capi
         if self.full.plan is None:
@@ -456,10 +510,8 @@ class RowPartitionedSpMM:
             pb = _PeerBuffers(self.world, self.rank, self.Rc, K, self.device, self.group, self._emulated)
             self._peer[K] = pb
             self._epoch[K] = 0
-            # arrival counters + timeout status per (K, mode), with their own launch count
-            for tm in (False, True):
-                self._gflags[(K, tm)] = [torch.zeros(8, dtype=torch.int32, device=self.device),
-                                         torch.zeros(1, dtype=torch.int32, device=self.device), 0]
+            self._gflags[K] = torch.zeros(1, dtype=torch.int32, device=self.device)     # timeout status
+            self._tiles_used = getattr(self, "_tiles_used", {})
         return pb
 
     def next_input_slice(self, K: int) -> torch.Tensor:
@@ -468,7 +520,7 @@ class RowPartitionedSpMM:
         pb = self.peer_buffers(K)
         return pb.own_slice((self._epoch[K] + 1) & 1)
 
-    def _tile_variant(self, K: int, code: int, x) -> int:
+    def _tile_variant(self, K: int, code, x) -> int:
         """Variant id of the 64-wide-K-tile lean kernel if the fused forward can run in tile mode at
         this width (>= 2 whole tiles), else -1."""
         from . import capi
@@ -478,35 +530,32 @@ class RowPartitionedSpMM:
         ok = capi.lib().isplib_b200_variant_supported(v, code, K, x.stride(0), K, x.data_ptr(), x.data_ptr())
         return v if ok else -1
 
-    def _forward_fused(self, x_slice, code, out, arg, bias=None, relu=False):
+    def _forward_fused(self, x_slice, code, out, arg, bias=None, relu=False, phase=0):
+        """phase 0: the product path (push + multiply in one launch).  phases 1 / 2 split a step into
+        its push and its multiply half: only for several ranks emulated on ONE GPU (emulated_step)."""
         from . import capi
         K = x_slice.size(1)
         pb = self.peer_buffers(K)
-        self._epoch[K] += 1
+        if phase != 2:
+            self._epoch[K] += 1
         epoch = self._epoch[K]
         b = epoch & 1
         own = pb.own_slice(b)
-        if x_slice.data_ptr() != own.data_ptr():
+        if phase != 2 and x_slice.data_ptr() != own.data_ptr():
             own.copy_(x_slice)                     # staging copy into the peer-visible buffer (Rc x K)
-        if self._emulated is not None:
-            # one process plays every rank in turn: the "peers" published their slices before this call
-            pb.ready_words(b)[: self.world] = epoch
+        if self._emulated is not None and phase == 0:
+            raise RuntimeError("emulated ranks cannot run the fused step in one launch: use dist.emulated_step()")
         full = self.full
         xg = pb.bufs[b][:, :K]
-        tv = self._tile_variant(K, code, xg) if self.variant < 0 else -1
-        tile_mode = tv >= 0
-        if tile_mode:
-            if self._plain_plan is None:
-                self._plain_plan = capi.Plan(full.rowptr, full.nnz)
-            plan, variant = self._plain_plan, tv
-        else:
-            plan, variant = self._fused_plan(), self.variant
-        fl = self._gflags[(K, tile_mode)]
-        fl[2] += 1
+        plan, variant, groups = self.fused_plan_and_variant(K, code)
+        tile_mode = groups == "K tiles"
+        self._tiles_used[K] = tile_mode
         capi.spmm_csr_gather(code, full.rowptr, full.col, full.val, xg, plan,
-                             world=self.world, rank=self.rank, peer_x=pb.peer_x(b), peer_ready=pb.peer_ready(b),
-                             owner_group=self.owner_group, slice_rows=self.Rc, flags=fl[0], status=fl[1],
-                             epoch=epoch, flag_epoch=fl[2], tile_mode=tile_mode, copy_ctas=self.copy_ctas, variant=variant, out=out,
+                             world=self.world, rank=self.rank, peer_x=pb.peer_x(b), peer_arrive=pb.peer_arrive(b),
+                             peer_credit=pb.peer_credit(), owner_group=self.owner_group,
+                             my_group_at_peer=self.my_group_at_peer, slice_rows=self.Rc, status=self._gflags[K],
+                             epoch=epoch, parity_launch=(epoch + 1) // 2, tile_mode=tile_mode, phase=phase,
+                             copy_ctas=self.copy_ctas, variant=variant, out=out,
                              arg_out=arg, edge_ids=full.edge_ids, arg_sentinel=self.nnz, bias=bias, relu=relu)
         return out, arg
 
@@ -536,7 +585,7 @@ class RowPartitionedSpMM:
         """{'forward', 'multiply_only'} ms (max over ranks): the fused forward vs the same kernel and
         plan on an already gathered X (no pulls, no waits); the difference is what the gather costs."""
         from . import capi
-        assert self.mode == "fused"
+        assert self.mode_for(x_slice.size(1), reduce) == "fused"
         K = x_slice.size(1)
         dev = x_slice.device
 
@@ -568,24 +617,32 @@ class RowPartitionedSpMM:
         return {"forward": fwd, "multiply_only": mul, "gather_exposed": round(max(0.0, fwd - mul), 4),
                 "arrival_groups": groups}
 
-    def fused_plan_and_variant(self, K: int, reduce: str = "sum"):
+    def fused_plan_and_variant(self, K: int, reduce="sum"):
         """(plan, variant id, 'K tiles' | 'column owners') the fused forward uses at width K."""
         from . import capi
+        code = capi.REDUCE_CODE[reduce] if isinstance(reduce, str) else int(reduce)
+        key = (K, code, self.variant)
+        hit = self._fpv_cache.get(key)
+        if hit is not None:
+            return hit
         pb = self.peer_buffers(K)
-        tv = self._tile_variant(K, capi.REDUCE_CODE[reduce], pb.bufs[0][:, :K]) if self.variant < 0 else -1
+        tv = self._tile_variant(K, code, pb.bufs[0][:, :K]) if self.variant < 0 else -1
         if tv >= 0:
             if self._plain_plan is None:
                 self._plain_plan = capi.Plan(self.full.rowptr, self.full.nnz)
-            return self._plain_plan, tv, "K tiles"
-        return self._fused_plan(), self.variant, "column owners"
+            res = (self._plain_plan, tv, "K tiles")
+        else:
+            res = (self._fused_plan(), self.variant, "column owners")
+        self._fpv_cache[key] = res
+        return res
 
     def check_status(self):
         """Raises if a fused-gather kernel gave up waiting for a peer (4 s timeout inside the kernel).
         Synchronises; call it outside hot loops."""
-        if self.mode == "fused":
-            for key, (_, status, _n) in self._gflags.items():
+        if self.mode in ("fused", "auto"):
+            for K, status in self._gflags.items():
                 if int(status.item()) != 0:
-                    raise RuntimeError(f"isplib_b200: fused gather (K, tile mode)={key} timed out waiting for a peer's slice")
+                    raise RuntimeError(f"isplib_b200: fused gather (K={K}) timed out waiting for a peer's slice")
 
     def _forward_pipelined(self, x_slice, inner, div, out, arg):
         """X slices travel peer-to-peer over NVLink by the copy engines (torch symmetric memory,
@@ -634,9 +691,9 @@ class RowPartitionedSpMM:
             return [(0, K)]
         return [(c0, min(K, c0 + kc)) for c0 in range(0, K, kc)]
 
-    def launches_per_forward(self) -> int:
+    def launches_per_forward(self, K: Optional[int] = None, reduce: str = "sum") -> int:
         """how many of OUR kernels one forward launches (for bench.py's gpu_launches)."""
-        if self.world > 1 and self.mode == "fused":
+        if self.world > 1 and (self.mode == "fused" or (K is not None and self.mode_for(K, reduce) == "fused")):
             return 1                      # gather + SpMM are one kernel
         n = 1 if self.world == 1 else 2   # one spmm_seg_kernel per column block (x feature chunks)
         return n

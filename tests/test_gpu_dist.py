@@ -32,8 +32,8 @@ def worker(rank, world, port, results, mode="fused"):
         go = torch.randn(g.m, K, generator=torch.Generator().manual_seed(2))
         pipelined = mode == "pipelined"
         op = DistSpMM(g.rowptr.to(dev), g.col.to(dev), val.to(dev), g.n, device=dev, pipelined=pipelined,
-                      mode="fused" if mode == "fused" else "nccl")
-        assert op.fwd.pipelined == pipelined and op.fwd.mode == ("fused" if mode == "fused" else "nccl")
+                      mode=mode if mode in ("fused", "auto") else "nccl")
+        assert op.fwd.pipelined == pipelined and op.fwd.mode == (mode if mode in ("fused", "auto") else "nccl")
         f = op.fwd
         r0, r1 = f.row_range()
         c0, c1 = f.col_range()
@@ -75,6 +75,18 @@ def test_row_partitioned_spmm_two_gpus_fused_gather():
     mgr = mp.Manager()
     results = mgr.dict()
     mp.spawn(worker, args=(2, 29350 + os.getpid() % 300, results, "fused"), nprocs=2, join=True)
+    for rank in range(2):
+        bad = [k for k, v in results[rank].items() if not v]
+        assert not bad, f"rank {rank}: {bad}"
+
+
+def test_row_partitioned_spmm_two_gpus_auto_mode():
+    """mode='auto' (the default): both paths are built and the faster one is measured per width."""
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs 2 GPUs")
+    mgr = mp.Manager()
+    results = mgr.dict()
+    mp.spawn(worker, args=(2, 29450 + os.getpid() % 300, results, "auto"), nprocs=2, join=True)
     for rank in range(2):
         bad = [k for k, v in results[rank].items() if not v]
         assert not bad, f"rank {rank}: {bad}"

@@ -60,8 +60,10 @@ def test_grouped_plan_with_the_plain_kernels(capi, oracle, reduce):
 @pytest.mark.parametrize("K,groups", [(32, "auto"), (47, "auto"), (128, "auto"), (128, "owners"), (256, "auto")])
 def test_fused_gather_emulated_ranks_match_oracle(capi, oracle, world, reduce, K, groups, monkeypatch):
     """K = 128 / 256 with "auto": arrival groups = the 64-wide K tiles (rows whole, plain plan);
-    narrower K or "owners": arrival groups = column owners (grouped plan, rows split per group)."""
-    from isplib_b200.dist import RowPartitionedSpMM
+    narrower K or "owners": arrival groups = column owners (grouped plan, rows split per group).
+    Every emulated rank pushes its slice into the others' buffers with the kernel's copy CTAs, then
+    every rank multiplies, waiting on the arrival counters the pushes bumped."""
+    from isplib_b200.dist import RowPartitionedSpMM, emulated_step
     monkeypatch.setenv("ISPLIB_B200_DIST_COPY_CTAS", "8")
     monkeypatch.setenv("ISPLIB_B200_DIST_GATHER", groups)
     M = N = 1500 + world          # not a multiple of world: padded slices
@@ -74,25 +76,18 @@ def test_fused_gather_emulated_ranks_match_oracle(capi, oracle, world, reduce, K
     for step in range(3):                      # both buffer parities, growing epochs
         mat = rng.standard_normal((N, K)).astype(np.float32)
         x = torch.from_numpy(mat).to(DEV)
-        ins = []
-        for op in ops:                         # every "rank" publishes its slice first ...
-            c0, c1 = op.col_range()
-            dst = op.next_input_slice(K)
-            dst.zero_()
-            dst[: c1 - c0] = x[c0:c1]
-            ins.append(dst)
+        xs = [op.pad_x(x[op.col_range()[0]:op.col_range()[1]]) for op in ops]
+        res = emulated_step(ops, xs, reduce)
         out = torch.empty(M, K, device=DEV)
         arg = torch.empty(M, K, dtype=torch.int64, device=DEV)
-        for op, xin in zip(ops, ins):          # ... then each one runs gather + SpMM in one kernel
-            o, a = op.forward(xin, reduce)
+        for op, (o, a) in zip(ops, res):
             r0, r1 = op.row_range()
             out[r0:r1] = o[: r1 - r0]
             if a is not None:
                 arg[r0:r1] = a[: r1 - r0]
         for op in ops:
             op.check_status()
-            used_tiles = any(n > 0 for (k_, tm), (_, _, n) in op._gflags.items() if tm)
-            assert used_tiles == (groups == "auto" and K >= 128)
+            assert op._tiles_used[K] == (groups == "auto" and K >= 128)
         ref, ref_arg = oracle.spmm_c(rowptr, col, val, mat, code)
         if reduce in ("max", "min"):
             assert np.array_equal(out.cpu().numpy(), ref), f"step {step}"
@@ -101,47 +96,25 @@ def test_fused_gather_emulated_ranks_match_oracle(capi, oracle, world, reduce, K
             assert_sum_close(out.cpu().numpy(), ref, abs_product_sum(rowptr, col, val, mat, mean=(reduce == "mean")))
 
 
-def test_fused_gather_autograd_emulated(capi, oracle, monkeypatch):
-    """DistSpMM forward + backward (A^T through the same fused kernel) with 4 emulated ranks."""
-    from isplib_b200.dist import DistSpMM
+def test_fused_gather_transposed_operator_emulated(capi, oracle, monkeypatch):
+    """The sum / mean backward is the same fused kernel on the row partition of A^T (DistSpMM.bwd_op)."""
+    from isplib_b200.dist import DistSpMM, emulated_step
     monkeypatch.setenv("ISPLIB_B200_DIST_COPY_CTAS", "4")
     world, K = 4, 64
     M = N = 1203
     rng, rowptr, col, val = _graph(77, M, N, 40, long_rows=[(1, 900)])
     rp_t, co_t, va_t = torch.from_numpy(rowptr).to(DEV), torch.from_numpy(col).to(DEV), torch.from_numpy(val).to(DEV)
-    shared_f, ops = {}, []
-    for r in range(world):
-        ops.append(DistSpMM(rp_t, co_t, va_t, N, device=DEV, mode="fused", emulate=(world, r, shared_f)))
-    mat = rng.standard_normal((N, K)).astype(np.float32)
+    shared = {}
+    ops = [DistSpMM(rp_t, co_t, va_t, N, device=DEV, mode="fused", emulate=(world, r, shared)) for r in range(world)]
     go = rng.standard_normal((M, K)).astype(np.float32)
-    x = torch.from_numpy(mat).to(DEV)
-    for reduce in ("sum", "mean"):
-        # forward: publish all slices, then run every rank
-        xs, outs = [], []
-        for op in ops:
-            c0, c1 = op.fwd.col_range()
-            xin = op.fwd.next_input_slice(K)
-            xin.zero_()
-            xin[: c1 - c0] = x[c0:c1]
-            xs.append(xin.clone().requires_grad_(True))
-        # the autograd Function copies its (cloned) input into the published slot itself
-        for op, xi in zip(ops, xs):
-            outs.append(op(xi, reduce))
-        ref = oracle.spmm_c(rowptr, col, val, mat, oracle.REDUCE_CODE[reduce])[0]
-        got = torch.cat([o[: op.fwd.row_range()[1] - op.fwd.row_range()[0]] for o, op in zip(outs, ops)]).detach().cpu().numpy()
-        assert_sum_close(got, ref, abs_product_sum(rowptr, col, val, mat, mean=(reduce == "mean")))
-        # backward: the transposed operators also need every rank's grad slice published first
-        gts = [op.bwd_op(reduce == "mean") for op in ops]
-        for t, op in zip(gts, ops):
-            r0, r1 = op.fwd.row_range()
-            slot = t.next_input_slice(K)
-            slot.zero_()
-            slot[: r1 - r0] = torch.from_numpy(go[r0:r1]).to(DEV)
-        grads = []
-        for t, op in zip(gts, ops):
-            gx, _ = t.forward(t.next_input_slice(K), "sum")
-            c0, c1 = op.fwd.col_range()
-            grads.append(gx[: c1 - c0])
-        bw = oracle.spmm_backward_sum if reduce == "sum" else oracle.spmm_backward_mean
+    go_d = torch.from_numpy(go).to(DEV)
+    for mean in (False, True):
+        ts = [op.bwd_op(mean) for op in ops]
+        gs = [t.pad_x(go_d[op.fwd.row_range()[0]:op.fwd.row_range()[1]]) for t, op in zip(ts, ops)]
+        res = emulated_step(ts, gs, "sum")
+        grads = [gx[: op.fwd.col_range()[1] - op.fwd.col_range()[0]] for (gx, _), op in zip(res, ops)]
+        bw = oracle.spmm_backward_mean if mean else oracle.spmm_backward_sum
         want = bw(rowptr, col, val, go, N)
         np.testing.assert_allclose(torch.cat(grads).cpu().numpy(), want, rtol=1e-4, atol=1e-4)
+        for t in ts:
+            t.check_status()
