@@ -94,6 +94,10 @@ class iSpLibPlugin:
     def spmm(src, other, reduce: str = "sum"):
         """The patched ``torch_sparse.matmul``: body of ``spmm_autotuned``
         (isplib/__init__.py:48-157) on the CUDA ops."""
+        if getattr(src, "is_partitioned", False):
+            # a row-partitioned adjacency (isplib_b200.dist.partition / iSpLibPlugin.partition): `other` is
+            # this rank's slice of X; the multi-GPU operator (fused gather + SpMM kernel, autograd) runs
+            return src.matmul(other, reduce)
         if not _is_sparse_tensor(src):
             # torch.sparse.mm is patched too (isplib/__init__.py:178); genuine torch sparse
             # tensors go to the original function instead of crashing on src.csr()
@@ -121,9 +125,22 @@ class iSpLibPlugin:
             return ops.fusedmm_spmm_min(rowptr, col, value, other)[0]
         raise ValueError(f"isplib: unsupported reduce {reduce!r} (sum, add, mean, max, min)")
 
+    dist_group = None      # process group of the row-partitioned mode (patch_pyg(group=...))
+
     @classmethod
-    def patch_pyg(cls):
+    def partition(cls, adj_t, device=None, **kw):
+        """Row-partition `adj_t` over the ranks of the group given to ``patch_pyg(group=...)`` (default:
+        the world group).  The result goes wherever the SparseTensor went: ``matmul(padj, x_slice, reduce)``."""
+        from .dist import partition
+        return partition(adj_t, group=cls.dist_group, device=device, **kw)
+
+    @classmethod
+    def patch_pyg(cls, group=None):
+        """``group``: a torch.distributed process group -- one process per GPU -- for the row-partitioned
+        multi-GPU mode: adjacencies made with ``iSpLibPlugin.partition(adj_t)`` are then multiplied
+        across its ranks by the same patched ``torch_sparse.matmul`` (new; the reference is single-process)."""
         global matmul
+        cls.dist_group = group
         try:  # isplib/__init__.py:159-171
             import torch_geometric.typing as tgt  # type: ignore
             cls.cache["WITH_PT2"] = getattr(tgt, "WITH_PT2", None)

@@ -797,3 +797,66 @@ class _DistSpMMFn(torch.autograd.Function):
             dist.all_reduce(partial, group=f.group)
             out.copy_(partial[f.rank * f.Rc:(f.rank + 1) * f.Rc])
         return out, None, None
+
+
+# ----------------------------------------------------------------------------------------
+# the drop-in surface for the row-partitioned mode
+# ----------------------------------------------------------------------------------------
+class PartitionedAdj:
+    """What ``torch_sparse.matmul(adj_t, x, reduce)`` receives in place of the SparseTensor when the
+    graph is row-partitioned over the ranks of a process group: with ``iSpLibPlugin.patch_pyg()``
+    active the patched matmul recognises it and runs ``DistSpMM`` (fused gather + SpMM kernel or
+    NCCL path, autograd included), so a model written against ``matmul(adj_t, x, reduce)`` -- the
+    reference's GCN / SAGE / GIN scripts, /root/reference/tests/cpu/gcn-sparse.py:55-68 -- trains on
+    N GPUs unchanged: it is handed this object and ITS rank's padded row slice of x.
+
+    Only what those callers touch is provided: ``sparse_sizes()``, ``has_value()``,
+    ``set_value(None)`` (SAGE / GIN drop the values), plus the slice helpers."""
+
+    is_partitioned = True
+
+    def __init__(self, rowptr, col, value, n_cols, **dist_kw):
+        self._args = (rowptr, col, n_cols)
+        self._value = value
+        self._kw = dist_kw
+        self.op = DistSpMM(rowptr, col, value, n_cols, **dist_kw)
+        self._novalue_twin = None
+
+    # --- what the callers of matmul use ---
+    def sparse_sizes(self):
+        return (self.op.fwd.R, self.op.fwd.Rc)
+
+    def has_value(self) -> bool:
+        return self._value is not None
+
+    def set_value(self, value, layout=None):
+        if value is not None:
+            raise NotImplementedError("PartitionedAdj.set_value: only set_value(None) (what SAGEConv / GINConv do)")
+        if self._value is None:
+            return self
+        if self._novalue_twin is None:
+            rowptr, col, n_cols = self._args
+            self._novalue_twin = PartitionedAdj(rowptr, col, None, n_cols, **self._kw)
+        return self._novalue_twin
+
+    def matmul(self, x_slice: torch.Tensor, reduce: str = "sum") -> torch.Tensor:
+        return self.op(x_slice, reduce)
+
+    # --- slice helpers for the training script ---
+    def row_range(self):
+        return self.op.fwd.row_range()
+
+    def col_range(self):
+        return self.op.fwd.col_range()
+
+    def local_slice(self, x_global: torch.Tensor) -> torch.Tensor:
+        """This rank's padded [Rc, K] slice of a replicated / host-side [N, K] feature matrix."""
+        c0, c1 = self.col_range()
+        return self.op.fwd.pad_x(x_global[c0:c1].to(self.op.fwd.device))
+
+
+def partition(adj_t, group=None, device=None, **dist_kw) -> PartitionedAdj:
+    """Row-partition a (replicated) ``torch_sparse.SparseTensor`` over the ranks of `group`."""
+    rowptr, col, value = adj_t.csr()
+    n_cols = adj_t.sparse_sizes()[1]
+    return PartitionedAdj(rowptr, col, value, n_cols, group=group, device=device, **dist_kw)

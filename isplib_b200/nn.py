@@ -24,11 +24,13 @@ def _matmul(adj_t, x, reduce):
     return sys.modules["torch_sparse"].matmul(adj_t, x, reduce)   # looked up per call: honours the patch
 
 
-def _fused_available(x, spmm) -> bool:
+def _fused_available(x, spmm, adj_t=None) -> bool:
     """The fused-epilogue kernels run when the plugin is patched in (the CUDA path is the active
     matmul), the data is on the GPU and no external spmm callable (multi-GPU) was handed in."""
     if spmm is not None or not x.is_cuda:
         return False
+    if getattr(adj_t, "is_partitioned", False):
+        return False        # the row-partitioned operator applies no epilogue (yet): plain torch ops follow it
     from . import iSpLibPlugin
     return iSpLibPlugin.is_patched() and iSpLibPlugin.fuse_epilogues
 
@@ -67,7 +69,7 @@ class GCNConv(nn.Module):
         if self.aggregate_first:
             out = F.linear(agg(x), self.lin.weight, self.bias)        # bias in the GEMM epilogue
             return F.relu(out) if self.relu else out
-        if _fused_available(x, spmm):
+        if _fused_available(x, spmm, adj_t):
             # + bias and ReLU inside the SpMM's final store: two [N, K] passes less
             from . import fused_matmul
             return fused_matmul(adj_t, _linear_padded(x, self.lin.weight), "sum", bias=self.bias, relu=self.relu)
@@ -106,7 +108,7 @@ class GINConv(nn.Module):
 
     def forward(self, x, adj_t, spmm: Optional[Callable] = None):
         adj = adj_t.set_value(None) if (spmm is None and adj_t.has_value()) else adj_t
-        if _fused_available(x, spmm) and adj.sparse_sizes()[0] == x.size(0):
+        if _fused_available(x, spmm, adj) and adj.sparse_sizes()[0] == x.size(0):
             # (1 + eps) * x_i + sum_j x_j in the SpMM's final store (addend = x itself)
             from . import fused_matmul
             return self.nn(fused_matmul(adj, x, "sum", addend=x, addend_scale=1.0 + self.eps))

@@ -181,3 +181,66 @@ def test_nnz_balanced_bounds_even_out_a_skewed_graph():
         pos = slice_position(torch.arange(M), nb, Rc)
         assert pos.unique().numel() == M and int(pos.max()) < world * Rc
     assert nnz_balanced_bounds(torch.zeros(6, dtype=torch.int64), 4) == even_bounds(5, 4)   # empty graph
+
+
+# ----------------------------------------------------------------------------------------
+# the drop-in surface of the multi-GPU mode: patch_pyg(group=...) + a partitioned adjacency
+# ----------------------------------------------------------------------------------------
+def plugin_worker(rank, world, port, results):
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        import isplib_b200  # noqa: F401
+        import torch_sparse
+        from isplib import iSpLibPlugin
+        from isplib_b200 import nn as gnn
+        from oracle import oracle
+        M = N = 77
+        K = 5
+        rowptr, col, val = make_graph(11, M, N, True)
+        x = np.random.default_rng(1).standard_normal((N, K)).astype(np.float32)
+        adj = torch_sparse.SparseTensor(rowptr=torch.from_numpy(rowptr), col=torch.from_numpy(col),
+                                        value=torch.from_numpy(val), sparse_sizes=(M, N), is_sorted=True)
+        iSpLibPlugin.patch_pyg(group=dist.group.WORLD)
+        try:
+            padj = iSpLibPlugin.partition(adj, device="cpu", block_spmm=oracle_block_spmm,
+                                          arg_backward=oracle_arg_backward, overlap=False, mode="nccl")
+            r0, r1 = padj.row_range()
+            xs = padj.local_slice(torch.from_numpy(x))
+            ok = {}
+            # the SAME call a single-process script makes: torch_sparse.matmul(adj_t, x, reduce)
+            for reduce in ("sum", "mean", "max"):
+                out = torch_sparse.matmul(padj, xs, reduce)
+                ref = oracle.spmm_c(rowptr, col, val, x, oracle.REDUCE_CODE[reduce])[0]
+                ok[reduce] = bool(np.allclose(out.numpy()[: r1 - r0], ref[r0:r1], rtol=1e-5, atol=1e-5))
+            # SAGE / GIN drop the values: set_value(None) must hand back a partitioned twin
+            nov = padj.set_value(None)
+            out = torch_sparse.matmul(nov, xs, "sum")
+            ref = oracle.spmm_c(rowptr, col, None, x, oracle.SUM)[0]
+            ok["novalue"] = bool(np.allclose(out.numpy()[: r1 - r0], ref[r0:r1], rtol=1e-5, atol=1e-5)) and not nov.has_value()
+            # a whole layer through the unchanged model code: GCNConv.forward calls matmul(adj_t, ...)
+            torch.manual_seed(0)
+            conv = gnn.GCNConv(K, 3, order="linear_first")
+            y = conv(xs, padj)
+            with torch.no_grad():
+                h = (torch.from_numpy(x) @ conv.lin.weight.t()).numpy()
+            ref = oracle.spmm_c(rowptr, col, val, h, oracle.SUM)[0] + conv.bias.detach().numpy()
+            ok["gcn_layer"] = bool(np.allclose(y.detach().numpy()[: r1 - r0], ref[r0:r1], rtol=1e-4, atol=1e-4))
+            results[rank] = ok
+        finally:
+            iSpLibPlugin.unpatch_pyg()
+    finally:
+        dist.destroy_process_group()
+
+
+def test_patched_matmul_dispatches_partitioned_adjacency_world2_gloo():
+    world = 2
+    port = 31500 + (os.getpid() % 2000)
+    mgr = mp.Manager()
+    results = mgr.dict()
+    mp.spawn(plugin_worker, args=(world, port, results), nprocs=world, join=True)
+    assert len(results) == world
+    for rank in range(world):
+        bad = [k for k, v in results[rank].items() if not v]
+        assert not bad, f"rank {rank}: {bad}"

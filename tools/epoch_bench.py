@@ -61,10 +61,13 @@ def run(a, init_dist=True):
         x, y, train = x_all, y_all, train_all
         n_train = int(train.sum())
     else:
-        op = DistSpMM(g.rowptr, g.col, g.value, N, device=dev)
+        # the drop-in multi-GPU path: the model still calls torch_sparse.matmul(adj_t, x, reduce); the
+        # patched matmul recognises the partitioned adjacency and runs the row-partitioned operator
+        iSpLibPlugin.dist_group = None
+        adj = iSpLibPlugin.partition(g.sparse_tensor(), device=dev)
+        op = adj.op
         f = op.fwd
-        adj = None
-        spmm = op
+        spmm = None
         r0, r1 = f.col_range()
         x = f.pad_x(x_all[r0:r1])
         y = torch.zeros(f.Rc, dtype=torch.long, device=dev)
