@@ -342,3 +342,37 @@ def test_accumulate_after_empty_zero_block(capi, oracle):
     want0 = np.maximum(mat[0], mat[1])
     assert np.array_equal(out[0].cpu().numpy(), want0), "a negative true max lost against the placeholder 0"
     assert bool((arg[0] != 5).all())
+
+
+# ------------------------------------------------------------- node reordering
+@pytest.mark.parametrize("order", ["degree", "bfs", "rcm", "random"])
+def test_reordering_on_device_commutes_with_cuda_spmm(isplib, oracle, order):
+    """(P A P^T)(P x) == P (A x) with the permuted adjacency BUILT ON THE DEVICE (COO -> CSR kernel)
+    and multiplied by the CUDA kernels, against the oracle on the unpermuted graph; `bfs` is also
+    COMPUTED on the device."""
+    import torch_sparse
+    from isplib import iSpLibPlugin
+    from isplib_b200 import reorder, synth
+    g = synth.make_graph(3000, 90_000, law="lognormal", param=1.2, values="uniform", seed=4, device=DEV)
+    adj = g.sparse_tensor()
+    K = 48
+    x = torch.randn(g.n, K, device=DEV)
+    perm = {"degree": lambda: reorder.degree_order(adj), "bfs": lambda: reorder.bfs_order(adj),
+            "rcm": lambda: reorder.reverse_cuthill_mckee(adj),
+            "random": lambda: torch.randperm(g.n, device=DEV)}[order]()
+    assert perm.is_cuda and sorted(perm.tolist()) == list(range(g.n))
+    adj_p = reorder.permute(adj, perm)
+    assert adj_p.csr()[1].is_cuda
+    rp, co, va = (t.cpu().numpy() for t in adj.csr())
+    xh = x.cpu().numpy()
+    p = perm.cpu().numpy()
+    iSpLibPlugin.patch_pyg()
+    try:
+        got_sum = torch_sparse.matmul(adj_p, x[perm], "sum").cpu().numpy()
+        got_max = torch_sparse.matmul(adj_p, x[perm], "max").cpu().numpy()
+    finally:
+        iSpLibPlugin.unpatch_pyg()
+    ref_sum = oracle.spmm_c(rp, co, va, xh, oracle.SUM)[0]
+    ref_max = oracle.spmm_c(rp, co, va, xh, oracle.MAX)[0]
+    assert_sum_close(got_sum, ref_sum[p], abs_product_sum(rp, co, va, xh)[p])
+    assert np.array_equal(got_max, ref_max[p])       # the max VALUE is order-independent (arg ids are relabelled)

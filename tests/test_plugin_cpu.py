@@ -157,7 +157,7 @@ def test_reordering_commutes_with_spmm():
     adj = g.sparse_tensor()
     x = torch.randn(g.n, 5)
     ref = sys.modules["torch_sparse"].matmul(adj, x, "sum")
-    for perm in (reorder.degree_order(adj), reorder.reverse_cuthill_mckee(adj), torch.randperm(g.n)):
+    for perm in (reorder.degree_order(adj), reorder.reverse_cuthill_mckee(adj), reorder.bfs_order(adj), torch.randperm(g.n)):
         assert sorted(perm.tolist()) == list(range(g.n))
         adj_p = reorder.permute(adj, perm)
         out_p = sys.modules["torch_sparse"].matmul(adj_p, x[perm], "sum")

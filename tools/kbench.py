@@ -26,6 +26,8 @@ def main():
     ap.add_argument("--json", default=None)
     ap.add_argument("--bwd", action="store_true", help="also time the backward (A^T SpMM / arg scatter)")
     ap.add_argument("--all", action="store_true", help="time every variant, not only the default candidate set")
+    ap.add_argument("--pad8", action="store_true", help="rows padded to a multiple of 8 floats (32-byte aligned), as the "
+                                                       "op layer / pad_features() lay out widths like 47 or 100")
     a = ap.parse_args()
     if a.all:
         os.environ["ISPLIB_B200_TUNE_ALL"] = "1"
@@ -41,7 +43,7 @@ def main():
         print(f"# {a.shape} m={g.m} nnz={g.nnz} maxdeg={g.max_degree} seg_len={i.seg_len} items={i.num_items} "
               f"split_rows={i.num_split_rows} split_items={i.num_split_items}")
         for k in a.k:
-            kp = (k + 3) // 4 * 4                      # rows padded like the op layer does for odd K
+            kp = (k + 7) // 8 * 8 if a.pad8 else (k + 3) // 4 * 4      # rows padded like the op layer does for odd K
             x = torch.randn(g.n, kp, device=dev)[:, :k]
             for red in a.reduce:
                 best, times = capi.spmm_autotune(red, rp, co, g.value, x, plan, iters=a.iters)
