@@ -680,6 +680,7 @@ def run_ours(args):
                "h2d_bytes_per_step": N * K * 4, "d2h_bytes_per_step": M * K * 4, "ms_per_step": round(ms_e2e, 3),
                "serial_ms_per_step": round(ms_serial, 3),
                "serial_value": round(b_alg / (ms_serial * 1e-3) / 1e9, 2),
+               "host_link_gbs_per_direction": round(N * K * 4 / (ms_e2e * 1e-3) / 1e9, 1),
                "path": "iSpLibPlugin.patch_pyg() -> torch_sparse.matmul(adj_t, X) -> torch.ops.isplib.fusedmm_spmm; "
                        "every step copies its X from pinned host memory and its result back to pinned host memory "
                        "inside the timed region; `value` overlaps the copies of neighbouring steps with the SpMM on "

@@ -18,6 +18,7 @@ ap.add_argument("--reduce", default="sum")
 ap.add_argument("--variant", type=int, default=-1)
 ap.add_argument("--novalue", action="store_true")
 ap.add_argument("--bwd", action="store_true", help="profile the arg-scatter backward (max/min)")
+ap.add_argument("--aux", action="store_true", help="with --bwd: the streamed scatter fed by the forward's col[arg] / val[arg] outputs")
 ap.add_argument("--reps", type=int, default=5)
 a = ap.parse_args()
 dev = "cuda:0"
@@ -30,7 +31,14 @@ if v < 0:
     v = capi.lib().isplib_b200_variant_default(capi.REDUCE_CODE[a.reduce], g.n, a.k, a.k, a.k, x.data_ptr(), x.data_ptr(), 0.0)
 print("variant", v, capi.variant_names()[v])
 out, arg = capi.spmm_csr(a.reduce, rp, co, g.value, x, plan, v)
-if a.bwd:
+if a.bwd and a.aux:
+    go = torch.randn(g.m, a.k, device=dev)
+    acol = torch.empty(g.m, a.k, dtype=torch.int32, device=dev)
+    aval = torch.empty(g.m, a.k, device=dev) if g.value is not None else None
+    capi.spmm_csr(a.reduce, rp, co, g.value, x, plan, v, out=out, arg_out=arg, arg_col=acol, arg_val=aval)
+    for _ in range(a.reps):
+        capi.spmm_arg_backward_aux(acol, aval, go, g.n)
+elif a.bwd:
     go = torch.randn(g.m, a.k, device=dev)
     for _ in range(a.reps):
         capi.spmm_arg_backward(co, g.value, None, arg, go, g.n, True, False)
