@@ -18,7 +18,8 @@ ap.add_argument("--shape", default="amazon")
 ap.add_argument("--k", type=int, default=200)
 ap.add_argument("--reduce", default="max")
 ap.add_argument("--steps", type=int, default=10)
-ap.add_argument("--balance", default="rows", choices=["nnz", "rows"], help="row ranges balanced by stored entries or by rows")
+ap.add_argument("--mode", default=None, choices=["auto", "fused", "nccl"], help="default: auto (measured per width)")
+ap.add_argument("--balance", default="nnz", choices=["nnz", "rows"], help="row ranges balanced by stored entries or by rows")
 ap.add_argument("--prebuild", action="store_true", help="build the transposed (backward) operator before timing")
 ap.add_argument("--sort-degree", action="store_true",
                 help="relabel the nodes by descending degree first (ids sorted by degree: the skewed case)")
@@ -38,7 +39,7 @@ g = synth.make_graph(a.shape, values="uniform", seed=0, device=dev)
 rowptr, col, value = g.rowptr, g.col, g.value
 if a.sort_degree:
     rowptr, col, value = synth.relabel_by_degree(rowptr, col, value, g.n)
-op = DistSpMM(rowptr, col, value, g.n, device=dev, balance=a.balance)
+op = DistSpMM(rowptr, col, value, g.n, device=dev, balance=a.balance, mode=a.mode)
 f = op.fwd
 if a.prebuild and a.reduce in ("sum", "mean"):
     op.bwd_op(a.reduce == "mean")
@@ -94,6 +95,8 @@ if rank == 0:
     print(json.dumps({"shape": a.shape, "nodes": g.m, "nnz": g.nnz, "K": a.k, "reduce": a.reduce, "n_gpus": world,
                       "fwd_ms": round(t_f, 3), "fwd_bwd_ms": round(t_fb, 3), "bwd_ms": round(t_fb - t_f, 3),
                       "fwd_total_effective_gbs": round(b / t_f / 1e6, 1), "balance": a.balance,
+                      "mode": f.mode, "mode_chosen": f.mode_for(a.k, a.reduce) if world > 1 else "single",
+                      "mode_times_ms": f._mode_choice.get((a.k, a.reduce in ("max", "min"))),
                       "sorted_by_degree": bool(a.sort_degree), "row_bounds": f.row_bounds,
                       "nnz_per_rank": nnz_all, "nnz_imbalance": round(max(nnz_all) * world / max(1, sum(nnz_all)), 3)}),
           flush=True)
