@@ -60,7 +60,7 @@ NCU_TRAFFIC_BYTES = {
     # per LAUNCH, like roofline.algorithmic_bytes_per_launch (dram__bytes_read.sum + dram__bytes_write.sum)
     ("reddit", 128, "sum", "seg/w4/u4/kt64"): 5_251_204_000 + 263_436_800,        # profiles/r1_full_spmm_seg_sum_k128_w4u4kt64.txt
     ("reddit", 128, "sum", "lean256/w4/kt64/seq"): 2_571_400_000 + 107_322_880,   # profiles/r1_full_lean256_sum_k128_kt64seq.txt (one of the two 64-wide launches)
-    ("reddit", 128, "sum", "lean256/w4/kt64"): 5_191_105_000 + 309_676_544,       # profiles/r1_full_lean_sum_k128_kt64_prefetch.txt
+    ("reddit", 128, "sum", "lean256/w4/kt64"): 5_196_220_000 + 317_164_032,       # profiles/r2_full_sum.txt (r1: 5.19 + 0.31 GB, r1_full_lean_sum_k128_kt64_prefetch.txt)
 }
 
 

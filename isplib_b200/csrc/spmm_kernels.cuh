@@ -783,6 +783,43 @@ __device__ __forceinline__ void gather_wait_for_item(const GatherParams& G, int 
     __syncwarp();
 }
 
+// max / min update of one accumulator: if (a * x is strictly better than acc) { acc = a * x; arg = e; }
+// The compare and the arg select issue on the ALU pipe; writing acc as a PREDICATED MULTIPLY (the same
+// product again, bit-identical) instead of a select puts that write on the FMA pipe next to the first
+// multiply: 2 + 2 instructions per element on the two half-rate pipes instead of 3 + 1 (both pipes
+// issue one warp instruction every 2 cycles per SM sub-partition; the 3 + 1 split made the ALU pipe
+// the limiter of the max/min kernels).
+#ifndef ISPLIB_ARGTRACK_PREDMUL
+#define ISPLIB_ARGTRACK_PREDMUL 1
+#endif
+template <int OP>
+__device__ __forceinline__ void track_better(float a, float x, int e, float nz, float& acc, int& arg) {
+#if ISPLIB_ARGTRACK_PREDMUL
+    // nz == -0.0f, but opaque to the compiler (derived from a launch parameter): fma(a, x, -0.0) is
+    // a * x bit for bit (one rounding, the sign of a zero product is kept), yet ptxas cannot merge it
+    // with the multiply above it into one FMUL + FSEL
+    if constexpr (OP == OP_MAX) {
+        asm("{\n\t.reg .pred p;\n\t.reg .f32 t;\n\t"
+            "mul.rn.f32 t, %2, %3;\n\t"
+            "setp.gt.f32 p, t, %0;\n\t"
+            "@p fma.rn.f32 %0, %2, %3, %5;\n\t"
+            "selp.s32 %1, %4, %1, p;\n\t}"
+            : "+f"(acc), "+r"(arg) : "f"(a), "f"(x), "r"(e), "f"(nz));
+    } else {
+        asm("{\n\t.reg .pred p;\n\t.reg .f32 t;\n\t"
+            "mul.rn.f32 t, %2, %3;\n\t"
+            "setp.lt.f32 p, t, %0;\n\t"
+            "@p fma.rn.f32 %0, %2, %3, %5;\n\t"
+            "selp.s32 %1, %4, %1, p;\n\t}"
+            : "+f"(acc), "+r"(arg) : "f"(a), "f"(x), "r"(e), "f"(nz));
+    }
+#else
+    (void)nz;
+    const float tt = __fmul_rn(a, x);
+    if (better<OP>(tt, acc)) { acc = tt; arg = e; }
+#endif
+}
+
 // NOVAL (max / min only): val == NULL (SAGE / GIN drop the values) -- no multiply and no value
 // shuffle at all in the hot loop.
 //
@@ -826,6 +863,8 @@ spmm_lean_kernel(const __grid_constant__ SpmmParams p) {
     const char* const xlane = reinterpret_cast<const char*>(p.x + k0);
     const unsigned ldxb = (unsigned)p.ldx * 4u;
     const bool has_val = !NOVAL && (p.val != nullptr);
+    // -0.0f the compiler cannot see through (kp is never negative): see track_better
+    const float neg_zero = __int_as_float((int)(0x80000000u ^ (unsigned)(p.kp < 0)));
 
     float acc[1][VEC];
     int arg[1][VEC];
@@ -877,9 +916,11 @@ spmm_lean_kernel(const __grid_constant__ SpmmParams p) {
                     for (int v = 0; v < VEC; ++v) {
                         if constexpr (OP == OP_SUM) {
                             acc[0][v] = fmaf(aa, xv[u][v], acc[0][v]);
-                        } else {
-                            const float tt = NOVAL ? xv[u][v] : __fmul_rn(aa, xv[u][v]);
+                        } else if constexpr (NOVAL) {
+                            const float tt = xv[u][v];
                             if (better<OP>(tt, acc[0][v])) { acc[0][v] = tt; arg[0][v] = e0 + t + u * NG + g; }
+                        } else {
+                            track_better<OP>(aa, xv[u][v], e0 + t + u * NG + g, neg_zero, acc[0][v], arg[0][v]);
                         }
                     }
                 }
