@@ -286,6 +286,17 @@ int isplib_b200_spmm_arg_backward_aux(int64_t m, int64_t n, int64_t k,
                                       float* grad_x, int64_t ldgx,
                                       int zero_init, isplib_stream_t stream);
 
+/* The same again for a grad_x far beyond L2 (Amazon-shape K=200: 1.25 GB), where every RED of the call
+ * above is a random DRAM read-modify-write: the (target, value) pairs are first partitioned by
+ * target-row range into 8-byte records (workspace: 8 * m * k bytes + 8 KB), then applied range after
+ * range into an L2-resident slab of grad_x.  Same result up to the order of the float adds.        */
+int isplib_b200_spmm_arg_backward_binned_workspace_bytes(int64_t m, int64_t n, int64_t k, size_t* bytes);
+int isplib_b200_spmm_arg_backward_binned(int64_t m, int64_t n, int64_t k,
+                                         const int32_t* arg_col, const float* arg_val, int64_t ld_aux,
+                                         const float* grad_out, int64_t ldgo,
+                                         float* grad_x, int64_t ldgx, int zero_init,
+                                         void* workspace, size_t workspace_bytes, isplib_stream_t stream);
+
 /* Gradient w.r.t. the stored values of the sum / mean SpMM (SDDMM on the CSR pattern):
  *     out_val[e] = < a[row(e),:], x[col[e],:] >   (mean_scale != 0: / max(deg(row(e)),1))
  * with a = grad_out.  The reference never computes it (csrc/fusedmm.cpp:268-272,349-353

@@ -30,6 +30,7 @@ EXPORTS = [
     "isplib_b200_plan_bytes", "isplib_b200_plan_build", "isplib_b200_spmm_workspace_bytes",
     "isplib_b200_spmm_csr", "isplib_b200_spmm_csr_ex", "isplib_b200_spmm_csr_fused",
     "isplib_b200_spmm_arg_backward_aux", "isplib_b200_spmm_csr_gather",
+    "isplib_b200_spmm_arg_backward_binned", "isplib_b200_spmm_arg_backward_binned_workspace_bytes",
     "isplib_b200_plan_grouped_bytes", "isplib_b200_plan_build_grouped",
     "isplib_b200_variant_count", "isplib_b200_variant_name", "isplib_b200_variant_supported",
     "isplib_b200_variant_default", "isplib_b200_spmm_autotune",
@@ -101,6 +102,8 @@ def lib() -> ctypes.CDLL:
     L.isplib_b200_plan_grouped_bytes.argtypes = [i64, i64, i32, i32, ctypes.POINTER(sz)]
     L.isplib_b200_plan_build_grouped.argtypes = [i64, i64, p, p, i32, i32, ctypes.POINTER(i32), ctypes.POINTER(i32), i32,
                                                  p, sz, pinfo, ctypes.POINTER(i64), p]
+    L.isplib_b200_spmm_arg_backward_binned_workspace_bytes.argtypes = [i64, i64, i64, ctypes.POINTER(sz)]
+    L.isplib_b200_spmm_arg_backward_binned.argtypes = [i64, i64, i64, p, p, i64, p, i64, p, i64, ctypes.c_int, p, sz, p]
     L.isplib_b200_spmm_arg_backward_aux.argtypes = [i64, i64, i64, p, p, i64, p, i64, p, i64, ctypes.c_int, p]
     L.isplib_b200_variant_count.restype = ctypes.c_int
     L.isplib_b200_variant_name.restype = ctypes.c_char_p
@@ -373,11 +376,20 @@ def spmm_arg_backward(col32, val, x, arg, grad_out, n: int, need_grad_x=True, ne
     return gx, gv
 
 
-def spmm_arg_backward_aux(arg_col, arg_val, grad_out, n: int):
-    """grad_x from the forward's auxiliary outputs -- isplib_b200_spmm_arg_backward_aux."""
+def spmm_arg_backward_aux(arg_col, arg_val, grad_out, n: int, binned: bool = False):
+    """grad_x from the forward's auxiliary outputs -- isplib_b200_spmm_arg_backward_aux, or
+    (binned=True) the partition-then-apply variant for a grad_x far beyond L2."""
     M, K = grad_out.shape
     dev = grad_out.device
     gx = torch.empty((n, K), dtype=torch.float32, device=dev)
+    if binned:
+        nb = ctypes.c_size_t(0)
+        check(lib().isplib_b200_spmm_arg_backward_binned_workspace_bytes(M, n, K, ctypes.byref(nb)), "binned_ws")
+        ws = _dev_bytes(nb.value, dev)
+        check(lib().isplib_b200_spmm_arg_backward_binned(M, n, K, _p(arg_col), _p(arg_val), arg_col.stride(0) if M > 1 else K,
+                                                         _p(grad_out), grad_out.stride(0) if M > 1 else K, _p(gx), K, 1,
+                                                         _aligned_ptr(ws), nb.value, _stream(dev)), "spmm_arg_backward_binned")
+        return gx
     check(lib().isplib_b200_spmm_arg_backward_aux(M, n, K, _p(arg_col), _p(arg_val), arg_col.stride(0) if M > 1 else K,
                                                   _p(grad_out), grad_out.stride(0) if M > 1 else K, _p(gx), K, 1,
                                                   _stream(dev)), "spmm_arg_backward_aux")

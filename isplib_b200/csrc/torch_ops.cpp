@@ -593,9 +593,22 @@ public:
             Tensor arg_val = saved.size() > 3 ? saved[3] : Tensor();
             const int64_t M = arg_col.size(0), K = arg_col.size(1), N = ctx->saved_data["n"].toInt();
             Tensor grad_mat = torch::empty({N, K}, grad_out.options());
-            ISPLIB_CHECK_STATUS(isplib_b200_spmm_arg_backward_aux(
-                M, N, K, arg_col.data_ptr<int32_t>(), arg_val.defined() ? arg_val.data_ptr<float>() : nullptr, K,
-                grad_out.data_ptr<float>(), K, grad_mat.data_ptr<float>(), K, 1, stream.stream()));
+            const float* av = arg_val.defined() ? arg_val.data_ptr<float>() : nullptr;
+            // grad_mat far beyond L2: partition the (target, value) pairs by target-row range first, so the
+            // adds of a range hit an L2-resident slab instead of being random read-modify-writes in DRAM
+            const bool binned = (double)N * (double)K * 4.0 > 256.0 * 1024 * 1024 && env_int("ISPLIB_B200_ARG_BINNED", 1);
+            if (binned) {
+                size_t wb = 0;
+                ISPLIB_CHECK_STATUS(isplib_b200_spmm_arg_backward_binned_workspace_bytes(M, N, K, &wb));
+                Tensor wst = torch::empty({(int64_t)wb}, grad_out.options().dtype(torch::kUInt8));
+                ISPLIB_CHECK_STATUS(isplib_b200_spmm_arg_backward_binned(
+                    M, N, K, arg_col.data_ptr<int32_t>(), av, K, grad_out.data_ptr<float>(), K,
+                    grad_mat.data_ptr<float>(), K, 1, wst.data_ptr(), wb, stream.stream()));
+            } else {
+                ISPLIB_CHECK_STATUS(isplib_b200_spmm_arg_backward_aux(
+                    M, N, K, arg_col.data_ptr<int32_t>(), av, K, grad_out.data_ptr<float>(), K,
+                    grad_mat.data_ptr<float>(), K, 1, stream.stream()));
+            }
             return {Variable(), Variable(), Variable(), grad_mat};
         }
         auto g = get_graph(saved[0], saved[1]);

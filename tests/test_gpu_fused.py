@@ -87,7 +87,7 @@ def test_fused_epilogue_matches_oracle(capi, oracle, K, reduce, combo):
 @pytest.mark.parametrize("K", [4, 32, 47, 64, 200])
 @pytest.mark.parametrize("reduce", ["max", "min"])
 @pytest.mark.parametrize("with_value", [True, False])
-def test_arg_aux_outputs_and_streamed_backward(capi, oracle, K, reduce, with_value):
+def test_arg_aux_outputs_and_streamed_backward(capi, oracle, K, reduce, with_value, monkeypatch):
     rng = np.random.default_rng(5 + K)
     M, N = 310, 280
     rowptr, col, val = random_csr(rng, M, N, 50, empty_prob=0.08, with_value=with_value, long_rows=[(9, 900)])
@@ -113,6 +113,16 @@ def test_arg_aux_outputs_and_streamed_backward(capi, oracle, K, reduce, with_val
         gx = capi.spmm_arg_backward_aux(arg_col, arg_val, torch.from_numpy(go).to(DEV), N)
         # float atomics add in arrival order: tolerance, not bit-exact
         np.testing.assert_allclose(gx.cpu().numpy(), rgx, rtol=1e-5, atol=1e-5)
+        if v == -1:
+            # the partition-then-apply scatter (what a grad_x far beyond L2 gets), with slabs small
+            # enough that this graph spans many bins, and with the default single bin
+            for slab in ("4096", None):
+                if slab:
+                    monkeypatch.setenv("ISPLIB_B200_BIN_BYTES", slab)
+                else:
+                    monkeypatch.delenv("ISPLIB_B200_BIN_BYTES", raising=False)
+                gb = capi.spmm_arg_backward_aux(arg_col, arg_val, torch.from_numpy(go).to(DEV), N, binned=True)
+                np.testing.assert_allclose(gb.cpu().numpy(), rgx, rtol=1e-5, atol=1e-5)
 
 
 @pytest.mark.parametrize("K", [8, 32, 64, 104, 128, 256])

@@ -19,6 +19,7 @@ ap.add_argument("--variant", type=int, default=-1)
 ap.add_argument("--novalue", action="store_true")
 ap.add_argument("--bwd", action="store_true", help="profile the arg-scatter backward (max/min)")
 ap.add_argument("--aux", action="store_true", help="with --bwd: the streamed scatter fed by the forward's col[arg] / val[arg] outputs")
+ap.add_argument("--binned", action="store_true", help="with --bwd --aux: the partition-then-apply scatter")
 ap.add_argument("--reps", type=int, default=5)
 a = ap.parse_args()
 dev = "cuda:0"
@@ -36,8 +37,17 @@ if a.bwd and a.aux:
     acol = torch.empty(g.m, a.k, dtype=torch.int32, device=dev)
     aval = torch.empty(g.m, a.k, device=dev) if g.value is not None else None
     capi.spmm_csr(a.reduce, rp, co, g.value, x, plan, v, out=out, arg_out=arg, arg_col=acol, arg_val=aval)
+    import time
     for _ in range(a.reps):
-        capi.spmm_arg_backward_aux(acol, aval, go, g.n)
+        capi.spmm_arg_backward_aux(acol, aval, go, g.n, binned=a.binned)
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(a.reps):
+        capi.spmm_arg_backward_aux(acol, aval, go, g.n, binned=a.binned)
+    e1.record()
+    torch.cuda.synchronize()
+    print(f"arg scatter ({'binned' if a.binned else 'direct'}) {e0.elapsed_time(e1) / a.reps:.3f} ms per call")
 elif a.bwd:
     go = torch.randn(g.m, a.k, device=dev)
     for _ in range(a.reps):
