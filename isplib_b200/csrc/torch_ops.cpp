@@ -596,7 +596,8 @@ public:
             const float* av = arg_val.defined() ? arg_val.data_ptr<float>() : nullptr;
             // grad_mat far beyond L2: partition the (target, value) pairs by target-row range first, so the
             // adds of a range hit an L2-resident slab instead of being random read-modify-writes in DRAM
-            const bool binned = (double)N * (double)K * 4.0 > 256.0 * 1024 * 1024 && env_int("ISPLIB_B200_ARG_BINNED", 1);
+            const double binned_min = (double)env_int("ISPLIB_B200_ARG_BINNED_MIN_MB", 256) * 1024.0 * 1024.0;
+            const bool binned = (double)N * (double)K * 4.0 > binned_min && env_int("ISPLIB_B200_ARG_BINNED", 1);
             if (binned) {
                 size_t wb = 0;
                 ISPLIB_CHECK_STATUS(isplib_b200_spmm_arg_backward_binned_workspace_bytes(M, N, K, &wb));

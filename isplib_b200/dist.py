@@ -480,7 +480,16 @@ class RowPartitionedSpMM:
         dev = x_slice.device
         for m in ("fused", "nccl"):
             self._mode_choice[key] = (m,)
-            self.forward(x_slice, reduce)
+            if m == "fused":
+                try:
+                    self.forward(x_slice, reduce)
+                except Exception as ex:      # e.g. no symmetric memory on this box: the NCCL path still works
+                    import warnings
+                    warnings.warn(f"isplib_b200: fused gather kernel unavailable ({ex!r}); using the NCCL path")
+                    times[m] = float("inf")
+                    continue
+            else:
+                self.forward(x_slice, reduce)
             dist.barrier(group=self.group)
             torch.cuda.synchronize(dev)
             e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
@@ -493,7 +502,8 @@ class RowPartitionedSpMM:
             dist.all_reduce(t, op=dist.ReduceOp.MAX, group=self.group)
             times[m] = float(t.item())
         best = min(times, key=times.get)
-        self._mode_choice[key] = (best, round(times["fused"], 4), round(times["nccl"], 4))
+        self._mode_choice[key] = (best, round(times["fused"], 4) if times["fused"] != float("inf") else None,
+                                  round(times["nccl"], 4))
         return best
 
     def _fused_plan(self):

@@ -244,8 +244,13 @@ def test_op_arg_backward_through_aux_equals_general(isplib, oracle, reduce, with
     ref, ref_arg = oracle.spmm_c(rowptr, col, val, mat, oracle.REDUCE_CODE[reduce])
     rgx, _ = oracle.arg_backward(col, val, mat, ref_arg, go, N, False)
     grads = []
-    for aux in ("1", "0"):
-        monkeypatch.setenv("ISPLIB_B200_ARG_AUX", aux)
+    for aux in ("1", "0", "binned"):
+        # "binned": the partition-then-apply scatter the op layer uses for a grad_mat beyond 256 MB,
+        # forced here by dropping that threshold to 0 MB and shrinking the slabs to 2 KB
+        monkeypatch.setenv("ISPLIB_B200_ARG_AUX", "0" if aux == "0" else "1")
+        if aux == "binned":
+            monkeypatch.setenv("ISPLIB_B200_ARG_BINNED_MIN_MB", "0")
+            monkeypatch.setenv("ISPLIB_B200_BIN_BYTES", "2048")
         x = torch.from_numpy(mat).to(DEV).requires_grad_(True)
         out, arg = op(rp, co, va, x)
         assert np.array_equal(out.detach().cpu().numpy(), ref) and np.array_equal(arg.cpu().numpy(), ref_arg)
