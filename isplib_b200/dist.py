@@ -269,6 +269,15 @@ def _cuda_block_spmm(reduce_code, block: CsrBlock, x, out, arg_out, flags, row_d
     from . import capi
     if block.plan is None:
         block.plan = capi.Plan(block.rowptr, block.nnz)
+    if variant < 0 and block.nnz >= (1 << 16) and os.environ.get("ISPLIB_B200_AUTOTUNE", "1") != "0" \
+            and not torch.cuda.is_current_stream_capturing():
+        # on-device variant selection per column block, once per (reduction, width, alignment class):
+        # every rank times its own block (no collective inside), like the single-GPU op layer does
+        key = (int(reduce_code), x.size(1), x.stride(0), x.data_ptr() % 32)
+        tuned = block.__dict__.setdefault("tuned", {})
+        if key not in tuned:
+            tuned[key], _ = capi.spmm_autotune(reduce_code, block.rowptr, block.col, block.val, x, block.plan, iters=2)
+        variant = tuned[key]
     return capi.spmm_csr(reduce_code, block.rowptr, block.col, block.val, x, block.plan, variant,
                          out=out, arg_out=arg_out, flags=flags, row_divisor=row_divisor,
                          edge_ids=block.edge_ids, arg_sentinel=arg_sentinel)

@@ -60,8 +60,9 @@ def test_golden_forward(capi, oracle, name, reduce):
         assert np.array_equal(out.cpu().numpy(), g[f"{reduce}_out"])
         assert np.array_equal(arg.cpu().numpy(), g[f"{reduce}_arg"])
     else:
-        assert_sum_close(out.cpu().numpy(), g[f"{reduce}_out"],
-                         abs_product_sum(g["rowptr"], g["col"], g["value"], g["mat"], mean=(reduce == "mean")))
+        # the golden vectors come from the reference's own operator layer: here the PLAIN north_star
+        # tolerance is asserted (rows are short; no element needs the condition-aware bound)
+        np.testing.assert_allclose(out.cpu().numpy(), g[f"{reduce}_out"], rtol=1e-5, atol=1e-6)
 
 
 @pytest.mark.parametrize("name", GOLDEN_CASES)
