@@ -70,7 +70,7 @@ def main():
         plan = capi.Plan(rp, g.nnz)
         for k in a.k:
             go = torch.randn(g.m, k, device=dev)
-            x = torch.randn(g.n, k, device=dev)
+            x = torch.randn(g.n, (k + 7) // 8 * 8, device=dev)[:, :k] if a.pad8 else torch.randn(g.n, k, device=dev)
             best, times = capi.spmm_autotune("sum", colptr, row_t, vt, go, plan_t, iters=a.iters)
             b = synth.algorithmic_bytes(g.n, g.nnz, k, vt is not None, "sum")
             print(f"K={k:4d} bwd(sum/mean) = A^T SpMM  {names[best]:24s} {times[best]:8.3f} ms  {b / times[best] / 1e6:9.1f} GB/s")
