@@ -366,8 +366,13 @@ class RowPartitionedSpMM:
             self.owner_group, self.n_groups = owner_groups(self.world, self.rank, n_remote_groups)
             # the arrival group THIS rank's slice belongs to at every peer (the pusher needs it)
             self.my_group_at_peer = [owner_groups(self.world, q, n_remote_groups)[0][self.rank] for q in range(self.world)]
-            # the pushes are NVLink-bound, not CTA-bound: 32, 64 and 128 CTAs measure the same (profiles/r2_dist_probe_n8.json)
-            self.copy_ctas = int(os.environ.get("ISPLIB_B200_DIST_COPY_CTAS", "32"))
+            # copy CTAs: one CTA pushes ~8 GB/s of LOADED bytes (4 x 16 B in flight per thread), every loaded
+            # vector is stored to world-1 peers, and the link saturates near 590 GB/s of egress
+            # (profiles/r2_push_probe_n2.json: 16/32/64/128 CTAs -> 129/254/492/587 GB/s to one peer; NCCL's
+            # all-gather of the same slices: 469 GB/s) -> 128 CTAs for one peer, 32 from 7 peers up, where
+            # 32, 64 and 128 measure the same (profiles/r2_dist_probe_n8_push.json)
+            default_ctas = max(32, min(128, (256 // max(1, self.world - 1)) // 32 * 32))
+            self.copy_ctas = int(os.environ.get("ISPLIB_B200_DIST_COPY_CTAS", str(default_ctas)))
             # what the arrival groups of the fused kernel are: "tiles" = the K tiles of the launch
             # (rows stay whole, plain plan; needs >= 2 tiles, i.e. K >= 128 in 64-wide tiles) or
             # "owners" = column owners (grouped plan, rows split per group); "auto" = tiles when possible
