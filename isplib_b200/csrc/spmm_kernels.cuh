@@ -771,14 +771,26 @@ static __device__ __noinline__ void gather_push_role(const GatherParams& G) {
     }
 }
 
-// consumer side: the arrival group of a work item, and the wait for it
-__device__ __forceinline__ void gather_wait_for_item(const GatherParams& G, int item, int tile, int lane) {
-    int g = tile;                        // tile mode: the item's K tile (every item gathers remote rows)
-    if (G.tile_vec4 <= 0) {              // owner mode: group 0 = the rank's own slice, nothing to wait for
-        g = 0;
-        while (g < G.n_groups - 1 && item >= G.group_item_end[g]) ++g;
-        if (g == 0) return;
+// consumer side.  Tile mode: every item of a CTA gathers remote rows of the same K tile, so ONE
+// thread per CTA polls the tile's arrival counter (4x fewer pollers than one per warp, and a backoff
+// up to 4 us: thousands of warps hammering one L2 sector delay the very RED they are waiting for).
+__device__ __forceinline__ void gather_wait_for_tile(const GatherParams& G, int tile) {
+    if (threadIdx.x == 0) {
+        const unsigned long long t0 = global_timer_ns();
+        unsigned ns = 64;
+        while ((int)(ld_acquire_sys(G.arrive_local + tile) - G.arrive_target[tile]) < 0) {
+            __nanosleep(ns);
+            if (ns < 4096) ns <<= 1;
+            if (global_timer_ns() - t0 > kGatherTimeoutNs) { atomicExch(G.status, 1u); break; }
+        }
     }
+    __syncthreads();
+}
+// Owner mode: the arrival group of a work item (group 0 = the rank's own slice: nothing to wait for)
+__device__ __forceinline__ void gather_wait_for_item(const GatherParams& G, int item, int lane) {
+    int g = 0;
+    while (g < G.n_groups - 1 && item >= G.group_item_end[g]) ++g;
+    if (g == 0) return;
     if (lane == 0) wait_reached(G.arrive_local + g, G.arrive_target[g], G.status);
     __syncwarp();
 }
@@ -852,6 +864,8 @@ spmm_lean_kernel(const __grid_constant__ SpmmParams p) {
         }
         bx -= p.gather.copy_ctas;
         if (p.gather.phase == 1) return;          // push-only launch (single-GPU emulation of the ranks)
+        // tile mode: has this CTA's K tile of every peer's slice landed?  (before any warp may leave the CTA)
+        if (p.gather.tile_vec4 > 0) gather_wait_for_tile(p.gather, blockIdx.y + p.tile_base);
     }
     const int item = bx * (blockDim.x >> 5) + (threadIdx.x >> 5);
     if (item >= p.num_items) return;
@@ -879,9 +893,9 @@ spmm_lean_kernel(const __grid_constant__ SpmmParams p) {
         if (has_val) a_next = __ldcs(p.val + eb + lane);
     }
 #endif
-    // fused all-gather: have the rows of this item's arrival group landed?  (checked here, with the
-    // first index chunk already in flight, so the flag's round trip hides behind it)
-    if (p.gather.copy_ctas > 0) gather_wait_for_item(p.gather, item, blockIdx.y + p.tile_base, lane);
+    // fused all-gather, owner mode: have the rows of this item's arrival group landed?  (checked here,
+    // with the first index chunk already in flight, so the flag's round trip hides behind it)
+    if (p.gather.copy_ctas > 0 && p.gather.tile_vec4 <= 0) gather_wait_for_item(p.gather, item, lane);
     for (int e0 = eb; e0 < ee; e0 += 32) {
         const int cnt = min(32, ee - e0);
 #if ISPLIB_LEAN_PREFETCH

@@ -480,7 +480,7 @@ class RowPartitionedSpMM:
 
     def mode_for(self, K: int, reduce: str = "sum", x_slice: Optional[torch.Tensor] = None) -> str:
         """'fused' or 'nccl' for this feature width.  mode='auto' times both once per (K, arg/additive)
-        -- 1 warm-up + 3 forwards each, max over ranks, every rank takes the same decision."""
+        -- 3 warm-up + 10 timed forwards each, max over ranks, every rank takes the same decision."""
         if self.mode != "auto":
             return self.mode
         code = REDUCE_CODE[reduce]
@@ -492,27 +492,28 @@ class RowPartitionedSpMM:
             return "fused"
         times = {}
         dev = x_slice.device
+        WARM, ITERS = 3, 10       # the first launches of either path run cold (plans, symmetric buffers, L2): 1 + 3 was too noisy
         for m in ("fused", "nccl"):
             self._mode_choice[key] = (m,)
-            if m == "fused":
-                try:
+            try:
+                for _ in range(WARM):
                     self.forward(x_slice, reduce)
-                except Exception as ex:      # e.g. no symmetric memory on this box: the NCCL path still works
-                    import warnings
-                    warnings.warn(f"isplib_b200: fused gather kernel unavailable ({ex!r}); using the NCCL path")
-                    times[m] = float("inf")
-                    continue
-            else:
-                self.forward(x_slice, reduce)
+            except Exception as ex:      # e.g. no symmetric memory on this box: the NCCL path still works
+                if m != "fused":
+                    raise
+                import warnings
+                warnings.warn(f"isplib_b200: fused gather kernel unavailable ({ex!r}); using the NCCL path")
+                times[m] = float("inf")
+                continue
             dist.barrier(group=self.group)
             torch.cuda.synchronize(dev)
             e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
             e0.record()
-            for _ in range(3):
+            for _ in range(ITERS):
                 self.forward(x_slice, reduce)
             e1.record()
             torch.cuda.synchronize(dev)
-            t = torch.tensor([e0.elapsed_time(e1) / 3.0], device=dev, dtype=torch.float64)
+            t = torch.tensor([e0.elapsed_time(e1) / ITERS], device=dev, dtype=torch.float64)
             dist.all_reduce(t, op=dist.ReduceOp.MAX, group=self.group)
             times[m] = float(t.item())
         best = min(times, key=times.get)
