@@ -272,7 +272,12 @@ Tensor permuted_values(GraphEntry& e, const c10::optional<Tensor>& value, bool m
 //      does not require grad (activations change every step; caching them would only pin memory).
 struct DenseOperand { Tensor t; int64_t ld; };
 
-struct PadCacheEntry { GraphEntry::TensorId id; Tensor padded; };
+struct PadCacheEntry {
+    GraphEntry::TensorId id;
+    int64_t rows = 0, cols = 0, stride0 = 0, stride1 = 0;   // the view the copy was made from (same storage, other layout = miss)
+    Tensor padded;
+    std::shared_ptr<at::cuda::CUDAEvent> ready;              // the pad kernel ran on the stream that first needed it
+};
 std::mutex& g_pad_mu = *new std::mutex();
 std::vector<PadCacheEntry>& g_pad_cache = *new std::vector<PadCacheEntry>();   // leaked like g_cache
 constexpr size_t kPadCacheEntries = 4;
@@ -302,10 +307,19 @@ DenseOperand dense_operand(const Tensor& mat_in, bool cacheable) {
     }
     if (!want_pad) return {mat_in.contiguous(), K};   // csrc/fusedmm.cpp:140
     const c10::optional<Tensor> key(mat_in);
+    auto stream = at::cuda::getCurrentCUDAStream();
     {
         std::lock_guard<std::mutex> lk(g_pad_mu);
-        for (auto& e : g_pad_cache)
-            if (e.id.matches(key) && e.padded.size(0) == N && e.padded.size(1) == Kp) return {e.padded.narrow(1, 0, K), Kp};
+        for (auto& e : g_pad_cache) {
+            if (e.id.matches(key) && e.rows == N && e.cols == K && e.stride0 == mat_in.stride(0) &&
+                e.stride1 == mat_in.stride(1) && e.padded.size(1) == Kp) {
+                // produced on another stream?  (no cross-stream wait while capturing a CUDA graph: the
+                // producer finished long before, during the warm-up the capture contract requires)
+                if (at::cuda::currentStreamCaptureStatus() == at::cuda::CaptureStatus::None) e.ready->block(stream);
+                c10::cuda::CUDACachingAllocator::recordStream(e.padded.storage().data_ptr(), stream);
+                return {e.padded.narrow(1, 0, K), Kp};
+            }
+        }
     }
     Tensor padded = at::constant_pad_nd(mat_in, {0, Kp - K}, 0);
     if (cacheable) {
@@ -315,7 +329,10 @@ DenseOperand dense_operand(const Tensor& mat_in, bool cacheable) {
         if (g_pad_cache.size() >= kPadCacheEntries) g_pad_cache.erase(g_pad_cache.begin());
         PadCacheEntry e;
         e.id.assign(key);
+        e.rows = N; e.cols = K; e.stride0 = mat_in.stride(0); e.stride1 = mat_in.stride(1);
         e.padded = padded;
+        e.ready = std::make_shared<at::cuda::CUDAEvent>();
+        e.ready->record(stream);
         g_pad_cache.push_back(std::move(e));
     }
     return {padded.narrow(1, 0, K), Kp};
