@@ -741,7 +741,7 @@ def run_ours(args):
         return 0
 
     peak, peak_src = peaks()
-    kernel_name = ("isplib::spmm_lean_kernel (its first CTAs pull the peers' X slices over NVLink: gather + SpMM in one launch)"
+    kernel_name = ("isplib::spmm_lean_kernel (its first CTAs push the rank's X slice to the peers over NVLink: all-gather + SpMM in one launch)"
                    if variant_name.startswith("fused-gather")
                    else "isplib::spmm_lean_kernel" if variant_name.startswith("lean")
                    else "isplib::spmm_bulk_kernel" if variant_name.startswith("bulk")

@@ -25,15 +25,16 @@ One process per GPU (``torchrun``), ``torch.distributed`` over NCCL/NVLink.
   backward (max/min): local arg-scatter into a zeroed [P*R, K] partial, then
   reduce-scatter(sum).
 
-* ``mode="fused"`` (the default on CUDA with more than one rank): NO collective call at all.  The
-  rank's whole row block is ONE CSR over the owner-major gathered columns with a *grouped* plan
-  (work items ordered by the arrival group of their columns), X lives in a double-buffered
-  symmetric-memory allocation, and ONE kernel (``isplib_b200_spmm_csr_gather``) pulls the peers'
-  slices over NVLink with its first CTAs while the others multiply -- each item as soon as the
-  slices of its group have landed.  Peers are told "my slice is readable" by a release store into
-  their ready words at kernel start; nobody waits for a barrier kernel.  max/min/mean need no
-  cross-block merge any more (a row is one CSR row again), so results equal the 1-GPU kernel's.
-  ``mode="nccl"`` keeps the all-gather + two-block path below.
+* ``mode="fused"``: NO collective call at all.  The rank's whole row block is ONE CSR over the
+  owner-major gathered columns, X lives in a double-buffered symmetric-memory allocation, and ONE
+  kernel (``isplib_b200_spmm_csr_gather``) pushes the rank's own slice into every peer's buffer over
+  NVLink with its first CTAs while the others multiply -- each work item as soon as the rows of its
+  arrival group (a K tile of the launch, or a group of column owners with a grouped plan) have
+  landed.  Flow control by credit words ("I have started step e"), arrivals by release-adds on the
+  peer's counters; nobody waits for a barrier kernel.  max/min/mean need no cross-block merge any
+  more (a row is one CSR row again), so results equal the 1-GPU kernel's.
+* ``mode="nccl"`` keeps the all-gather + two-block path below; ``mode="auto"`` (the default on CUDA
+  with more than one rank) builds both and times them per feature width on first use.
 
 The block SpMM is injectable (``block_spmm``) so the partitioning / merge logic can be
 tested on CPU with gloo; the default is the CUDA C ABI (isplib_b200.capi) and there is no
@@ -608,7 +609,7 @@ class RowPartitionedSpMM:
 
     def phase_split(self, x_slice, reduce: str = "sum", steps: int = 10):
         """{'forward', 'multiply_only'} ms (max over ranks): the fused forward vs the same kernel and
-        plan on an already gathered X (no pulls, no waits); the difference is what the gather costs."""
+        plan on an already gathered X (no pushes, no waits); the difference is what the gather costs."""
         from . import capi
         assert self.mode_for(x_slice.size(1), reduce) == "fused"
         K = x_slice.size(1)

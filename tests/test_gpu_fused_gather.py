@@ -1,7 +1,7 @@
 """GPU tests (-m gpu, ONE GPU) of the fused all-gather + SpMM kernel and its grouped plan.
 
-The multi-GPU forward pulls the peers' slices of X over NVLink inside the SpMM kernel
-(isplib_b200_spmm_csr_gather).  Everything but the NVLink hop is exercised here on one device: the
+The multi-GPU forward moves the slices of X over NVLink inside the SpMM kernel (the copy CTAs push
+the rank's slice into the peers' buffers; isplib_b200_spmm_csr_gather).  Everything but the NVLink hop is exercised here on one device: the
 "peers" are ordinary local buffers (RowPartitionedSpMM(emulate=...)), so the copy CTAs, the arrival
 flags, the group-ordered work items and the in-kernel merge of split rows all run for real, and the
 assembled result must equal the single-GPU oracle: max/min/arg bit-exact, sum/mean in tolerance.
