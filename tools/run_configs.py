@@ -46,7 +46,7 @@ def run_shape(shape, ks, reduces, values, rows, iters):
     hv = g.value is not None
     pk = peak()
     for k in ks:
-        kp = (k + 3) // 4 * 4
+        kp = (k + 7) // 8 * 8                         # the op layer's / pad_features() layout: rows padded to 32 bytes
         x = torch.randn(g.n, kp, device=DEV)[:, :k]
         go = torch.randn(g.m, kp, device=DEV)[:, :k]
         for red in reduces:
@@ -65,10 +65,16 @@ def run_shape(shape, ks, reduces, values, rows, iters):
                     b = 4 * (g.m + 1) + 4 * g.nnz + 4 * k * g.nnz + 4 * k * g.m + 4 * g.nnz
                     rows.append((shape, g.m, g.nnz, k, red, "bwd grad_value (SDDMM)", "sddmm_lean256 / sddmm_seg", t, 2 * g.nnz * k / t / 1e6, b / t / 1e6, b / t / 1e6 / pk))
             else:
-                _, arg = capi.spmm_csr(red, rp, co, g.value, x, plan, best)
-                t = ev_time(lambda: capi.spmm_arg_backward(co, g.value, None, arg, go.contiguous(), g.n, True, False), iters)
-                b = (8 + 4 + 4 + (4 if hv else 0) + 8) * k * g.m + 4 * k * g.n
-                rows.append((shape, g.m, g.nnz, k, red, "bwd (arg scatter)", "arg_backward_kernel", t, 2 * k * g.m / t / 1e6, b / t / 1e6, b / t / 1e6 / pk))
+                # the op layer's path: the forward also writes col[arg] / val[arg]; the backward streams them
+                # (direct REDs while grad_x can be L2-resident, partition-then-apply beyond 256 MB)
+                acol = torch.empty(g.m, k, dtype=torch.int32, device=DEV)
+                aval = torch.empty(g.m, k, device=DEV) if hv else None
+                capi.spmm_csr(red, rp, co, g.value, x, plan, best, arg_col=acol, arg_val=aval)
+                binned = g.n * k * 4 > 256 * 2**20
+                goc = go.contiguous()
+                t = ev_time(lambda: capi.spmm_arg_backward_aux(acol, aval, goc, g.n, binned=binned), iters)
+                b = (4 + 4 + (4 if hv else 0) + 8) * k * g.m + 4 * k * g.n      # SURVEY 8d with the 4-byte aux stream instead of the 8-byte arg + col gather
+                rows.append((shape, g.m, g.nnz, k, red, "bwd (arg scatter)", "arg_backward_binned" if binned else "arg_backward_aux_kernel", t, 2 * k * g.m / t / 1e6, b / t / 1e6, b / t / 1e6 / pk))
             print(rows[-2], flush=True)
             print(rows[-1], flush=True)
     del g
