@@ -585,28 +585,6 @@ class RowPartitionedSpMM:
                              arg_out=arg, edge_ids=full.edge_ids, arg_sentinel=self.nnz, bias=bias, relu=relu)
         return out, arg
 
-    def fused_variant(self, K: int, reduce: str = "sum") -> int:
-        """The kernel variant the C ABI's AUTO rule picks for the fused forward at width K (lean
-        kernels, one launch: 64-wide K tiles when they make the slab of X L2-resident), as an id."""
-        from . import capi
-        names = capi.variant_names()
-        n = self.world * self.Rc
-        x_bytes = n * K * 4.0
-        pb = self.peer_buffers(K)
-        x = pb.bufs[0][:, :K]
-        cands = []
-        if self._tile_variant(K, capi.REDUCE_CODE[reduce], x) >= 0:
-            return -1        # tile mode picks lean256/w4/kt64 itself (forward sets it per call)
-        if x_bytes > 96 * 2**20 and K > 64 and n * 256.0 <= 64 * 2**20:
-            cands.append("lean256/w4/kt64")
-        cands += ["lean256/w4/kfull", "lean128/w4/kfull"]
-        L = capi.lib()
-        for nm in cands:
-            v = names.index(nm)
-            if L.isplib_b200_variant_supported(v, capi.REDUCE_CODE[reduce], K, x.stride(0), K, x.data_ptr(), x.data_ptr()):
-                return v
-        return -1
-
     def phase_split(self, x_slice, reduce: str = "sum", steps: int = 10):
         """{'forward', 'multiply_only'} ms (max over ranks): the fused forward vs the same kernel and
         plan on an already gathered X (no pushes, no waits); the difference is what the gather costs."""

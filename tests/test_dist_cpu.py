@@ -244,3 +244,28 @@ def test_patched_matmul_dispatches_partitioned_adjacency_world2_gloo():
     for rank in range(world):
         bad = [k for k, v in results[rank].items() if not v]
         assert not bad, f"rank {rank}: {bad}"
+
+
+def test_owner_groups_and_runs_of_the_fused_gather():
+    """Host logic of the fused gather's owner mode: arrival groups by ring distance (own slice = group 0,
+    every group non-empty, sizes within one of each other), and the contiguous owner runs handed to
+    isplib_b200_plan_build_grouped (run starts ascending from column 0, adjacent runs differ in group)."""
+    from isplib_b200.dist import owner_groups, group_runs
+    for world in (1, 2, 3, 4, 8, 16):
+        for G in (1, 2, 3, 7):
+            for rank in range(world):
+                groups, n_groups = owner_groups(world, rank, G)
+                assert len(groups) == world and groups[rank] == 0
+                assert n_groups == (min(G, world - 1) + 1 if world > 1 else 1)
+                remote = [groups[(rank + d) % world] for d in range(1, world)]
+                assert remote == sorted(remote)                       # nearer peers land earlier
+                if world > 1:
+                    sizes = [remote.count(g) for g in range(1, n_groups)]
+                    assert min(sizes) >= 1 and max(sizes) - min(sizes) <= 1
+                starts, grp = group_runs(groups, 10)
+                assert starts[0] == 0 and starts == sorted(starts) and len(starts) == len(grp)
+                assert all(a != b for a, b in zip(grp, grp[1:]))
+                # expanding the runs gives back the per-owner groups
+                ends = starts[1:] + [world * 10]
+                expanded = [g for s, e, g in zip(starts, ends, grp) for _ in range((e - s) // 10)]
+                assert expanded == groups
