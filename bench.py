@@ -540,6 +540,63 @@ def e2e_legs(torch, dev, run, x_host, out_hosts, in_shape, n_e2e, barrier):
     return ms_serial, a0.elapsed_time(a1) / n_e2e
 
 
+def other_shapes_table(torch, capi, synth, peak):
+    """The HBM-regime configs of BASELINE.json on this GPU, one row each (N=1): products-shape K=256 / 100 sum
+    (configs[2]'s layers), proteins-shape K=128 value-free mean (configs[3]), Amazon-shape K=200 max forward +
+    argmax backward (configs[4]).  Autotuned variant, median of 3 launches, frac = B_alg / ms / HBM peak."""
+    dev = "cuda:0"
+    names = capi.variant_names()
+
+    def med_ms(fn, n=3):
+        fn()
+        ts = []
+        for _ in range(n):
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            fn()
+            e1.record()
+            torch.cuda.synchronize()
+            ts.append(e0.elapsed_time(e1))
+        ts.sort()
+        return ts[len(ts) // 2]
+
+    rows = []
+    for shape, values, cases in (("products", "gcn", [(256, "sum"), (100, "sum")]),
+                                 ("proteins", None, [(128, "mean")]),
+                                 ("amazon", "uniform", [(200, "max")])):
+        g = synth.make_graph(shape, values=values, seed=0, device=dev)
+        rp, co = capi.narrow_i64_to_i32(g.rowptr), capi.narrow_i64_to_i32(g.col)
+        plan = capi.Plan(rp, g.nnz)
+        hv = g.value is not None
+        for K, reduce in cases:
+            kp = (K + 7) // 8 * 8
+            x = torch.randn(g.n, kp, device=dev)[:, :K]            # rows padded to 32 bytes, as the op layer lays them out
+            best, _ = capi.spmm_autotune(reduce, rp, co, g.value, x, plan, iters=2)
+            out = torch.empty(g.m, K, device=dev)
+            is_arg = reduce in ("max", "min")
+            arg = torch.empty(g.m, K, dtype=torch.int64, device=dev) if is_arg else None
+            ms = med_ms(lambda: capi.spmm_csr(reduce, rp, co, g.value, x, plan, best, out=out, arg_out=arg))
+            b = synth.algorithmic_bytes(g.m, g.nnz, K, hv, reduce)
+            row = {"shape": shape, "nodes": g.m, "nnz": g.nnz, "K": K, "reduce": reduce, "has_value": hv,
+                   "fwd_ms": round(ms, 3), "fwd_frac": round(b / ms / 1e6 / peak, 3), "fwd_variant": names[best]}
+            if is_arg:
+                acol = torch.empty(g.m, K, dtype=torch.int32, device=dev)
+                aval = torch.empty(g.m, K, device=dev) if hv else None
+                go = torch.randn(g.m, K, device=dev)
+                capi.spmm_csr(reduce, rp, co, g.value, x, plan, best, out=out, arg_out=arg, arg_col=acol, arg_val=aval)
+                binned = g.n * K * 4 > 256 * 2**20
+                msb = med_ms(lambda: capi.spmm_arg_backward_aux(acol, aval, go, g.n, binned=binned))
+                bb = (4 + (4 if hv else 0) + 4 + 8) * K * g.m + 4 * K * g.n
+                row.update({"bwd": "arg scatter, partition-then-apply" if binned else "arg scatter (aux streams)",
+                            "bwd_ms": round(msb, 3), "bwd_frac": round(bb / msb / 1e6 / peak, 3)})
+                del acol, aval, go
+            rows.append(row)
+            del x, out, arg
+        del g, rp, co, plan
+        torch.cuda.empty_cache()
+    return rows
+
+
 def run_ours(args):
     import torch
     import torch.distributed as dist
@@ -740,6 +797,15 @@ def run_ours(args):
             dist.destroy_process_group()
         return 0
 
+    hbm_table = None
+    if world == 1 and not args.no_configs and args.shape == "reddit":
+        try:
+            del g, xs
+            torch.cuda.empty_cache()
+            hbm_table = other_shapes_table(torch, capi, synth, peaks()[0])
+        except Exception as ex:
+            hbm_table = [{"error": repr(ex)[:300]}]
+
     peak, peak_src = peaks()
     kernel_name = ("isplib::spmm_lean_kernel (its first CTAs push the rank's X slice to the peers over NVLink: all-gather + SpMM in one launch)"
                    if variant_name.startswith("fused-gather")
@@ -793,6 +859,8 @@ def run_ours(args):
         line["parity_check"] = parity
     if cfg_table is not None:
         line["configs"] = cfg_table
+    if hbm_table is not None:
+        line["configs_other_shapes"] = hbm_table
     if tune:
         line["autotune_ms"] = tune
     if e2e is not None:
