@@ -210,7 +210,7 @@ def spmm_csr_gather(reduce, rowptr32, col32, val, x_gathered, plan, *, world: in
                     epoch: int, parity_launch: int, tile_mode: bool = False, phase: int = 0,
                     copy_ctas: int = 0, variant: int = VARIANT_AUTO, out=None, arg_out=None, row_divisor=None,
                     edge_ids=None, arg_sentinel: Optional[int] = None, bias=None, addend=None,
-                    addend_scale: float = 1.0, relu: bool = False, spmm_flags: int = 0):
+                    addend_scale: float = 1.0, relu: bool = False, spmm_flags: int = 0, arg_col=None, arg_val=None):
     """Fused all-gather + SpMM (isplib_b200_spmm_csr_gather).  x_gathered: the LOCAL [world *
     slice_rows, K] buffer of this step's parity whose own slice already holds this step's rows;
     peer_x / peer_arrive / peer_credit: the device addresses (ints) of every rank's buffer / arrival
@@ -247,6 +247,10 @@ def spmm_csr_gather(reduce, rowptr32, col32, val, x_gathered, plan, *, world: in
         epi.addend = addend.data_ptr()
         epi.ld_addend = addend.stride(0) if addend.size(0) > 1 else max(K, addend.stride(0))
         epi.addend_scale = float(addend_scale)
+    if arg_col is not None:
+        epi.arg_col = arg_col.data_ptr()
+        if arg_val is not None:
+            epi.arg_val = arg_val.data_ptr()
     ldx = x_gathered.stride(0) if N > 1 else max(K, x_gathered.stride(0))
     ldo = out.stride(0) if M > 1 else max(K, out.stride(0))
     st = lib().isplib_b200_spmm_csr_gather(

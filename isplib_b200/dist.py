@@ -427,9 +427,11 @@ class RowPartitionedSpMM:
         dist.all_gather_into_tensor(gathered, x_slice, group=self.group)
         return gathered
 
-    def forward(self, x_slice: torch.Tensor, reduce: str = "sum"):
+    def forward(self, x_slice: torch.Tensor, reduce: str = "sum", aux=None):
         """x_slice: [Rc, K] (use pad_x).  Returns (out [R, K], arg_out [R, K] int64 or None);
-        rows beyond own_rows are padding (zeros / init values)."""
+        rows beyond own_rows are padding (zeros / init values).  ``aux``: max/min in fused mode only -- a
+        dict that receives 'arg_col' / 'arg_val' ([R, K]: the winner's column, as a position in the
+        gathered layout, and its value) for the streamed backward scatter."""
         code = REDUCE_CODE[reduce]
         is_arg = code in (MAX, MIN)
         K = x_slice.size(1)
@@ -443,7 +445,7 @@ class RowPartitionedSpMM:
             return out, arg
 
         if self.mode_for(K, reduce, x_slice) == "fused":
-            return self._forward_fused(x_slice, code, out, arg)
+            return self._forward_fused(x_slice, code, out, arg, aux=aux if is_arg else None)
 
         if self.pipelined:
             return self._forward_pipelined(x_slice, inner, div, out, arg)
@@ -556,7 +558,7 @@ class RowPartitionedSpMM:
         ok = capi.lib().isplib_b200_variant_supported(v, code, K, x.stride(0), K, x.data_ptr(), x.data_ptr())
         return v if ok else -1
 
-    def _forward_fused(self, x_slice, code, out, arg, bias=None, relu=False, phase=0):
+    def _forward_fused(self, x_slice, code, out, arg, bias=None, relu=False, phase=0, aux=None):
         """phase 0: the product path (push + multiply in one launch).  phases 1 / 2 split a step into
         its push and its multiply half: only for several ranks emulated on ONE GPU (emulated_step)."""
         from . import capi
@@ -576,13 +578,19 @@ class RowPartitionedSpMM:
         plan, variant, groups = self.fused_plan_and_variant(K, code)
         tile_mode = groups == "K tiles"
         self._tiles_used[K] = tile_mode
+        arg_col = arg_val = None
+        if aux is not None:
+            arg_col = torch.empty((self.R, K), dtype=torch.int32, device=x_slice.device)
+            arg_val = torch.empty((self.R, K), dtype=torch.float32, device=x_slice.device) if full.val is not None else None
+            aux["arg_col"], aux["arg_val"] = arg_col, arg_val
         capi.spmm_csr_gather(code, full.rowptr, full.col, full.val, xg, plan,
                              world=self.world, rank=self.rank, peer_x=pb.peer_x(b), peer_arrive=pb.peer_arrive(b),
                              peer_credit=pb.peer_credit(), owner_group=self.owner_group,
                              my_group_at_peer=self.my_group_at_peer, slice_rows=self.Rc, status=self._gflags[K],
                              epoch=epoch, parity_launch=(epoch + 1) // 2, tile_mode=tile_mode, phase=phase,
                              copy_ctas=self.copy_ctas, variant=variant, out=out,
-                             arg_out=arg, edge_ids=full.edge_ids, arg_sentinel=self.nnz, bias=bias, relu=relu)
+                             arg_out=arg, edge_ids=full.edge_ids, arg_sentinel=self.nnz, bias=bias, relu=relu,
+                             arg_col=arg_col, arg_val=arg_val)
         return out, arg
 
     def phase_split(self, x_slice, reduce: str = "sum", steps: int = 10):
@@ -765,8 +773,13 @@ class DistSpMM:
 class _DistSpMMFn(torch.autograd.Function):
     @staticmethod
     def forward(ctx, x_slice, op: DistSpMM, reduce: str):
-        out, arg = op.fwd.forward(x_slice.contiguous(), reduce)
+        # max/min through the fused kernel: let its final store also write col[arg] / val[arg] (positions in
+        # the gathered layout = the scatter targets of the backward), so the backward streams them instead of
+        # gathering through a rank-local copy of the GLOBAL column array
+        aux = {} if (REDUCE_CODE[reduce] in (MAX, MIN) and x_slice.requires_grad) else None
+        out, arg = op.fwd.forward(x_slice.contiguous(), reduce, aux=aux)
         ctx.op, ctx.reduce = op, reduce
+        ctx.aux = aux if aux else None            # stays empty when the NCCL path ran
         if arg is not None:
             ctx.save_for_backward(arg)
         return out
@@ -787,6 +800,14 @@ class _DistSpMMFn(torch.autograd.Function):
         (arg,) = ctx.saved_tensors
         f = op.fwd
         dev = grad_out.device
+        if ctx.aux is not None:
+            from . import capi
+            n_rows = f.world * f.Rc
+            binned = n_rows * grad_out.size(1) * 4 > 256 * 2**20
+            partial = capi.spmm_arg_backward_aux(ctx.aux["arg_col"], ctx.aux["arg_val"], grad_out, n_rows, binned=binned)
+            out = torch.empty((f.Rc, partial.size(1)), dtype=partial.dtype, device=dev)
+            dist.reduce_scatter_tensor(out, partial, group=f.group)
+            return out, None, None
         if op._col32 is None:
             # scatter target = position of the column in the width-padded gathered layout
             op._col32 = slice_position(op.col.to(dev).to(torch.int64), f.col_bounds, f.Rc).to(torch.int32)
