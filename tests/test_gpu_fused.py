@@ -391,3 +391,56 @@ def test_reordering_on_device_commutes_with_cuda_spmm(isplib, oracle, order):
     ref_max = oracle.spmm_c(rp, co, va, xh, oracle.MAX)[0]
     assert_sum_close(got_sum, ref_sum[p], abs_product_sum(rp, co, va, xh)[p])
     assert np.array_equal(got_max, ref_max[p])       # the max VALUE is order-independent (arg ids are relabelled)
+
+
+# ------------------------------------------- caller-level golden vectors from the reference's operator layer
+def _caller_cases():
+    from conftest import CALLER_CASES
+    return CALLER_CASES
+
+
+@pytest.mark.parametrize("name", _caller_cases())
+def test_fused_layers_match_reference_caller_goldens(isplib, name):
+    """isplib_b200.nn layers with their fused epilogues (bias + ReLU in the SpMM's final store, GIN's self
+    term as the kernel's addend, SAGE's accumulate-GEMM) against what the reference's operator layer + the
+    callers' torch ops give on CPU (tests/golden/make_golden_callers.py): outputs and every gradient."""
+    import os
+    import torch_sparse
+    from conftest import GOLDEN_DIR
+    from isplib import iSpLibPlugin
+    from isplib_b200 import nn as gnn
+    z = np.load(os.path.join(GOLDEN_DIR, name + ".npz"))
+    M = z["x"].shape[0]
+    val = torch.from_numpy(z["value"]).to(DEV) if "value" in z.files else None
+    adj = torch_sparse.SparseTensor(rowptr=torch.from_numpy(z["rowptr"]).to(DEV), col=torch.from_numpy(z["col"]).to(DEV),
+                                    value=val, sparse_sizes=(M, M), is_sorted=True)
+    t = lambda k: torch.from_numpy(z[k]).to(DEV)
+    close = lambda a, k: np.testing.assert_allclose(a.detach().cpu().numpy(), z[k], rtol=2e-4, atol=2e-5, err_msg=k)
+    iSpLibPlugin.patch_pyg()
+    try:
+        # GCN layer + ReLU (PyG order)
+        conv = gnn.GCNConv(z["W"].shape[1], z["W"].shape[0], order="linear_first", relu=True).to(DEV)
+        with torch.no_grad():
+            conv.lin.weight.copy_(t("W"))
+            conv.bias.copy_(t("b"))
+        x = t("x").requires_grad_(True)
+        out = conv(x, adj)
+        out.backward(t("grad_out"))
+        close(out, "gcn_out"); close(x.grad, "gcn_grad_x"); close(conv.lin.weight.grad, "gcn_grad_W"); close(conv.bias.grad, "gcn_grad_b")
+        # GIN aggregation input
+        gin = gnn.GINConv(torch.nn.Identity(), eps=float(z["eps"]))
+        x = t("x").requires_grad_(True)
+        out = gin(x, adj)
+        out.backward(t("grad_in"))
+        close(out, "gin_out"); close(x.grad, "gin_grad_x")
+        # SAGE-mean layer
+        sage = gnn.SAGEConv(z["W"].shape[1], z["W"].shape[0], aggr="mean").to(DEV)
+        with torch.no_grad():
+            sage.lin_l.weight.copy_(t("W")); sage.lin_l.bias.copy_(t("b")); sage.lin_r.weight.copy_(t("Wr"))
+        x = t("x").requires_grad_(True)
+        out = sage(x, adj)
+        out.backward(t("grad_out"))
+        close(out, "sage_out"); close(x.grad, "sage_grad_x"); close(sage.lin_l.weight.grad, "sage_grad_Wl")
+        close(sage.lin_l.bias.grad, "sage_grad_b"); close(sage.lin_r.weight.grad, "sage_grad_Wr")
+    finally:
+        iSpLibPlugin.unpatch_pyg()

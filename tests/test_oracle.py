@@ -145,3 +145,20 @@ def test_unsupported_message_status(oracle):
     st = lib.fusedMM_csr(0x11101, 1, 1, 1, 1.0, 0, 1, 1, None, None, oracle._ptr(rp),
                          ctypes.c_void_p(rp.ctypes.data + 8), None, 1, None, 1, 0.0, oracle._ptr(z), 1, None)
     assert st == 128   # FUSEDMM_NO_OPT_IMPL, csrc/fusedMM.h:114
+
+
+def test_oracle_epilogue_matches_the_reference_callers(oracle):
+    """The epilogue restatement (oracle.apply_epilogue) against vectors produced by the reference's own
+    operator layer + the torch ops its callers apply (tests/golden/make_golden_callers.py)."""
+    from conftest import CALLER_CASES, GOLDEN_DIR
+    import os
+    assert len(CALLER_CASES) >= 2
+    for name in CALLER_CASES:
+        z = np.load(os.path.join(GOLDEN_DIR, name + ".npz"))
+        val = z["value"] if "value" in z.files else None
+        h = (z["x"] @ z["W"].T).astype(np.float32)
+        agg = oracle.spmm_c(z["rowptr"], z["col"], val, h, oracle.SUM)[0]
+        np.testing.assert_allclose(oracle.apply_epilogue(agg, bias=z["b"], relu=True), z["gcn_out"], rtol=1e-5, atol=1e-5)
+        agg = oracle.spmm_c(z["rowptr"], z["col"], None, z["x"], oracle.SUM)[0]
+        np.testing.assert_allclose(oracle.apply_epilogue(agg, addend=z["x"], addend_scale=1.0 + float(z["eps"])),
+                                   z["gin_out"], rtol=1e-5, atol=1e-5)
