@@ -562,6 +562,8 @@ class RowPartitionedSpMM:
         """phase 0: the product path (push + multiply in one launch).  phases 1 / 2 split a step into
         its push and its multiply half: only for several ranks emulated on ONE GPU (emulated_step)."""
         from . import capi
+        if self._emulated is not None and phase == 0:
+            raise RuntimeError("emulated ranks cannot run the fused step in one launch: use dist.emulated_step()")
         K = x_slice.size(1)
         pb = self.peer_buffers(K)
         if phase != 2:
@@ -571,8 +573,6 @@ class RowPartitionedSpMM:
         own = pb.own_slice(b)
         if phase != 2 and x_slice.data_ptr() != own.data_ptr():
             own.copy_(x_slice)                     # staging copy into the peer-visible buffer (Rc x K)
-        if self._emulated is not None and phase == 0:
-            raise RuntimeError("emulated ranks cannot run the fused step in one launch: use dist.emulated_step()")
         full = self.full
         xg = pb.bufs[b][:, :K]
         plan, variant, groups = self.fused_plan_and_variant(K, code)
