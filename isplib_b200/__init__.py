@@ -130,7 +130,8 @@ class iSpLibPlugin:
     @classmethod
     def partition(cls, adj_t, device=None, **kw):
         """Row-partition `adj_t` over the ranks of the group given to ``patch_pyg(group=...)`` (default:
-        the world group).  The result goes wherever the SparseTensor went: ``matmul(padj, x_slice, reduce)``."""
+        the world group).  The result goes wherever the SparseTensor went: ``matmul(padj, x_slice, reduce)``.
+        ``local_rows=True``: `adj_t` is only this rank's block of rows (rank-local ingest, see dist.partition)."""
         from .dist import partition
         return partition(adj_t, group=cls.dist_group, device=device, **kw)
 

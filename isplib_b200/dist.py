@@ -125,7 +125,7 @@ def split_row_block(rowptr: torch.Tensor, col: torch.Tensor, val: Optional[torch
     r0, r1 = row_bounds[rank], row_bounds[rank + 1]
     e0, e1 = int(rowptr[r0]), int(rowptr[r1])
     dev = col.device
-    sub_col = col[e0:e1]
+    sub_col = col[e0:e1].to(torch.int64)
     sub_val = None if val is None else val[e0:e1]
     eid = torch.arange(e0, e1, device=dev, dtype=torch.int64)
     deg = (rowptr[r0 + 1:r1 + 1] - rowptr[r0:r1])
@@ -159,7 +159,7 @@ def split_row_block_by_owner(rowptr: torch.Tensor, col: torch.Tensor, val: Optio
     r0, r1 = row_bounds[rank], row_bounds[rank + 1]
     e0, e1 = int(rowptr[r0]), int(rowptr[r1])
     dev = col.device
-    sub_col = col[e0:e1]
+    sub_col = col[e0:e1].to(torch.int64)
     sub_val = None if val is None else val[e0:e1]
     eid = torch.arange(e0, e1, device=dev, dtype=torch.int64)
     deg = (rowptr[r0 + 1:r1 + 1] - rowptr[r0:r1])
@@ -733,6 +733,105 @@ def transpose_csr(rowptr: torch.Tensor, col: torch.Tensor, value: Optional[torch
     return colptr, row_t, val_t
 
 
+class _OffsetArray:
+    """A rank's slice [e0, e0 + local.numel()) of a conceptually GLOBAL 1-D array of `total` elements:
+    exactly what the partitioning code touches of `col` / `value` (one slice inside the rank's own edge
+    range), so a rank that only ever loaded its own rows can be partitioned like one that holds the whole
+    graph (rank-local ingest, `from_local_rows`)."""
+
+    def __init__(self, local: torch.Tensor, e0: int, total: int):
+        self.local, self.e0, self.total = local, int(e0), int(total)
+
+    def numel(self) -> int:
+        return self.total
+
+    @property
+    def device(self):
+        return self.local.device
+
+    @property
+    def dtype(self):
+        return self.local.dtype
+
+    def __getitem__(self, sl):
+        assert isinstance(sl, slice) and sl.step in (None, 1)
+        a = 0 if sl.start is None else sl.start
+        b = self.total if sl.stop is None else sl.stop
+        assert self.e0 <= a <= b <= self.e0 + self.local.numel(), "only the rank's own edge range is resident"
+        return self.local[a - self.e0:b - self.e0]
+
+
+def exchange_by_owner(arrays, owner: torch.Tensor, group=None):
+    """Every element i of the parallel 1-D `arrays` goes to rank owner[i]; returns the received arrays,
+    concatenated in source-rank order.  Point-to-point (batch_isend_irecv): works on gloo and NCCL."""
+    world = dist.get_world_size(group)
+    rank = dist.get_rank(group)
+    dev = owner.device
+    order = torch.argsort(owner, stable=True)
+    counts = torch.bincount(owner, minlength=world).to(torch.int64)
+    all_counts = [torch.zeros(world, dtype=torch.int64, device=dev) for _ in range(world)]
+    dist.all_gather(all_counts, counts, group=group)                    # all_counts[s][q] = elements s sends to q
+    send_off = torch.zeros(world + 1, dtype=torch.int64)
+    send_off[1:] = torch.cumsum(counts.cpu(), 0)
+    recv_counts = [int(all_counts[s][rank]) for s in range(world)]
+    out = []
+    for a in arrays:
+        a_sorted = a[order].contiguous()
+        recv = [torch.empty(recv_counts[s], dtype=a.dtype, device=dev) for s in range(world)]
+        ops = []
+        for d in range(1, world):
+            dst, src = (rank + d) % world, (rank - d) % world
+            chunk = a_sorted[int(send_off[dst]):int(send_off[dst + 1])]
+            if chunk.numel():
+                ops.append(dist.P2POp(dist.isend, chunk, dist.get_global_rank(group, dst) if group is not None else dst, group))
+            if recv_counts[src]:
+                ops.append(dist.P2POp(dist.irecv, recv[src], dist.get_global_rank(group, src) if group is not None else src, group))
+        recv[rank] = a_sorted[int(send_off[rank]):int(send_off[rank + 1])]
+        if ops:
+            for w in dist.batch_isend_irecv(ops):
+                w.wait()
+        out.append(torch.cat(recv) if world > 1 else recv[0])
+    return out
+
+
+def distributed_transpose(rowptr_global, col_local, val_local, r0, r1, n_cols, col_bounds, mean_weights, group=None):
+    """The rank's rows of A^T from every rank's rows of A, without any rank holding the whole graph:
+    each stored entry (i, j, w) travels to the owner of column j, which sorts what it received by
+    (j, i).  Returns (colptr GLOBAL [n_cols + 1] int64, row_t local, val_t local, first local position)."""
+    world = dist.get_world_size(group)
+    rank = dist.get_rank(group)
+    dev = col_local.device
+    m = rowptr_global.numel() - 1
+    deg = (rowptr_global[r0 + 1:r1 + 1] - rowptr_global[r0:r1]).to(dev)
+    assert int(deg.sum()) == col_local.numel()
+    row = torch.repeat_interleave(torch.arange(r0, r1, device=dev, dtype=torch.int64), deg)
+    w = None
+    if val_local is not None or mean_weights:
+        w = torch.ones(col_local.numel(), dtype=torch.float32, device=dev) if val_local is None else val_local.to(torch.float32)
+        if mean_weights:
+            w = w / deg.clamp(min=1).to(torch.float32)[row - r0]
+    cb = torch.as_tensor(col_bounds, dtype=torch.int64, device=dev)
+    owner = torch.bucketize(col_local.to(torch.int64), cb[1:-1], right=True)
+    arrays = [col_local.to(torch.int64), row] + ([w] if w is not None else [])
+    got = exchange_by_owner(arrays, owner, group)
+    j, i = got[0], got[1]
+    order = torch.argsort(j * m + i, stable=True)
+    row_t = i[order].contiguous()
+    val_t = got[2][order].contiguous() if w is not None else None
+    c0, c1 = col_bounds[rank], col_bounds[rank + 1]
+    cnt_local = torch.bincount(j - c0, minlength=c1 - c0) if j.numel() else torch.zeros(c1 - c0, dtype=torch.int64, device=dev)
+    # global colptr: every rank contributes the counts of its own column range
+    width = bounds_width(col_bounds)
+    padded = torch.zeros(width, dtype=torch.int64, device=dev)
+    padded[: c1 - c0] = cnt_local
+    allc = [torch.zeros(width, dtype=torch.int64, device=dev) for _ in range(world)]
+    dist.all_gather(allc, padded, group=group)
+    counts = torch.cat([allc[q][: col_bounds[q + 1] - col_bounds[q]] for q in range(world)])
+    colptr = torch.zeros(n_cols + 1, dtype=torch.int64, device=dev)
+    colptr[1:] = torch.cumsum(counts, 0)
+    return colptr, row_t, val_t, int(colptr[c0])
+
+
 def _cuda_arg_backward(col32, val, arg, grad_out, n_rows_out, arg_sentinel):
     from . import capi
     gx, _ = capi.spmm_arg_backward(col32, val, None, arg, grad_out, n_rows_out, True, False, arg_sentinel)
@@ -747,20 +846,67 @@ class DistSpMM:
     machinery as the forward), max/min through a local arg-scatter + reduce-scatter."""
 
     def __init__(self, rowptr, col, value, n_cols, group=None, device=None, block_spmm=None,
-                 arg_backward=None, overlap=True, pipelined=None, balance="nnz", mode=None, emulate=None):
+                 arg_backward=None, overlap=True, pipelined=None, balance="nnz", mode=None, emulate=None,
+                 row_bounds=None, _local=None):
         self.rowptr, self.col, self.value = rowptr, col, value
         self.m, self.n = rowptr.numel() - 1, int(n_cols)
         self.group, self.device = group, device
         self._kw = dict(group=group, device=device, block_spmm=block_spmm, overlap=overlap, pipelined=pipelined,
                         mode=mode, emulate=emulate)
-        self.fwd = RowPartitionedSpMM(rowptr, col, value, n_cols, balance=balance, **self._kw)
+        self._local = _local         # (r0, r1, e0) when built by from_local_rows: col / value hold the rank's own rows only
+        self.fwd = RowPartitionedSpMM(rowptr, col, value, n_cols, balance=balance, row_bounds=row_bounds, **self._kw)
         self._bwd = {}
         self._arg_backward = arg_backward or _cuda_arg_backward
         self._col32 = None
 
+    @classmethod
+    def from_local_rows(cls, rowptr_local, col_local, value_local, n_cols, group=None, device=None, **kw):
+        """Rank-local ingest: every rank passes ONLY its own contiguous block of rows (`rowptr_local` starting
+        at 0, global column ids), in rank order -- no rank ever holds the whole graph.  Row ownership = the
+        blocks as given (balance them by stored entries when you cut the file); the small global row-pointer
+        array is assembled with one all-gather, the transposed partition for the backward with one exchange
+        of the entries by column owner (`distributed_transpose`)."""
+        world, rank = dist.get_world_size(group), dist.get_rank(group)
+        dev = col_local.device
+        rows = rowptr_local.numel() - 1
+        info = torch.tensor([rows, int(col_local.numel())], dtype=torch.int64, device=dev)
+        infos = [torch.zeros(2, dtype=torch.int64, device=dev) for _ in range(world)]
+        dist.all_gather(infos, info, group=group)
+        rows_all = [int(t[0]) for t in infos]
+        nnz_all = [int(t[1]) for t in infos]
+        row_bounds = [0]
+        for r in rows_all:
+            row_bounds.append(row_bounds[-1] + r)
+        e0 = sum(nnz_all[:rank])
+        m, nnz = row_bounds[-1], sum(nnz_all)
+        # global rowptr (m + 1 integers -- the only global array anybody holds)
+        width = max(1, max(rows_all))
+        deg = torch.zeros(width, dtype=torch.int64, device=dev)
+        deg[:rows] = (rowptr_local[1:] - rowptr_local[:-1]).to(torch.int64)
+        degs = [torch.zeros(width, dtype=torch.int64, device=dev) for _ in range(world)]
+        dist.all_gather(degs, deg, group=group)
+        deg_all = torch.cat([degs[q][: rows_all[q]] for q in range(world)])
+        rowptr = torch.zeros(m + 1, dtype=torch.int64, device=dev)
+        rowptr[1:] = torch.cumsum(deg_all, 0)
+        col = _OffsetArray(col_local, e0, nnz)
+        value = None if value_local is None else _OffsetArray(value_local, e0, nnz)
+        kw.pop("balance", None)
+        kw.pop("emulate", None)
+        return cls(rowptr, col, value, n_cols, group=group, device=device, row_bounds=row_bounds,
+                   _local=(row_bounds[rank], row_bounds[rank + 1], e0), **kw)
+
     def bwd_op(self, mean: bool) -> RowPartitionedSpMM:
         if mean not in self._bwd:
-            colptr, row_t, val_t = transpose_csr(self.rowptr, self.col, self.value, self.n, mean_weights=mean)
+            if self._local is not None:
+                r0, r1, _ = self._local
+                colptr, row_t, val_t, p0 = distributed_transpose(
+                    self.rowptr, self.col.local, None if self.value is None else self.value.local, r0, r1, self.n,
+                    self.fwd.col_bounds, mean, self.group)
+                nnz = self.col.numel()
+                row_t = _OffsetArray(row_t, p0, nnz)
+                val_t = None if val_t is None else _OffsetArray(val_t, p0, nnz)
+            else:
+                colptr, row_t, val_t = transpose_csr(self.rowptr, self.col, self.value, self.n, mean_weights=mean)
             # rows of A^T are the columns of A and vice versa: swap the forward's bounds
             self._bwd[mean] = RowPartitionedSpMM(colptr, row_t, val_t, self.m, row_bounds=self.fwd.col_bounds,
                                                  col_bounds=self.fwd.row_bounds, **self._kw)
@@ -810,9 +956,17 @@ class _DistSpMMFn(torch.autograd.Function):
             return out, None, None
         if op._col32 is None:
             # scatter target = position of the column in the width-padded gathered layout
-            op._col32 = slice_position(op.col.to(dev).to(torch.int64), f.col_bounds, f.Rc).to(torch.int32)
-            op._val_dev = None if op.value is None else op.value.to(dev)
-        partial = op._arg_backward(op._col32, op._val_dev, arg, grad_out, f.world * f.Rc, f.nnz)
+            col_res = op.col.local if op._local is not None else op.col
+            val_res = None if op.value is None else (op.value.local if op._local is not None else op.value)
+            op._col32 = slice_position(col_res.to(dev).to(torch.int64), f.col_bounds, f.Rc).to(torch.int32)
+            op._val_dev = None if val_res is None else val_res.to(dev)
+        if op._local is not None:
+            # rank-local ingest: only the rank's own edge range is resident; its rows' winners all lie inside it
+            e0, n_loc = op._local[2], op._col32.numel()
+            arg = torch.where(arg == f.nnz, torch.full_like(arg, n_loc), arg - e0)
+            partial = op._arg_backward(op._col32, op._val_dev, arg, grad_out, f.world * f.Rc, n_loc)
+        else:
+            partial = op._arg_backward(op._col32, op._val_dev, arg, grad_out, f.world * f.Rc, f.nnz)
         if f.world == 1:
             return partial, None, None
         out = torch.empty((f.Rc, partial.size(1)), dtype=partial.dtype, device=dev)
@@ -840,11 +994,14 @@ class PartitionedAdj:
 
     is_partitioned = True
 
-    def __init__(self, rowptr, col, value, n_cols, **dist_kw):
+    def __init__(self, rowptr, col, value, n_cols, local_rows=False, **dist_kw):
         self._args = (rowptr, col, n_cols)
         self._value = value
         self._kw = dist_kw
-        self.op = DistSpMM(rowptr, col, value, n_cols, **dist_kw)
+        self._local_rows = bool(local_rows)
+        # local_rows: (rowptr, col, value) are THIS rank's contiguous block of rows only (rank-local ingest)
+        self.op = (DistSpMM.from_local_rows(rowptr, col, value, n_cols, **dist_kw) if local_rows
+                   else DistSpMM(rowptr, col, value, n_cols, **dist_kw))
         self._novalue_twin = None
 
     # --- what the callers of matmul use ---
@@ -861,7 +1018,7 @@ class PartitionedAdj:
             return self
         if self._novalue_twin is None:
             rowptr, col, n_cols = self._args
-            self._novalue_twin = PartitionedAdj(rowptr, col, None, n_cols, **self._kw)
+            self._novalue_twin = PartitionedAdj(rowptr, col, None, n_cols, local_rows=self._local_rows, **self._kw)
         return self._novalue_twin
 
     def matmul(self, x_slice: torch.Tensor, reduce: str = "sum") -> torch.Tensor:
@@ -880,8 +1037,11 @@ class PartitionedAdj:
         return self.op.fwd.pad_x(x_global[c0:c1].to(self.op.fwd.device))
 
 
-def partition(adj_t, group=None, device=None, **dist_kw) -> PartitionedAdj:
-    """Row-partition a (replicated) ``torch_sparse.SparseTensor`` over the ranks of `group`."""
+def partition(adj_t, group=None, device=None, local_rows=False, **dist_kw) -> PartitionedAdj:
+    """Row-partition a ``torch_sparse.SparseTensor`` over the ranks of `group`.  By default `adj_t` is the
+    whole (replicated) graph and the rows are cut by stored entries; with ``local_rows=True`` it holds only
+    THIS rank's contiguous block of rows ([rows_local, N], global column ids, blocks in rank order), so no
+    rank ever materialises the whole graph."""
     rowptr, col, value = adj_t.csr()
     n_cols = adj_t.sparse_sizes()[1]
-    return PartitionedAdj(rowptr, col, value, n_cols, group=group, device=device, **dist_kw)
+    return PartitionedAdj(rowptr, col, value, n_cols, local_rows=local_rows, group=group, device=device, **dist_kw)

@@ -128,6 +128,90 @@ def test_row_partitioned_spmm_world2_gloo(with_value, balance):
         assert not bad, f"rank {rank}: {bad}"
 
 
+def local_ingest_worker(rank, world, port, with_value, results):
+    """Every rank builds the operator from ITS OWN rows only (DistSpMM.from_local_rows) -- cut unevenly on
+    purpose -- and must produce what the whole-graph constructor and the single-process oracle produce."""
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        from isplib_b200.dist import DistSpMM, distributed_transpose
+        from oracle import oracle
+        M, N, K = 101, 101, 6
+        rowptr, col, val = make_graph(7, M, N, with_value)
+        x = np.random.default_rng(1).integers(-3, 4, size=(N, K)).astype(np.float32)
+        go = np.random.default_rng(2).standard_normal((M, K)).astype(np.float32)
+        cuts = [0, 37, M] if world == 2 else [0, 20, 75, M]
+        r0, r1 = cuts[rank], cuts[rank + 1]
+        e0, e1 = int(rowptr[r0]), int(rowptr[r1])
+        rp_loc = torch.from_numpy(rowptr[r0:r1 + 1] - e0)
+        col_loc = torch.from_numpy(col[e0:e1].copy())
+        val_loc = None if val is None else torch.from_numpy(val[e0:e1].copy())
+        op = DistSpMM.from_local_rows(rp_loc, col_loc, val_loc, N, device="cpu", block_spmm=oracle_block_spmm,
+                                      arg_backward=oracle_arg_backward, overlap=False)
+        f = op.fwd
+        ok = {"bounds": f.row_bounds == cuts and f.col_bounds == cuts and f.nnz == col.shape[0],
+              "rowptr": bool(np.array_equal(op.rowptr.numpy(), rowptr))}
+        # the distributed transpose = this rank's rows of the single-process transpose (same order: by source row)
+        for mean in (False, True):
+            colptr, csr2csc, row_t = oracle.build_csc(rowptr, col, N)
+            w = np.ones(col.shape[0], np.float32) if val is None else val
+            w = w[csr2csc]
+            if mean:
+                w = w / np.maximum(np.diff(rowptr), 1)[row_t].astype(np.float32)
+            cp, rt, vt, p0 = distributed_transpose(op.rowptr, col_loc, val_loc, r0, r1, N, f.col_bounds, mean)
+            a, b = int(colptr[cuts[rank]]), int(colptr[cuts[rank + 1]])
+            good = np.array_equal(cp.numpy(), colptr) and p0 == a and np.array_equal(rt.numpy(), row_t[a:b])
+            if vt is not None:
+                good = good and np.allclose(vt.numpy(), w[a:b], rtol=1e-6)
+            else:
+                good = good and val is None and not mean
+            ok[f"transpose_mean{int(mean)}"] = bool(good)
+        for reduce in ("sum", "mean", "max", "min"):
+            xs = f.pad_x(torch.from_numpy(x[r0:r1])).requires_grad_(True)
+            out = op(xs, reduce)
+            gpad = torch.zeros((f.R, K))
+            gpad[: r1 - r0] = torch.from_numpy(go[r0:r1])
+            out.backward(gpad)
+            code = oracle.REDUCE_CODE[reduce]
+            ref, ref_arg = oracle.spmm_c(rowptr, col, val, x, code)
+            got = out.detach().numpy()[: r1 - r0]
+            if reduce in ("max", "min"):
+                ok[reduce + "_fwd"] = bool(np.array_equal(got, ref[r0:r1]))
+                _, a = f.forward(f.pad_x(torch.from_numpy(x[r0:r1])), reduce)
+                ok[reduce + "_arg"] = bool(np.array_equal(a.numpy()[: r1 - r0], ref_arg[r0:r1]))     # GLOBAL edge ids
+                gref, _ = oracle.arg_backward(col, val, None, ref_arg, go, N)
+            else:
+                ok[reduce + "_fwd"] = bool(np.allclose(got, ref[r0:r1], rtol=1e-5, atol=1e-5))
+                bw = oracle.spmm_backward_sum if reduce == "sum" else oracle.spmm_backward_mean
+                gref = bw(rowptr, col, val, go, N)
+            ok[reduce + "_bwd"] = bool(np.allclose(xs.grad.numpy()[: r1 - r0], gref[r0:r1], rtol=1e-4, atol=1e-4))
+        results[rank] = ok
+    finally:
+        dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("world", [2, 3])
+@pytest.mark.parametrize("with_value", [True, False])
+def test_rank_local_ingest_matches_whole_graph_gloo(with_value, world):
+    port = 31500 + (os.getpid() % 2000) + (1 if with_value else 0) + 2 * world
+    mgr = mp.Manager()
+    results = mgr.dict()
+    mp.spawn(local_ingest_worker, args=(world, port, with_value, results), nprocs=world, join=True)
+    assert len(results) == world
+    for rank in range(world):
+        bad = [k for k, v in results[rank].items() if not v]
+        assert not bad, f"rank {rank}: {bad}"
+
+
+def test_offset_array_only_serves_the_resident_range():
+    from isplib_b200.dist import _OffsetArray
+    a = _OffsetArray(torch.arange(10, 20), 100, 500)
+    assert a.numel() == 500 and torch.equal(a[103:106], torch.tensor([13, 14, 15]))
+    with pytest.raises(AssertionError):
+        a[0:5]                      # outside the rank's own edge range: not resident
+
+
 def test_split_row_block_partitions_every_entry_once():
     from isplib_b200.dist import split_row_block
     rowptr, col, val = make_graph(9, 57, 44, True)
@@ -227,6 +311,19 @@ def plugin_worker(rank, world, port, results):
                 h = (torch.from_numpy(x) @ conv.lin.weight.t()).numpy()
             ref = oracle.spmm_c(rowptr, col, val, h, oracle.SUM)[0] + conv.bias.detach().numpy()
             ok["gcn_layer"] = bool(np.allclose(y.detach().numpy()[: r1 - r0], ref[r0:r1], rtol=1e-4, atol=1e-4))
+            # rank-local ingest: a SparseTensor holding ONLY this rank's rows gives the same partitioned operator
+            e0, e1 = int(rowptr[r0]), int(rowptr[r1])
+            mine = torch_sparse.SparseTensor(rowptr=torch.from_numpy(rowptr[r0:r1 + 1] - e0), col=torch.from_numpy(col[e0:e1].copy()),
+                                             value=torch.from_numpy(val[e0:e1].copy()), sparse_sizes=(r1 - r0, N), is_sorted=True)
+            ladj = iSpLibPlugin.partition(mine, device="cpu", local_rows=True, block_spmm=oracle_block_spmm,
+                                          arg_backward=oracle_arg_backward, overlap=False, mode="nccl")
+            ok["local_rows_range"] = ladj.row_range() == (r0, r1)
+            for reduce in ("sum", "max"):
+                a = torch_sparse.matmul(ladj, xs, reduce)
+                b = torch_sparse.matmul(padj, xs, reduce)
+                ok["local_rows_" + reduce] = bool(torch.equal(a, b))
+            ok["local_rows_novalue"] = bool(torch.equal(torch_sparse.matmul(ladj.set_value(None), xs, "sum"),
+                                                        torch_sparse.matmul(nov, xs, "sum")))
             results[rank] = ok
         finally:
             iSpLibPlugin.unpatch_pyg()

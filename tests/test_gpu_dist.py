@@ -114,3 +114,64 @@ def test_row_partitioned_spmm_two_gpus_pipelined_p2p():
     for rank in range(2):
         bad = [k for k, v in results[rank].items() if not v]
         assert not bad, f"rank {rank}: {bad}"
+
+
+def local_ingest_worker(rank, world, port, results, mode):
+    """Rank-local ingest on the real kernels: every rank hands DistSpMM.from_local_rows ITS rows only."""
+    sys.path.insert(0, ROOT)
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    torch.cuda.set_device(rank)
+    dev = torch.device("cuda", rank)
+    dist.init_process_group("nccl", rank=rank, world_size=world, device_id=dev)
+    try:
+        from isplib_b200 import synth
+        from isplib_b200.dist import DistSpMM
+        from oracle import oracle
+        g = synth.make_graph(4001, 300_000, law="lognormal", param=1.3, values="uniform", seed=3)
+        val = torch.round(g.value * 4) / 4
+        K = 32
+        x = torch.randint(-3, 4, (g.n, K), generator=torch.Generator().manual_seed(1)).float()
+        go = torch.randn(g.m, K, generator=torch.Generator().manual_seed(2))
+        cuts = [0, g.m] if world == 1 else [0, 1700, g.m]          # uneven on purpose
+        r0, r1 = cuts[rank], cuts[rank + 1]
+        e0, e1 = int(g.rowptr[r0]), int(g.rowptr[r1])
+        op = DistSpMM.from_local_rows((g.rowptr[r0:r1 + 1] - e0).to(dev), g.col[e0:e1].to(dev), val[e0:e1].to(dev),
+                                      g.n, device=dev, mode=mode)
+        f = op.fwd
+        assert f.row_bounds == cuts and f.row_range() == (r0, r1)
+        rp, co, va = g.rowptr.numpy(), g.col.numpy(), val.numpy()
+        ok = {}
+        for reduce in ("sum", "mean", "max", "min"):
+            xs = f.pad_x(x[r0:r1].to(dev)).requires_grad_(True)
+            out = op(xs, reduce)
+            gpad = torch.zeros((f.R, K), device=dev)
+            gpad[: r1 - r0] = go[r0:r1].to(dev)
+            out.backward(gpad)
+            torch.cuda.synchronize()
+            ref, ref_arg = oracle.spmm_c(rp, co, va, x.numpy(), oracle.REDUCE_CODE[reduce])
+            got = out.detach().cpu().numpy()[: r1 - r0]
+            if reduce in ("max", "min"):
+                ok[reduce + "_fwd"] = bool(np.array_equal(got, ref[r0:r1]))
+                gref, _ = oracle.arg_backward(co, va, None, ref_arg, go.numpy(), g.n)
+            else:
+                ok[reduce + "_fwd"] = bool(np.allclose(got, ref[r0:r1], rtol=1e-4, atol=1e-4))
+                bw = oracle.spmm_backward_sum if reduce == "sum" else oracle.spmm_backward_mean
+                gref = bw(rp, co, va, go.numpy(), g.n)
+            ok[reduce + "_bwd"] = bool(np.allclose(xs.grad.cpu().numpy()[: r1 - r0], gref[r0:r1], rtol=1e-3, atol=1e-3))
+        f.check_status()
+        results[rank] = ok
+    finally:
+        dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("world,mode", [(1, "nccl"), (2, "nccl"), (2, "fused")])
+def test_rank_local_ingest_on_the_gpu(world, mode):
+    if torch.cuda.device_count() < world:
+        pytest.skip(f"needs {world} GPUs")
+    mgr = mp.Manager()
+    results = mgr.dict()
+    mp.spawn(local_ingest_worker, args=(world, 30250 + os.getpid() % 300 + 7 * world, results, mode), nprocs=world, join=True)
+    for rank in range(world):
+        bad = [k for k, v in results[rank].items() if not v]
+        assert not bad, f"rank {rank}: {bad}"
