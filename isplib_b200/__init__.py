@@ -187,6 +187,8 @@ def fused_matmul(src, other, reduce: str = "sum", bias=None, addend=None, addend
     (gin-sparse.py:73-78; pass ``addend=other``) -- fused into the kernel's final store
     (``isplib_b200_spmm_csr_fused``).  sum / add / mean; differentiable w.r.t. other, value, bias,
     addend.  CUDA tensors only, like every op of this package."""
+    if getattr(src, "is_partitioned", False):      # row-partitioned over a process group: same epilogue, last launch
+        return src.matmul(other, reduce, bias=bias, addend=addend, addend_scale=addend_scale, relu=relu)
     if not _is_sparse_tensor(src):
         raise TypeError("isplib: expected a torch_sparse.SparseTensor")
     rowptr, col, value = src.csr()

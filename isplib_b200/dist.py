@@ -248,7 +248,7 @@ class _PeerBuffers:
         return self.bufs[b][self.rank * self.Rc:(self.rank + 1) * self.Rc, :self.K]
 
 
-def emulated_step(ops, xs, reduce: str = "sum"):
+def emulated_step(ops, xs, reduce: str = "sum", epilogues=None):
     """One forward of several ranks emulated in ONE process / on ONE GPU (tests): every rank pushes
     its slice first (phase 1), then every rank multiplies (phase 2, still waiting on the arrival
     counters the pushes bumped).  Real ranks do both in one launch (phase 0).  Returns [(out, arg)]."""
@@ -261,12 +261,16 @@ def emulated_step(ops, xs, reduce: str = "sum"):
         arg = torch.empty((op.R, K), dtype=torch.int64, device=x.device) if is_arg else None
         op._forward_fused(x, code, out, arg, phase=1)
         outs.append((out, arg))
-    for op, x, (out, arg) in zip(ops, xs, outs):
-        op._forward_fused(x, code, out, arg, phase=2)
+    for i, (op, x, (out, arg)) in enumerate(zip(ops, xs, outs)):
+        op._forward_fused(x, code, out, arg, phase=2, epilogue=None if epilogues is None else epilogues[i])
     return outs
 
 
-def _cuda_block_spmm(reduce_code, block: CsrBlock, x, out, arg_out, flags, row_divisor, arg_sentinel, variant=-1):
+def _cuda_block_spmm(reduce_code, block: CsrBlock, x, out, arg_out, flags, row_divisor, arg_sentinel, variant=-1,
+                     **epilogue):
+    """One launch of isplib_b200_spmm_csr_fused on a column block.  ``epilogue`` (bias / addend / addend_scale /
+    relu) is only ever given to the LAST launch that writes a row block: the kernel's final store applies it
+    after the ACCUMULATE merge and the mean division."""
     from . import capi
     if block.plan is None:
         block.plan = capi.Plan(block.rowptr, block.nnz)
@@ -281,7 +285,38 @@ def _cuda_block_spmm(reduce_code, block: CsrBlock, x, out, arg_out, flags, row_d
         variant = tuned[key]
     return capi.spmm_csr(reduce_code, block.rowptr, block.col, block.val, x, block.plan, variant,
                          out=out, arg_out=arg_out, flags=flags, row_divisor=row_divisor,
-                         edge_ids=block.edge_ids, arg_sentinel=arg_sentinel)
+                         edge_ids=block.edge_ids, arg_sentinel=arg_sentinel, **epilogue)
+
+
+def make_epilogue(bias=None, addend=None, addend_scale: float = 1.0, relu: bool = False):
+    """{} when there is nothing to fuse, else the keyword arguments of the last kernel launch."""
+    if bias is None and addend is None and not relu:
+        return {}
+    return dict(bias=bias, addend=addend, addend_scale=float(addend_scale), relu=bool(relu))
+
+
+def _epilogue_columns(epi: dict, c0: int, c1: int) -> dict:
+    """The epilogue of feature columns [c0, c1) (K-chunked launches)."""
+    if not epi:
+        return epi
+    e = dict(epi)
+    if e.get("bias") is not None:
+        e["bias"] = e["bias"][c0:c1]
+    if e.get("addend") is not None:
+        e["addend"] = e["addend"][:, c0:c1]
+    return e
+
+
+def _epilogue_torch(out: torch.Tensor, epi: dict) -> torch.Tensor:
+    """The same epilogue as separate passes, for the one path whose launches are not ordered last-writer
+    (the opt-in copy-engine pipeline)."""
+    if epi.get("addend") is not None:
+        out.add_(epi["addend"], alpha=epi.get("addend_scale", 1.0))
+    if epi.get("bias") is not None:
+        out.add_(epi["bias"])
+    if epi.get("relu"):
+        out.relu_()
+    return out
 
 
 class RowPartitionedSpMM:
@@ -407,6 +442,15 @@ class RowPartitionedSpMM:
         out[: x_own.size(0)] = x_own
         return out
 
+    def pad_out(self, y_own: torch.Tensor) -> torch.Tensor:
+        """[rows <= R, K] -> contiguous [R, K] zero padded (an epilogue addend shaped like the output slice)."""
+        if y_own.size(0) == self.R and y_own.stride(1) == 1:
+            return y_own
+        out = torch.zeros((self.R, y_own.size(1)), dtype=y_own.dtype, device=y_own.device)
+        n = min(self.R, y_own.size(0))
+        out[:n] = y_own[:n]
+        return out
+
     def _all_gather(self, x_slice: torch.Tensor, persistent: bool = False) -> torch.Tensor:
         if self.world == 1:
             return x_slice
@@ -427,11 +471,14 @@ class RowPartitionedSpMM:
         dist.all_gather_into_tensor(gathered, x_slice, group=self.group)
         return gathered
 
-    def forward(self, x_slice: torch.Tensor, reduce: str = "sum", aux=None):
+    def forward(self, x_slice: torch.Tensor, reduce: str = "sum", aux=None, epilogue: Optional[dict] = None):
         """x_slice: [Rc, K] (use pad_x).  Returns (out [R, K], arg_out [R, K] int64 or None);
         rows beyond own_rows are padding (zeros / init values).  ``aux``: max/min in fused mode only -- a
         dict that receives 'arg_col' / 'arg_val' ([R, K]: the winner's column, as a position in the
-        gathered layout, and its value) for the streamed backward scatter."""
+        gathered layout, and its value) for the streamed backward scatter.  ``epilogue`` (make_epilogue):
+        relu?(result + addend_scale * addend[R, K] + bias[K]) in the final store of the last launch that
+        writes the rows -- the fused gather kernel, or the remote-block kernel of the NCCL path."""
+        epi = epilogue or {}
         code = REDUCE_CODE[reduce]
         is_arg = code in (MAX, MIN)
         K = x_slice.size(1)
@@ -441,14 +488,15 @@ class RowPartitionedSpMM:
         div = self.row_degree if code == MEAN else None
 
         if self.world == 1:
-            self.block_spmm(inner, self.local, x_slice, out, arg, 0, div, self.nnz, self.variant)
+            self.block_spmm(inner, self.local, x_slice, out, arg, 0, div, self.nnz, self.variant, **epi)
             return out, arg
 
         if self.mode_for(K, reduce, x_slice) == "fused":
-            return self._forward_fused(x_slice, code, out, arg, aux=aux if is_arg else None)
+            return self._forward_fused(x_slice, code, out, arg, aux=aux if is_arg else None, epilogue=epi)
 
         if self.pipelined:
-            return self._forward_pipelined(x_slice, inner, div, out, arg)
+            out, arg = self._forward_pipelined(x_slice, inner, div, out, arg)
+            return (_epilogue_torch(out, epi) if epi else out), arg
 
         # K-chunk pipeline: the all-gather of feature chunk c+1 runs on the comm stream while the
         # SpMM of chunk c runs on the compute stream, so only the first chunk's transfer is
@@ -474,11 +522,12 @@ class RowPartitionedSpMM:
                 cur.wait_event(events[ci])
                 if len(chunks) > 1:
                     gathered[ci].record_stream(cur)
-                self.block_spmm(inner, self.remote, gathered[ci], oo, ao, FLAG_ACCUMULATE, div, self.nnz, self.variant)
+                self.block_spmm(inner, self.remote, gathered[ci], oo, ao, FLAG_ACCUMULATE, div, self.nnz, self.variant,
+                                **(epi if len(chunks) == 1 else _epilogue_columns(epi, c0, c1)))
             return out, arg
         gathered = self._all_gather(x_slice)
         self.block_spmm(inner, self.local, x_slice, out, arg, 0, None, self.nnz, self.variant)
-        self.block_spmm(inner, self.remote, gathered, out, arg, FLAG_ACCUMULATE, div, self.nnz, self.variant)
+        self.block_spmm(inner, self.remote, gathered, out, arg, FLAG_ACCUMULATE, div, self.nnz, self.variant, **epi)
         return out, arg
 
     def mode_for(self, K: int, reduce: str = "sum", x_slice: Optional[torch.Tensor] = None) -> str:
@@ -558,7 +607,7 @@ class RowPartitionedSpMM:
         ok = capi.lib().isplib_b200_variant_supported(v, code, K, x.stride(0), K, x.data_ptr(), x.data_ptr())
         return v if ok else -1
 
-    def _forward_fused(self, x_slice, code, out, arg, bias=None, relu=False, phase=0, aux=None):
+    def _forward_fused(self, x_slice, code, out, arg, phase=0, aux=None, epilogue=None):
         """phase 0: the product path (push + multiply in one launch).  phases 1 / 2 split a step into
         its push and its multiply half: only for several ranks emulated on ONE GPU (emulated_step)."""
         from . import capi
@@ -589,8 +638,8 @@ class RowPartitionedSpMM:
                              my_group_at_peer=self.my_group_at_peer, slice_rows=self.Rc, status=self._gflags[K],
                              epoch=epoch, parity_launch=(epoch + 1) // 2, tile_mode=tile_mode, phase=phase,
                              copy_ctas=self.copy_ctas, variant=variant, out=out,
-                             arg_out=arg, edge_ids=full.edge_ids, arg_sentinel=self.nnz, bias=bias, relu=relu,
-                             arg_col=arg_col, arg_val=arg_val)
+                             arg_out=arg, edge_ids=full.edge_ids, arg_sentinel=self.nnz,
+                             arg_col=arg_col, arg_val=arg_val, **(epilogue or {}))
         return out, arg
 
     def phase_split(self, x_slice, reduce: str = "sum", steps: int = 10):
@@ -912,22 +961,30 @@ class DistSpMM:
                                                  col_bounds=self.fwd.row_bounds, **self._kw)
         return self._bwd[mean]
 
-    def __call__(self, x_slice: torch.Tensor, reduce: str = "sum") -> torch.Tensor:
-        return _DistSpMMFn.apply(x_slice, self, reduce)
+    def __call__(self, x_slice: torch.Tensor, reduce: str = "sum", bias=None, addend=None, addend_scale: float = 1.0,
+                 relu: bool = False) -> torch.Tensor:
+        """``relu?(A @ x + addend_scale * addend + bias)`` on this rank's rows; the epilogue rides in the final
+        store of the step's last kernel (single-GPU counterpart: ``isplib_b200.fused_matmul``)."""
+        return _DistSpMMFn.apply(x_slice, self, reduce, bias, addend, float(addend_scale), bool(relu))
 
 
 class _DistSpMMFn(torch.autograd.Function):
     @staticmethod
-    def forward(ctx, x_slice, op: DistSpMM, reduce: str):
+    def forward(ctx, x_slice, op: DistSpMM, reduce: str, bias=None, addend=None, addend_scale=1.0, relu=False):
         # max/min through the fused kernel: let its final store also write col[arg] / val[arg] (positions in
         # the gathered layout = the scatter targets of the backward), so the backward streams them instead of
         # gathering through a rank-local copy of the GLOBAL column array
         aux = {} if (REDUCE_CODE[reduce] in (MAX, MIN) and x_slice.requires_grad) else None
-        out, arg = op.fwd.forward(x_slice.contiguous(), reduce, aux=aux)
+        epi = make_epilogue(None if bias is None else bias.detach().contiguous(),
+                            None if addend is None else addend.detach(), addend_scale, relu)
+        if epi.get("addend") is not None and (addend.stride(1) != 1 or addend.size(0) < op.fwd.R):
+            epi["addend"] = op.fwd.pad_out(addend.detach())
+        out, arg = op.fwd.forward(x_slice.contiguous(), reduce, aux=aux, epilogue=epi)
         ctx.op, ctx.reduce = op, reduce
         ctx.aux = aux if aux else None            # stays empty when the NCCL path ran
-        if arg is not None:
-            ctx.save_for_backward(arg)
+        ctx.epi = (bias is not None, addend is not None, float(addend_scale), bool(relu),
+                   None if addend is None else addend.size(0))
+        ctx.save_for_backward(arg if arg is not None else None, out if relu else None)
         return out
 
     @staticmethod
@@ -935,15 +992,23 @@ class _DistSpMMFn(torch.autograd.Function):
         op, reduce = ctx.op, ctx.reduce
         code = REDUCE_CODE[reduce]
         grad_out = grad_out.contiguous()
+        arg, out_saved = ctx.saved_tensors
+        has_bias, has_addend, addend_scale, relu, addend_rows = ctx.epi
+        if relu:
+            grad_out = grad_out * (out_saved > 0).to(grad_out.dtype)
+        # the epilogue's own inputs: bias sums over the rank's REAL rows (the ranks' shares are summed by
+        # whoever all-reduces the parameter gradients, like every other replicated weight)
+        grad_bias = grad_out[: op.fwd.own_rows].sum(0) if (has_bias and ctx.needs_input_grad[3]) else None
+        grad_addend = (grad_out[:addend_rows] * addend_scale) if (has_addend and ctx.needs_input_grad[4]) else None
+        tail = (None, None, grad_bias, grad_addend, None, None)
         if code in (SUM, MEAN):
             t = op.bwd_op(code == MEAN)
             g = grad_out
             if g.size(0) != t.Rc:                      # pad the row slice of grad_out like X
                 g = t.pad_x(g[: t.Rc])
             gx, _ = t.forward(g, "sum")                # csrc/fusedmm.cpp:285 / :375 of the reference
-            return gx, None, None
+            return (gx,) + tail
         # max / min: scatter through the global edge ids, then sum the partials of all ranks
-        (arg,) = ctx.saved_tensors
         f = op.fwd
         dev = grad_out.device
         if ctx.aux is not None:
@@ -953,7 +1018,7 @@ class _DistSpMMFn(torch.autograd.Function):
             partial = capi.spmm_arg_backward_aux(ctx.aux["arg_col"], ctx.aux["arg_val"], grad_out, n_rows, binned=binned)
             out = torch.empty((f.Rc, partial.size(1)), dtype=partial.dtype, device=dev)
             dist.reduce_scatter_tensor(out, partial, group=f.group)
-            return out, None, None
+            return (out,) + tail
         if op._col32 is None:
             # scatter target = position of the column in the width-padded gathered layout
             col_res = op.col.local if op._local is not None else op.col
@@ -968,14 +1033,14 @@ class _DistSpMMFn(torch.autograd.Function):
         else:
             partial = op._arg_backward(op._col32, op._val_dev, arg, grad_out, f.world * f.Rc, f.nnz)
         if f.world == 1:
-            return partial, None, None
+            return (partial,) + tail
         out = torch.empty((f.Rc, partial.size(1)), dtype=partial.dtype, device=dev)
         if dist.get_backend(f.group) == "nccl":
             dist.reduce_scatter_tensor(out, partial, group=f.group)
         else:                                          # gloo (CPU tests) has no reduce-scatter
             dist.all_reduce(partial, group=f.group)
             out.copy_(partial[f.rank * f.Rc:(f.rank + 1) * f.Rc])
-        return out, None, None
+        return (out,) + tail
 
 
 # ----------------------------------------------------------------------------------------
@@ -1021,8 +1086,9 @@ class PartitionedAdj:
             self._novalue_twin = PartitionedAdj(rowptr, col, None, n_cols, local_rows=self._local_rows, **self._kw)
         return self._novalue_twin
 
-    def matmul(self, x_slice: torch.Tensor, reduce: str = "sum") -> torch.Tensor:
-        return self.op(x_slice, reduce)
+    def matmul(self, x_slice: torch.Tensor, reduce: str = "sum", bias=None, addend=None, addend_scale: float = 1.0,
+               relu: bool = False) -> torch.Tensor:
+        return self.op(x_slice, reduce, bias=bias, addend=addend, addend_scale=addend_scale, relu=relu)
 
     # --- slice helpers for the training script ---
     def row_range(self):

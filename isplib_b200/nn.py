@@ -12,6 +12,7 @@ stock (torch-op) matmul.  A layer can also be handed a ``spmm`` callable (e.g. a
 """
 from __future__ import annotations
 
+import os
 import sys
 from typing import Callable, Optional
 
@@ -29,8 +30,8 @@ def _fused_available(x, spmm, adj_t=None) -> bool:
     matmul), the data is on the GPU and no external spmm callable (multi-GPU) was handed in."""
     if spmm is not None or not x.is_cuda:
         return False
-    if getattr(adj_t, "is_partitioned", False):
-        return False        # the row-partitioned operator applies no epilogue (yet): plain torch ops follow it
+    if getattr(adj_t, "is_partitioned", False) and os.environ.get("ISPLIB_B200_DIST_EPILOGUE", "1") == "0":
+        return False        # opt-out: plain torch ops after the row-partitioned operator
     from . import iSpLibPlugin
     return iSpLibPlugin.is_patched() and iSpLibPlugin.fuse_epilogues
 
@@ -72,6 +73,8 @@ class GCNConv(nn.Module):
         if _fused_available(x, spmm, adj_t):
             # + bias and ReLU inside the SpMM's final store: two [N, K] passes less
             from . import fused_matmul
+            if getattr(adj_t, "is_partitioned", False):      # the slice is staged into the peer-visible buffer anyway
+                return fused_matmul(adj_t, F.linear(x, self.lin.weight), "sum", bias=self.bias, relu=self.relu)
             return fused_matmul(adj_t, _linear_padded(x, self.lin.weight), "sum", bias=self.bias, relu=self.relu)
         out = agg(self.lin(x))
         out = out if self.bias is None else out + self.bias

@@ -19,10 +19,14 @@ if ROOT not in sys.path:
     sys.path.insert(0, ROOT)
 
 
-def oracle_block_spmm(reduce_code, block, x, out, arg_out, flags, row_divisor, arg_sentinel, variant=-1):
-    """numpy stand-in for isplib_b200_spmm_csr_ex with the same contract (edge_ids,
-    ISPLIB_FLAG_ACCUMULATE, row_divisor, arg_sentinel)."""
+def oracle_block_spmm(reduce_code, block, x, out, arg_out, flags, row_divisor, arg_sentinel, variant=-1, **epi):
+    """numpy stand-in for isplib_b200_spmm_csr_fused with the same contract (edge_ids,
+    ISPLIB_FLAG_ACCUMULATE, row_divisor, arg_sentinel; the epilogue after merge and division)."""
     from oracle import oracle
+    if epi:
+        epi = dict(bias=None if epi.get("bias") is None else epi["bias"].numpy(),
+                   addend=None if epi.get("addend") is None else epi["addend"].numpy(),
+                   addend_scale=epi.get("addend_scale", 1.0), relu=epi.get("relu", False))
     rp = block.rowptr.numpy().astype(np.int64)
     co = block.col.numpy().astype(np.int64)
     va = None if block.val is None else block.val.numpy()
@@ -36,6 +40,8 @@ def oracle_block_spmm(reduce_code, block, x, out, arg_out, flags, row_divisor, a
             better = (o > po) if reduce_code == 1 else (o < po)
             take = better | ((o == po) & (gid < pa))
             o, gid = np.where(take, o, po), np.where(take, gid, pa)
+        if epi:
+            o = oracle.apply_epilogue(o, **epi)
         out.copy_(torch.from_numpy(o))
         arg_out.copy_(torch.from_numpy(gid))
     else:
@@ -43,7 +49,10 @@ def oracle_block_spmm(reduce_code, block, x, out, arg_out, flags, row_divisor, a
             o = out.numpy() + o
         if row_divisor is not None:
             o = o / row_divisor.numpy()[:, None]
-        out.copy_(torch.from_numpy(o.astype(np.float32)))
+        o = o.astype(np.float32)
+        if epi:
+            o = oracle.apply_epilogue(o, **epi)
+        out.copy_(torch.from_numpy(o))
     return out, arg_out
 
 
@@ -122,6 +131,68 @@ def test_row_partitioned_spmm_world2_gloo(with_value, balance):
     mgr = mp.Manager()
     results = mgr.dict()
     mp.spawn(worker, args=(world, port, with_value, balance, results), nprocs=world, join=True)
+    assert len(results) == world
+    for rank in range(world):
+        bad = [k for k, v in results[rank].items() if not v]
+        assert not bad, f"rank {rank}: {bad}"
+
+
+def epilogue_worker(rank, world, port, results):
+    """relu?(A x + scale * addend + bias) through the row-partitioned operator: the epilogue rides in the LAST
+    launch (after the ACCUMULATE merge and the mean division), gradients reach x, bias and addend."""
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        from isplib_b200.dist import DistSpMM
+        from oracle import oracle
+        M = N = 101
+        K = 6
+        rowptr, col, val = make_graph(9, M, N, True)
+        x = np.random.default_rng(1).integers(-3, 4, size=(N, K)).astype(np.float32)
+        bias = np.random.default_rng(3).standard_normal(K).astype(np.float32)
+        go = np.random.default_rng(2).standard_normal((M, K)).astype(np.float32)
+        ok = {}
+        for k_chunk in (None, 4):
+            op = DistSpMM(torch.from_numpy(rowptr), torch.from_numpy(col), torch.from_numpy(val), N, device="cpu",
+                          block_spmm=oracle_block_spmm, arg_backward=oracle_arg_backward, overlap=False)
+            op.fwd.k_chunk = k_chunk
+            f = op.fwd
+            r0, r1 = f.row_range()
+            for reduce, relu, use_addend in (("sum", True, False), ("mean", False, True), ("sum", True, True), ("max", True, False)):
+                xs = f.pad_x(torch.from_numpy(x[r0:r1])).requires_grad_(True)
+                b = torch.from_numpy(bias.copy()).requires_grad_(True)
+                scale = 1.25
+                out = op(xs, reduce, bias=b, addend=xs if use_addend else None, addend_scale=scale, relu=relu)
+                gpad = torch.zeros((f.R, K))
+                gpad[: r1 - r0] = torch.from_numpy(go[r0:r1])
+                out.backward(gpad)
+                code = oracle.REDUCE_CODE[reduce]
+                plain, ref_arg = oracle.spmm_c(rowptr, col, val, x, code)
+                ref = oracle.apply_epilogue(plain, bias=bias, addend=x if use_addend else None, addend_scale=scale, relu=relu)
+                tag = f"{reduce}_relu{int(relu)}_add{int(use_addend)}_chunk{k_chunk}"
+                ok[tag + "_fwd"] = bool(np.allclose(out.detach().numpy()[: r1 - r0], ref[r0:r1], rtol=1e-5, atol=1e-5))
+                g = go * (ref > 0) if relu else go
+                if reduce == "max":
+                    gx, _ = oracle.arg_backward(col, val, None, ref_arg, g, N)
+                else:
+                    bw = oracle.spmm_backward_sum if reduce == "sum" else oracle.spmm_backward_mean
+                    gx = bw(rowptr, col, val, g, N)
+                if use_addend:
+                    gx = gx + scale * g
+                ok[tag + "_gx"] = bool(np.allclose(xs.grad.numpy()[: r1 - r0], gx[r0:r1], rtol=1e-4, atol=1e-4))
+                ok[tag + "_gbias"] = bool(np.allclose(b.grad.numpy(), g[r0:r1].sum(0), rtol=1e-4, atol=1e-4))
+        results[rank] = ok
+    finally:
+        dist.destroy_process_group()
+
+
+def test_epilogue_rides_in_the_last_launch_world2_gloo():
+    world = 2
+    port = 33500 + (os.getpid() % 2000)
+    mgr = mp.Manager()
+    results = mgr.dict()
+    mp.spawn(epilogue_worker, args=(world, port, results), nprocs=world, join=True)
     assert len(results) == world
     for rank in range(world):
         bad = [k for k, v in results[rank].items() if not v]

@@ -175,3 +175,73 @@ def test_rank_local_ingest_on_the_gpu(world, mode):
     for rank in range(world):
         bad = [k for k, v in results[rank].items() if not v]
         assert not bad, f"rank {rank}: {bad}"
+
+
+def epilogue_worker(rank, world, port, results, mode):
+    """relu(A x + bias) through DistSpMM on real ranks, forward and gradients, and a GCN layer through the
+    patched matmul with a partitioned adjacency (the fused path of nn.GCNConv)."""
+    sys.path.insert(0, ROOT)
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    torch.cuda.set_device(rank)
+    dev = torch.device("cuda", rank)
+    dist.init_process_group("nccl", rank=rank, world_size=world, device_id=dev)
+    try:
+        import isplib_b200  # noqa: F401
+        from isplib import iSpLibPlugin
+        from isplib_b200 import nn as gnn, synth
+        from isplib_b200.dist import PartitionedAdj
+        from oracle import oracle
+        g = synth.make_graph(4001, 300_000, law="lognormal", param=1.3, values="uniform", seed=3)
+        K = 128 if mode == "fused" else 32
+        x = torch.randn(g.n, K, generator=torch.Generator().manual_seed(1))
+        bias = torch.randn(K, generator=torch.Generator().manual_seed(4))
+        go = torch.randn(g.m, K, generator=torch.Generator().manual_seed(2))
+        rp, co, va = g.rowptr.numpy(), g.col.numpy(), g.value.numpy()
+        iSpLibPlugin.patch_pyg(group=dist.group.WORLD)
+        try:
+            padj = PartitionedAdj(g.rowptr.to(dev), g.col.to(dev), g.value.to(dev), g.n, device=dev, mode=mode)
+            r0, r1 = padj.row_range()
+            ok = {}
+            xs = padj.local_slice(x).requires_grad_(True)
+            b = bias.to(dev).requires_grad_(True)
+            out = isplib_b200.fused_matmul(padj, xs, "sum", bias=b, relu=True)
+            gpad = torch.zeros_like(out)
+            gpad[: r1 - r0] = go[r0:r1].to(dev)
+            out.backward(gpad)
+            torch.cuda.synchronize()
+            plain, _ = oracle.spmm_c(rp, co, va, x.numpy(), oracle.SUM)
+            ref = oracle.apply_epilogue(plain, bias=bias.numpy(), relu=True)
+            ok["fwd"] = bool(np.allclose(out.detach().cpu().numpy()[: r1 - r0], ref[r0:r1], rtol=1e-4, atol=1e-4))
+            gm = go.numpy() * (ref > 0)
+            ok["gx"] = bool(np.allclose(xs.grad.cpu().numpy()[: r1 - r0], oracle.spmm_backward_sum(rp, co, va, gm, g.n)[r0:r1],
+                                        rtol=1e-3, atol=1e-3))
+            ok["gbias"] = bool(np.allclose(b.grad.cpu().numpy(), gm[r0:r1].sum(0), rtol=1e-3, atol=1e-3))
+            # the model code, unchanged: GCNConv -> fused_matmul -> the partitioned operator
+            torch.manual_seed(0)
+            conv = gnn.GCNConv(K, 16, order="linear_first", relu=True).to(dev)
+            with torch.no_grad():
+                conv.bias.normal_()
+            y = conv(xs.detach(), padj)
+            with torch.no_grad():
+                h = (x.to(dev) @ conv.lin.weight.t()).cpu().numpy()
+            ref = oracle.apply_epilogue(oracle.spmm_c(rp, co, va, h, oracle.SUM)[0], bias=conv.bias.detach().cpu().numpy(), relu=True)
+            ok["gcn_layer"] = bool(np.allclose(y.detach().cpu().numpy()[: r1 - r0], ref[r0:r1], rtol=1e-3, atol=1e-3))
+            padj.op.fwd.check_status()
+            results[rank] = ok
+        finally:
+            iSpLibPlugin.unpatch_pyg()
+    finally:
+        dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("mode", ["fused", "nccl"])
+def test_epilogue_through_the_partitioned_operator_two_gpus(mode):
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs 2 GPUs")
+    mgr = mp.Manager()
+    results = mgr.dict()
+    mp.spawn(epilogue_worker, args=(2, 30650 + os.getpid() % 300, results, mode), nprocs=2, join=True)
+    for rank in range(2):
+        bad = [k for k, v in results[rank].items() if not v]
+        assert not bad, f"rank {rank}: {bad}"

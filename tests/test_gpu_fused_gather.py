@@ -118,3 +118,77 @@ def test_fused_gather_transposed_operator_emulated(capi, oracle, monkeypatch):
         np.testing.assert_allclose(torch.cat(grads).cpu().numpy(), want, rtol=1e-4, atol=1e-4)
         for t in ts:
             t.check_status()
+
+
+@pytest.mark.parametrize("world", [2, 4])
+@pytest.mark.parametrize("reduce,K,groups", [("sum", 128, "auto"), ("sum", 47, "auto"), ("mean", 64, "owners"), ("max", 128, "auto")])
+def test_fused_gather_epilogue_emulated_ranks(capi, oracle, world, reduce, K, groups, monkeypatch):
+    """relu(A x + scale * addend + bias) in the fused gather kernel's final store (tile mode, owner mode with
+    rows split per group, ragged width): bit-equal to the epilogue applied to the kernel's own plain result."""
+    from isplib_b200.dist import RowPartitionedSpMM, emulated_step, make_epilogue
+    monkeypatch.setenv("ISPLIB_B200_DIST_COPY_CTAS", "8")
+    monkeypatch.setenv("ISPLIB_B200_DIST_GATHER", groups)
+    M = N = 1300 + world
+    rng, rowptr, col, val = _graph(40 + world, M, N, 50, long_rows=[(5, 1200)])
+    rp_t, co_t, va_t = torch.from_numpy(rowptr).to(DEV), torch.from_numpy(col).to(DEV), torch.from_numpy(val).to(DEV)
+    shared = {}
+    ops = [RowPartitionedSpMM(rp_t, co_t, va_t, N, device=DEV, mode="fused", emulate=(world, r, shared)) for r in range(world)]
+    mat = rng.standard_normal((N, K)).astype(np.float32)
+    bias = rng.standard_normal(K).astype(np.float32)
+    x = torch.from_numpy(mat).to(DEV)
+    b = torch.from_numpy(bias).to(DEV)
+    xs = [op.pad_x(x[op.col_range()[0]:op.col_range()[1]]) for op in ops]
+    plain = emulated_step(ops, xs, reduce)
+    epis = [make_epilogue(bias=b, addend=op.pad_out(xs[i]), addend_scale=1.5, relu=True) for i, op in enumerate(ops)]
+    fused = emulated_step(ops, xs, reduce, epilogues=epis)
+    ref_plain, _ = oracle.spmm_c(rowptr, col, val, mat, oracle.REDUCE_CODE[reduce])
+    for op, (o0, a0), (o1, a1) in zip(ops, plain, fused):
+        op.check_status()
+        r0, r1 = op.row_range()
+        n = r1 - r0
+        want = oracle.apply_epilogue(o0.cpu().numpy()[:n], bias=bias, addend=mat[r0:r1], addend_scale=1.5, relu=True)
+        got = o1.cpu().numpy()[:n]
+        # same reduction result underneath; the epilogue itself adds at most two fp32 roundings
+        np.testing.assert_allclose(got, want, rtol=2e-6, atol=2e-5, err_msg=f"rank {op.rank}")
+        if a0 is not None:
+            assert torch.equal(a0, a1)
+        # and against the oracle end to end
+        ref = oracle.apply_epilogue(ref_plain[r0:r1], bias=bias, addend=mat[r0:r1], addend_scale=1.5, relu=True)
+        np.testing.assert_allclose(got, ref, rtol=2e-6 if reduce == "max" else 1e-4, atol=2e-5 if reduce == "max" else 1e-4)
+
+
+@pytest.mark.parametrize("reduce", ["sum", "mean", "max"])
+def test_block_kernel_epilogue_after_accumulate(capi, oracle, reduce):
+    """The NCCL path's last launch: the remote block ACCUMULATEs into what the local block stored, divides
+    (mean) and only then applies bias / addend / ReLU -- through the same block launcher dist.py uses."""
+    from isplib_b200.dist import FLAG_ACCUMULATE, RowPartitionedSpMM, make_epilogue
+    M = N = 900
+    rng, rowptr, col, val = _graph(5, M, N, 40, long_rows=[(7, 800)])
+    K = 64
+    mat = rng.standard_normal((N, K)).astype(np.float32)
+    bias = rng.standard_normal(K).astype(np.float32)
+    add = rng.standard_normal((M // 2, K)).astype(np.float32)
+    shared = {}
+    # rank 0 of an emulated world of 2 in NCCL mode: only its two column blocks are used here
+    op = RowPartitionedSpMM(torch.from_numpy(rowptr).to(DEV), torch.from_numpy(col).to(DEV), torch.from_numpy(val).to(DEV),
+                            N, device=DEV, mode="nccl", emulate=(2, 0, shared), balance="rows")
+    x = torch.from_numpy(mat).to(DEV)
+    gathered = torch.cat([op.pad_x(x[c0:c1]) for c0, c1 in (op.col_range(0), op.col_range(1))])
+    code = oracle.REDUCE_CODE[reduce]
+    inner = 0 if code == 3 else code
+    div = op.row_degree if code == 3 else None
+    epi = make_epilogue(bias=torch.from_numpy(bias).to(DEV), addend=torch.from_numpy(add).to(DEV), addend_scale=0.5, relu=True)
+    outs = []
+    for e in ({}, epi):
+        out = torch.empty((op.R, K), device=DEV)
+        arg = torch.empty((op.R, K), dtype=torch.int64, device=DEV) if inner in (1, 2) else None
+        op.block_spmm(inner, op.local, gathered[: op.Rc], out, arg, 0, None, op.nnz, -1)
+        op.block_spmm(inner, op.remote, gathered, out, arg, FLAG_ACCUMULATE, div, op.nnz, -1, **e)
+        outs.append(out.cpu().numpy())
+    r0, r1 = op.row_range()
+    want = oracle.apply_epilogue(outs[0][: r1 - r0], bias=bias, addend=add, addend_scale=0.5, relu=True)
+    np.testing.assert_allclose(outs[1][: r1 - r0], want, rtol=2e-6, atol=2e-5)
+    ref, _ = oracle.spmm_c(rowptr, col, val, mat, code)
+    ref = oracle.apply_epilogue(ref[r0:r1], bias=bias, addend=add, addend_scale=0.5, relu=True)
+    np.testing.assert_allclose(outs[1][: r1 - r0], ref, rtol=2e-6 if reduce == "max" else 1e-4,
+                               atol=2e-5 if reduce == "max" else 1e-4)
