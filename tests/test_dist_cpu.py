@@ -437,3 +437,122 @@ def test_owner_groups_and_runs_of_the_fused_gather():
                 ends = starts[1:] + [world * 10]
                 expanded = [g for s, e, g in zip(starts, ends, grp) for _ in range((e - s) // 10)]
                 assert expanded == groups
+
+
+# ------------------------------------------------------------------------------------------------------------
+# partitioned ingest (isplib_b200/dist_io.py): byte-range Matrix Market shards -> row owners -> operator
+# ------------------------------------------------------------------------------------------------------------
+def numpy_csr_builder(row, col, val, m, n):
+    """Stand-in for isplib_b200_coo_to_csr in the CPU tests: stable sort by (row, col)."""
+    r, c = row.numpy(), col.numpy()
+    order = np.lexsort((c, r))            # numpy's lexsort is stable
+    rowptr = np.zeros(m + 1, dtype=np.int64)
+    rowptr[1:] = np.cumsum(np.bincount(r, minlength=m))
+    return (torch.from_numpy(rowptr), torch.from_numpy(c[order].copy()),
+            None if val is None else torch.from_numpy(val.numpy()[order].copy()))
+
+
+def write_test_mtx(path, kind):
+    import scipy.io
+    import scipy.sparse
+    rng = np.random.default_rng(21)
+    M = N = 83
+    if kind == "symmetric":
+        a = scipy.sparse.random(M, N, density=0.06, random_state=3, format="coo", dtype=np.float64)
+        a = scipy.sparse.triu(a + a.T).tocoo()
+        a.data = np.round(a.data * 8) / 8 + 0.125
+        scipy.io.mmwrite(path, a, symmetry="symmetric", comment="lower half implied")
+    else:
+        deg = rng.integers(0, 14, size=M)
+        deg[5] = 70                       # a heavy row: the nnz-balanced cut is not the even one
+        row = np.repeat(np.arange(M), deg)
+        col = np.concatenate([rng.choice(N, size=d, replace=False) for d in deg]) if row.size else row
+        perm = rng.permutation(row.size)  # file order is NOT row order: entries really have to travel
+        data = np.round(rng.random(row.size) * 8) / 8 + 0.125
+        a = scipy.sparse.coo_matrix((data[perm], (row[perm], col[perm])), shape=(M, N))
+        scipy.io.mmwrite(path, a, field="pattern" if kind == "pattern" else "real", symmetry="general",
+                         comment="lines of\nvery different length follow")
+    return M, N
+
+
+def mtx_ingest_worker(rank, world, port, path, kind, results):
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        import scipy.io
+        from isplib_b200 import dist_io
+        from isplib_b200.dist import nnz_balanced_bounds
+        from oracle import oracle
+        coo = scipy.io.mmread(path).tocoo()
+        M, N = coo.shape
+        order = np.lexsort((coo.col, coo.row))
+        g_row, g_col = coo.row[order].astype(np.int64), coo.col[order].astype(np.int64)
+        g_val = None if kind == "pattern" else coo.data[order].astype(np.float32)
+        rowptr = np.zeros(M + 1, dtype=np.int64)
+        rowptr[1:] = np.cumsum(np.bincount(g_row, minlength=M))
+        padj = dist_io.read_mtx_partitioned(path, device="cpu", csr_builder=numpy_csr_builder,
+                                            block_spmm=oracle_block_spmm, arg_backward=oracle_arg_backward,
+                                            overlap=False, mode="nccl")
+        f = padj.op.fwd
+        r0, r1 = padj.row_range()
+        e0, e1 = int(rowptr[r0]), int(rowptr[r1])
+        ok = {"bounds": f.row_bounds == nnz_balanced_bounds(torch.from_numpy(rowptr), world),
+              "rowptr": bool(np.array_equal(padj.op.rowptr.numpy(), rowptr)),
+              "col": bool(np.array_equal(padj.op.col.local.numpy(), g_col[e0:e1])),
+              "has_value": padj.has_value() == (kind != "pattern")}
+        if g_val is not None:
+            ok["val"] = bool(np.array_equal(padj.op.value.local.numpy(), g_val[e0:e1]))
+        # every line was parsed by exactly one rank
+        n_lines = torch.tensor([dist_io.read_mtx_shard(path, rank, world)[0].numel()])
+        dist.all_reduce(n_lines)
+        ok["every_entry_once"] = int(n_lines) == g_col.shape[0]
+        K = 5
+        x = np.random.default_rng(1).standard_normal((N, K)).astype(np.float32)
+        xs = padj.local_slice(torch.from_numpy(x)).requires_grad_(True)
+        for reduce in ("sum", "max"):
+            out = padj.matmul(xs, reduce)
+            ref = oracle.spmm_c(rowptr, g_col, g_val, x, oracle.REDUCE_CODE[reduce])[0]
+            ok[reduce] = bool(np.allclose(out.detach().numpy()[: r1 - r0], ref[r0:r1], rtol=1e-5, atol=1e-5))
+        go = np.random.default_rng(2).standard_normal((M, K)).astype(np.float32)
+        gpad = torch.zeros((f.R, K))
+        gpad[: r1 - r0] = torch.from_numpy(go[r0:r1])
+        padj.matmul(xs, "sum").backward(gpad)
+        gref = oracle.spmm_backward_sum(rowptr, g_col, g_val, go, N)
+        ok["sum_bwd"] = bool(np.allclose(xs.grad.numpy()[: r1 - r0], gref[r0:r1], rtol=1e-4, atol=1e-4))
+        results[rank] = ok
+    finally:
+        dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("kind,world", [("real", 2), ("real", 3), ("pattern", 2), ("symmetric", 3)])
+def test_matrix_market_byte_range_ingest_gloo(tmp_path, kind, world):
+    path = str(tmp_path / f"g_{kind}.mtx")
+    write_test_mtx(path, kind)
+    port = 35500 + (os.getpid() % 2000) + 3 * world + {"real": 0, "pattern": 1, "symmetric": 2}[kind]
+    mgr = mp.Manager()
+    results = mgr.dict()
+    mp.spawn(mtx_ingest_worker, args=(world, port, path, kind, results), nprocs=world, join=True)
+    assert len(results) == world
+    for rank in range(world):
+        bad = [k for k, v in results[rank].items() if not v]
+        assert not bad, f"rank {rank}: {bad}"
+
+
+def test_mtx_shards_cover_every_line_once_for_any_world(tmp_path):
+    from isplib_b200 import dist_io
+    path = str(tmp_path / "g.mtx")
+    write_test_mtx(path, "real")
+    m, n, nnz, field, symmetry, _ = dist_io.mtx_header(path)
+    assert (m, n, field, symmetry) == (83, 83, "real", "general")
+    whole = dist_io.read_mtx_shard(path, 0, 1)
+    assert whole[0].numel() == nnz
+    for world in (2, 5, 16, 200, 5000):      # more ranks than lines: some shards are empty, none overlaps
+        parts = [dist_io.read_mtx_shard(path, r, world) for r in range(world)]
+        assert torch.equal(torch.cat([p[0] for p in parts]), whole[0])
+        assert torch.equal(torch.cat([p[1] for p in parts]), whole[1])
+        assert torch.equal(torch.cat([p[2] for p in parts]), whole[2])
+    with pytest.raises(ValueError):
+        bad = tmp_path / "dense.mtx"
+        bad.write_text("%%MatrixMarket matrix array real general\n2 2\n1\n2\n3\n4\n")
+        dist_io.mtx_header(str(bad))

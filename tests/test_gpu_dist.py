@@ -245,3 +245,56 @@ def test_epilogue_through_the_partitioned_operator_two_gpus(mode):
     for rank in range(2):
         bad = [k for k, v in results[rank].items() if not v]
         assert not bad, f"rank {rank}: {bad}"
+
+
+def mtx_ingest_worker(rank, world, port, path, results):
+    """Partitioned ingest with the real device CSR build (isplib_b200_coo_to_csr per rank) against io.read_mtx."""
+    sys.path.insert(0, ROOT)
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    torch.cuda.set_device(rank)
+    dev = torch.device("cuda", rank)
+    dist.init_process_group("nccl", rank=rank, world_size=world, device_id=dev)
+    try:
+        from isplib_b200 import dist_io, io as gio
+        whole = gio.read_mtx(path, device=dev)
+        rowptr, col, val = whole.csr()
+        padj = dist_io.read_mtx_partitioned(path, device=dev, mode="nccl")
+        r0, r1 = padj.row_range()
+        e0, e1 = int(rowptr[r0]), int(rowptr[r1])
+        ok = {"rowptr": bool(torch.equal(padj.op.rowptr, rowptr.to(torch.int64))),
+              "col": bool(torch.equal(padj.op.col.local, col[e0:e1].to(torch.int64))),
+              "val": bool(torch.equal(padj.op.value.local, val[e0:e1]))}
+        x = torch.randn(whole.sparse_sizes()[1], 32, device=dev, generator=torch.Generator(device=dev).manual_seed(1))
+        import isplib_b200
+        from isplib import iSpLibPlugin
+        iSpLibPlugin.patch_pyg(group=dist.group.WORLD)
+        try:
+            import torch_sparse
+            for reduce in ("sum", "max"):
+                a = torch_sparse.matmul(padj, padj.local_slice(x), reduce)[: r1 - r0]
+                b = torch_sparse.matmul(whole, x, reduce)[r0:r1]
+                ok[reduce] = bool(torch.allclose(a, b, rtol=1e-4, atol=1e-4))
+        finally:
+            iSpLibPlugin.unpatch_pyg()
+        results[rank] = ok
+    finally:
+        dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("world", [1, 2])
+def test_matrix_market_partitioned_ingest_on_the_gpu(tmp_path, world):
+    if torch.cuda.device_count() < world:
+        pytest.skip(f"needs {world} GPUs")
+    import scipy.io
+    import scipy.sparse
+    a = scipy.sparse.random(3001, 3001, density=0.004, random_state=5, format="coo", dtype=np.float64)
+    a.data = np.round(a.data * 16) / 16 + 0.0625
+    path = str(tmp_path / "g.mtx")
+    scipy.io.mmwrite(path, a)
+    mgr = mp.Manager()
+    results = mgr.dict()
+    mp.spawn(mtx_ingest_worker, args=(world, 30950 + os.getpid() % 300 + world, path, results), nprocs=world, join=True)
+    for rank in range(world):
+        bad = [k for k, v in results[rank].items() if not v]
+        assert not bad, f"rank {rank}: {bad}"
