@@ -6,7 +6,7 @@ import numpy as np
 import pytest
 import torch
 
-from conftest import GOLDEN_CASES, abs_product_sum, assert_sum_close, grad_cond, load_golden, random_csr
+from conftest import GOLDEN_CASES, abs_product_sum, assert_sum_close, grad_cond, load_golden
 
 pytestmark = pytest.mark.gpu
 DEV = "cuda:0"

@@ -105,7 +105,6 @@ def test_shim_sparse_tensor_storage_fields():
 
 
 def test_missing_extension_is_an_import_error(tmp_path, monkeypatch):
-    import importlib
     import isplib_b200
     monkeypatch.setattr(isplib_b200, "_PKG_DIR", str(tmp_path))
     with pytest.raises(ImportError, match="no CPU implementation"):

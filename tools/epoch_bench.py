@@ -13,7 +13,6 @@ import argparse
 import json
 import os
 import sys
-import time
 
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import torch  # noqa: E402
@@ -34,7 +33,6 @@ def run(a, init_dist=True):
     import isplib_b200  # noqa: F401
     from isplib import iSpLibPlugin
     from isplib_b200 import nn as gnn, synth
-    from isplib_b200.dist import DistSpMM
 
     torch.manual_seed(0)
     values = "gcn" if a.model == "gcn" else None

@@ -37,7 +37,6 @@ if a.bwd and a.aux:
     acol = torch.empty(g.m, a.k, dtype=torch.int32, device=dev)
     aval = torch.empty(g.m, a.k, device=dev) if g.value is not None else None
     capi.spmm_csr(a.reduce, rp, co, g.value, x, plan, v, out=out, arg_out=arg, arg_col=acol, arg_val=aval)
-    import time
     for _ in range(a.reps):
         capi.spmm_arg_backward_aux(acol, aval, go, g.n, binned=a.binned)
     torch.cuda.synchronize()
