@@ -171,9 +171,10 @@ def spmm_numpy(rowptr, col, value, mat, reduction: int):
         if reduction == MEAN:
             out /= np.maximum(deg, 1).astype(np.float32)[:, None]
     else:
-        red = np.maximum if reduction == MAX else np.minimum
+        # fmax / fmin skip NaNs: a NaN product never wins under strict compare (an all-NaN segment stays
+        # NaN here and fails `beats` below, so the row keeps the init value and the sentinel)
+        red = np.fmax if reduction == MAX else np.fmin
         best = red.reduceat(prod, starts, axis=0)          # [len(nz), K]
-        # NaN never wins under strict compare; keep inputs finite in tests.
         init = F32_LOWEST if reduction == MAX else F32_MAX
         row_of = np.repeat(np.arange(M), deg)
         seg_of = np.searchsorted(nz, row_of)
@@ -182,7 +183,9 @@ def spmm_numpy(rowptr, col, value, mat, reduction: int):
         first = np.minimum.reduceat(eid, starts, axis=0)
         # an entry only replaces the init value under STRICT compare
         beats = (best > init) if reduction == MAX else (best < init)
-        out[nz] = np.where(beats, best, init)
+        # the stored value is the WINNING entry's product (its bit pattern: +0.0 and -0.0 tie, first seen stays)
+        won = np.take_along_axis(prod, np.minimum(first, nnz - 1), axis=0)
+        out[nz] = np.where(beats, won, init)
         arg[nz] = np.where(beats, first, nnz)
     return out, arg
 

@@ -162,3 +162,35 @@ def test_oracle_epilogue_matches_the_reference_callers(oracle):
         agg = oracle.spmm_c(z["rowptr"], z["col"], None, z["x"], oracle.SUM)[0]
         np.testing.assert_allclose(oracle.apply_epilogue(agg, addend=z["x"], addend_scale=1.0 + float(z["eps"])),
                                    z["gin_out"], rtol=1e-5, atol=1e-5)
+
+
+def test_compare_conventions_nan_signed_zero_and_ties(oracle):
+    """The conventions the reference tree leaves open, pinned for all three restatements:
+    strict compare scanning in CSR order -> the smallest edge id wins a tie, +0.0 and -0.0 tie (first seen
+    wins), and a NaN product never replaces a candidate (a row of NaNs only keeps the init value + sentinel)."""
+    nan = np.float32("nan")
+    rowptr = np.array([0, 3, 6, 8, 10], dtype=np.int64)
+    col = np.array([0, 1, 2, 0, 1, 2, 3, 3, 4, 5], dtype=np.int64)
+    val = np.ones(10, dtype=np.float32)
+    #            x[0]  x[1]  x[2]  x[3]  x[4]  x[5]
+    mat = np.array([[2.0, 2.0, 1.0, nan, 0.0, -0.0],
+                    [nan, 5.0, 5.0, nan, -0.0, 0.0]], dtype=np.float32).T.copy()     # [6, 2]
+    nnz = col.shape[0]
+    for impl in (oracle.spmm_c, oracle.spmm_loops, oracle.spmm_numpy):
+        out, arg = impl(rowptr, col, val, mat, oracle.MAX)
+        # row 0, k=0: products 2, 2, 1 -> tie between edges 0 and 1 -> edge 0
+        assert out[0, 0] == 2.0 and arg[0, 0] == 0, impl.__name__
+        # row 0, k=1: NaN, 5, 5 -> the NaN never wins, first 5 is edge 1
+        assert out[0, 1] == 5.0 and arg[0, 1] == 1, impl.__name__
+        # row 1 repeats the columns with edge ids 3..5
+        assert arg[1, 0] == 3 and arg[1, 1] == 4, impl.__name__
+        # row 2: both entries are column 3 (NaN, NaN): nothing ever wins
+        assert arg[2, 0] == nnz and arg[2, 1] == nnz, impl.__name__
+        assert out[2, 0] == np.finfo(np.float32).min and out[2, 1] == np.finfo(np.float32).min, impl.__name__
+        # row 3: +0.0 then -0.0 (k=0), -0.0 then +0.0 (k=1): equal, the first seen (edge 8) stays, bit pattern kept
+        assert arg[3, 0] == 8 and arg[3, 1] == 8, impl.__name__
+        assert not np.signbit(out[3, 0]) and np.signbit(out[3, 1]), impl.__name__
+        out, arg = impl(rowptr, col, val, mat, oracle.MIN)
+        assert out[0, 0] == 1.0 and arg[0, 0] == 2 and out[0, 1] == 5.0 and arg[0, 1] == 1, impl.__name__
+        assert arg[2, 0] == nnz and out[2, 0] == np.finfo(np.float32).max, impl.__name__
+        assert arg[3, 0] == 8 and arg[3, 1] == 8, impl.__name__
