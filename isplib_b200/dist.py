@@ -479,6 +479,19 @@ class RowPartitionedSpMM:
         relu?(result + addend_scale * addend[R, K] + bias[K]) in the final store of the last launch that
         writes the rows -- the fused gather kernel, or the remote-block kernel of the NCCL path."""
         epi = epilogue or {}
+        if reduce not in REDUCE_CODE:
+            raise ValueError(f"isplib_b200.dist: reduce must be one of {sorted(REDUCE_CODE)}, got {reduce!r}")
+        if x_slice.dim() != 2 or x_slice.size(0) != self.Rc or x_slice.dtype != torch.float32:
+            raise ValueError(f"isplib_b200.dist: x_slice must be this rank's padded fp32 slice [{self.Rc}, K] (pad_x), "
+                             f"got {tuple(x_slice.shape)} {x_slice.dtype}")
+        if x_slice.device.type != self.device.type or (
+                self.device.index is not None and x_slice.device.index not in (None, self.device.index)):
+            raise ValueError(f"isplib_b200.dist: x_slice is on {x_slice.device}, the partition on {self.device}")
+        if epi.get("bias") is not None and tuple(epi["bias"].shape) != (x_slice.size(1),):
+            raise ValueError(f"isplib_b200.dist: bias must have shape [{x_slice.size(1)}], got {tuple(epi['bias'].shape)}")
+        if epi.get("addend") is not None and tuple(epi["addend"].shape) != (self.R, x_slice.size(1)):
+            raise ValueError(f"isplib_b200.dist: addend must have shape [{self.R}, {x_slice.size(1)}] (pad_out), "
+                             f"got {tuple(epi['addend'].shape)}")
         code = REDUCE_CODE[reduce]
         is_arg = code in (MAX, MIN)
         K = x_slice.size(1)

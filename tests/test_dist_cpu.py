@@ -556,3 +556,22 @@ def test_mtx_shards_cover_every_line_once_for_any_world(tmp_path):
         bad = tmp_path / "dense.mtx"
         bad.write_text("%%MatrixMarket matrix array real general\n2 2\n1\n2\n3\n4\n")
         dist_io.mtx_header(str(bad))
+
+
+def test_partitioned_forward_refuses_malformed_slices():
+    """A wrong slice shape would make the block kernels read outside the gathered matrix: refuse it up front."""
+    from isplib_b200.dist import RowPartitionedSpMM, make_epilogue
+    rowptr, col, val = make_graph(3, 40, 40, True)
+    op = RowPartitionedSpMM(torch.from_numpy(rowptr), torch.from_numpy(col), torch.from_numpy(val), 40, device="cpu",
+                            block_spmm=oracle_block_spmm, overlap=False, emulate=(2, 0, {}), mode="nccl")
+    good = torch.zeros(op.Rc, 4)
+    with pytest.raises(ValueError, match="padded fp32 slice"):
+        op.forward(torch.zeros(op.Rc - 1, 4))
+    with pytest.raises(ValueError, match="padded fp32 slice"):
+        op.forward(good.double())
+    with pytest.raises(ValueError, match="reduce must be"):
+        op.forward(good, "prod")
+    with pytest.raises(ValueError, match="bias must have shape"):
+        op.forward(good, "sum", epilogue=make_epilogue(bias=torch.zeros(5)))
+    with pytest.raises(ValueError, match="addend must have shape"):
+        op.forward(good, "sum", epilogue=make_epilogue(addend=torch.zeros(op.R + 1, 4)))
