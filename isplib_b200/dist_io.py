@@ -40,6 +40,18 @@ def _cuda_csr_builder(row: torch.Tensor, col: torch.Tensor, val: Optional[torch.
     return rowptr.to(torch.int64), col_s.to(torch.int64), val_s
 
 
+def _raise_together(err: Optional[Exception], group, device) -> None:
+    """Every rank raises if ANY rank holds an error: an exception on one rank alone would leave the others
+    waiting in the next collective forever."""
+    flag = torch.tensor([0 if err is None else 1], dtype=torch.int32, device=device)
+    dist.all_reduce(flag, op=dist.ReduceOp.MAX, group=group)
+    if err is not None:
+        raise err
+    if int(flag):
+        raise RuntimeError("isplib_b200.dist_io: another rank of the group rejected its shard of the input "
+                           "(its own exception names the cause)")
+
+
 def partition_edges(row: torch.Tensor, col: torch.Tensor, val: Optional[torch.Tensor], num_rows: int, num_cols: int,
                     group=None, device=None, balance: str = "nnz", csr_builder: Optional[Callable] = None,
                     **dist_kw) -> PartitionedAdj:
@@ -51,10 +63,14 @@ def partition_edges(row: torch.Tensor, col: torch.Tensor, val: Optional[torch.Te
     col = col.to(dev).to(torch.int64)
     val = None if val is None else val.to(dev).to(torch.float32)
     m, n = int(num_rows), int(num_cols)
-    if row.numel() and (int(row.min()) < 0 or int(row.max()) >= m or int(col.min()) < 0 or int(col.max()) >= n):
-        raise ValueError("isplib_b200.dist_io: edge endpoint outside [0, num_rows) x [0, num_cols)")
     if balance not in ("nnz", "rows"):
-        raise ValueError(f"balance must be 'nnz' or 'rows', got {balance!r}")
+        raise ValueError(f"balance must be 'nnz' or 'rows', got {balance!r}")   # same argument on every rank
+    err = None
+    if row.numel() != col.numel() or (val is not None and val.numel() != row.numel()):
+        err = ValueError("isplib_b200.dist_io: row, col and val of a shard must have the same length")
+    elif row.numel() and (int(row.min()) < 0 or int(row.max()) >= m or int(col.min()) < 0 or int(col.max()) >= n):
+        err = ValueError("isplib_b200.dist_io: edge endpoint outside [0, num_rows) x [0, num_cols)")
+    _raise_together(err, group, dev)
     if balance == "nnz":
         deg = torch.bincount(row, minlength=m) if row.numel() else torch.zeros(m, dtype=torch.int64, device=dev)
         dist.all_reduce(deg, group=group)
@@ -154,7 +170,13 @@ def read_mtx_partitioned(path: str, group=None, device="cuda", pattern_as_none: 
     """Every rank parses its own byte range of one Matrix Market file and the edges are routed to their row
     owners: ``io.read_mtx`` + ``iSpLibPlugin.partition`` without the whole graph in any one process."""
     world, rank = dist.get_world_size(group), dist.get_rank(group)
-    row, col, val, m, n = read_mtx_shard(path, rank, world)
+    err, shard = None, None
+    try:
+        shard = read_mtx_shard(path, rank, world)
+    except Exception as e:          # a malformed line in ONE byte range must stop every rank, not hang the rest
+        err = e
+    _raise_together(err, group, torch.device(device))
+    row, col, val, m, n = shard
     if val is None and not pattern_as_none:
         val = torch.ones(row.numel(), dtype=torch.float32)
     return partition_edges(row, col, val, m, n, group=group, device=device, **kw)

@@ -575,3 +575,56 @@ def test_partitioned_forward_refuses_malformed_slices():
         op.forward(good, "sum", epilogue=make_epilogue(bias=torch.zeros(5)))
     with pytest.raises(ValueError, match="addend must have shape"):
         op.forward(good, "sum", epilogue=make_epilogue(addend=torch.zeros(op.R + 1, 4)))
+
+
+def bad_shard_worker(rank, world, port, path, results):
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        from isplib_b200 import dist_io
+        seen = {}
+        # (1) an endpoint outside the matrix in ONE rank's edge shard
+        row = torch.tensor([0, 1, 2]) if rank == 0 else torch.tensor([1, 99])
+        col = torch.tensor([1, 2, 0]) if rank == 0 else torch.tensor([0, 1])
+        try:
+            dist_io.partition_edges(row, col, None, 4, 4, device="cpu", csr_builder=numpy_csr_builder)
+            seen["edges"] = "no error"
+        except ValueError as e:
+            seen["edges"] = "own: " + str(e)
+        except RuntimeError as e:
+            seen["edges"] = "peer: " + str(e)
+        # (2) a malformed line in ONE rank's byte range of the file
+        try:
+            dist_io.read_mtx_partitioned(path, device="cpu", csr_builder=numpy_csr_builder)
+            seen["mtx"] = "no error"
+        except RuntimeError as e:
+            seen["mtx"] = "peer: " + str(e)
+        except Exception as e:
+            seen["mtx"] = "own: " + type(e).__name__
+        # the group is still usable afterwards: nobody is stuck in a half-entered collective
+        t = torch.ones(1)
+        dist.all_reduce(t)
+        seen["alive"] = int(t)
+        results[rank] = seen
+    finally:
+        dist.destroy_process_group()
+
+
+def test_a_bad_shard_on_one_rank_stops_every_rank_gloo(tmp_path):
+    """Validation errors are agreed on by the whole group before the first data collective: the rank with
+    the bad shard raises its own error, the others a RuntimeError naming a peer -- none is left waiting."""
+    path = tmp_path / "broken.mtx"
+    lines = ["%%MatrixMarket matrix coordinate real general", "6 6 8"]
+    lines += [f"{i + 1} {(i * 5) % 6 + 1} 0.5" for i in range(7)] + ["6 oops 0.25"]     # the last line is rank 1's
+    path.write_text("\n".join(lines) + "\n")
+    world, port = 2, 36900 + (os.getpid() % 2000)
+    mgr = mp.Manager()
+    results = mgr.dict()
+    mp.spawn(bad_shard_worker, args=(world, port, str(path), results), nprocs=world, join=True)
+    assert len(results) == world
+    assert results[1]["edges"].startswith("own: ") and "outside" in results[1]["edges"]
+    assert results[0]["edges"].startswith("peer: ")
+    assert results[1]["mtx"].startswith("own: ")
+    assert results[0]["mtx"].startswith("peer: ")
+    assert results[0]["alive"] == results[1]["alive"] == world
