@@ -126,6 +126,7 @@ class iSpLibPlugin:
         raise ValueError(f"isplib: unsupported reduce {reduce!r} (sum, add, mean, max, min)")
 
     dist_group = None      # process group of the row-partitioned mode (patch_pyg(group=...))
+    _group_backup = []     # the groups of the enclosing patch scopes (the patch is a stack, like `backup`)
 
     @classmethod
     def partition(cls, adj_t, device=None, **kw):
@@ -141,6 +142,7 @@ class iSpLibPlugin:
         multi-GPU mode: adjacencies made with ``iSpLibPlugin.partition(adj_t)`` are then multiplied
         across its ranks by the same patched ``torch_sparse.matmul`` (new; the reference is single-process)."""
         global matmul
+        cls._group_backup.append(cls.dist_group)
         cls.dist_group = group
         try:  # isplib/__init__.py:159-171
             import torch_geometric.typing as tgt  # type: ignore
@@ -165,6 +167,7 @@ class iSpLibPlugin:
             ts = sys.modules["torch_sparse"]
             ts.matmul = cls.backup.pop()
             matmul = ts.matmul
+            cls.dist_group = cls._group_backup.pop() if cls._group_backup else None
             try:
                 import torch_geometric.typing as tgt  # type: ignore
                 if cls.cache.get("WITH_PT2") is not None:

@@ -48,6 +48,24 @@ def test_patch_unpatch_is_a_stack():
     assert ts.matmul is orig_mm and torch.sparse.mm is orig_sparse_mm and not P.is_patched()
 
 
+def test_process_group_follows_the_patch_stack():
+    """patch_pyg(group=g) scopes nest: an inner patch without a group does not lose the outer group."""
+    import isplib
+    P = isplib.iSpLibPlugin
+    g = object()                                      # only stored and handed on; never used without a partition
+    assert P.dist_group is None
+    P.patch_pyg(group=g)
+    assert P.dist_group is g
+    P.patch_pyg()                                     # e.g. an @isplib_autotune function called inside
+    assert P.dist_group is None
+    P.unpatch_pyg()
+    assert P.dist_group is g and P.is_patched()
+    P.unpatch_pyg()
+    assert P.dist_group is None and not P.is_patched()
+    P.unpatch_pyg()                                   # still a no-op when nothing is patched
+    assert P.dist_group is None
+
+
 def test_decorator_unpatches_even_on_exception():
     import isplib
     ts = sys.modules["torch_sparse"]
