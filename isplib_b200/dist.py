@@ -990,8 +990,13 @@ class _DistSpMMFn(torch.autograd.Function):
         aux = {} if (REDUCE_CODE[reduce] in (MAX, MIN) and x_slice.requires_grad) else None
         epi = make_epilogue(None if bias is None else bias.detach().contiguous(),
                             None if addend is None else addend.detach(), addend_scale, relu)
-        if epi.get("addend") is not None and (addend.stride(1) != 1 or addend.size(0) < op.fwd.R):
-            epi["addend"] = op.fwd.pad_out(addend.detach())
+        if epi.get("addend") is not None:
+            # the kernel reads the first R rows with unit inner stride: pad a shorter / strided addend, cut a
+            # longer one (an x slice of Rc > R rows handed in as GIN's self term on a non-square operator)
+            if addend.stride(1) != 1 or addend.size(0) < op.fwd.R:
+                epi["addend"] = op.fwd.pad_out(addend.detach())
+            elif addend.size(0) > op.fwd.R:
+                epi["addend"] = addend.detach()[: op.fwd.R]
         out, arg = op.fwd.forward(x_slice.contiguous(), reduce, aux=aux, epilogue=epi)
         ctx.op, ctx.reduce = op, reduce
         ctx.aux = aux if aux else None            # stays empty when the NCCL path ran
@@ -1012,7 +1017,11 @@ class _DistSpMMFn(torch.autograd.Function):
         # the epilogue's own inputs: bias sums over the rank's REAL rows (the ranks' shares are summed by
         # whoever all-reduces the parameter gradients, like every other replicated weight)
         grad_bias = grad_out[: op.fwd.own_rows].sum(0) if (has_bias and ctx.needs_input_grad[3]) else None
-        grad_addend = (grad_out[:addend_rows] * addend_scale) if (has_addend and ctx.needs_input_grad[4]) else None
+        grad_addend = None
+        if has_addend and ctx.needs_input_grad[4]:
+            grad_addend = grad_out[:addend_rows] * addend_scale
+            if addend_rows > grad_addend.size(0):          # rows of the addend the kernel never read
+                grad_addend = torch.nn.functional.pad(grad_addend, (0, 0, 0, addend_rows - grad_addend.size(0)))
         tail = (None, None, grad_bias, grad_addend, None, None)
         if code in (SUM, MEAN):
             t = op.bwd_op(code == MEAN)

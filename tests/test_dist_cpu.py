@@ -628,3 +628,33 @@ def test_a_bad_shard_on_one_rank_stops_every_rank_gloo(tmp_path):
     assert results[1]["mtx"].startswith("own: ")
     assert results[0]["mtx"].startswith("peer: ")
     assert results[0]["alive"] == results[1]["alive"] == world
+
+
+def test_epilogue_addend_of_any_row_count_single_rank():
+    """The addend may be shorter than the padded output slice (zero padded), exactly R rows, or longer (cut):
+    forward and the gradient w.r.t. the addend keep the addend's own shape."""
+    from isplib_b200.dist import DistSpMM
+    from oracle import oracle
+    M = N = 37
+    K = 5
+    rowptr, col, val = make_graph(11, M, N, True)
+    op = DistSpMM(torch.from_numpy(rowptr), torch.from_numpy(col), torch.from_numpy(val), N, device="cpu",
+                  block_spmm=oracle_block_spmm, arg_backward=oracle_arg_backward, overlap=False, emulate=(1, 0, {}),
+                  mode="nccl")
+    R = op.fwd.R
+    assert R == M
+    x = np.random.default_rng(3).integers(-3, 4, size=(N, K)).astype(np.float32)
+    ref = oracle.spmm_c(rowptr, col, val, x, oracle.SUM)[0]
+    go = torch.from_numpy(np.random.default_rng(4).standard_normal((R, K)).astype(np.float32))
+    for rows in (R - 7, R, R + 9):
+        add = torch.from_numpy(np.random.default_rng(rows).standard_normal((rows, K)).astype(np.float32)).requires_grad_(True)
+        xs = torch.from_numpy(x).requires_grad_(True)
+        out = op(xs, "sum", addend=add, addend_scale=0.5)
+        want = ref.copy()
+        n = min(rows, R)
+        want[:n] += 0.5 * add.detach().numpy()[:n]
+        np.testing.assert_allclose(out.detach().numpy(), want, rtol=1e-5, atol=1e-5)
+        out.backward(go)
+        assert add.grad.shape == add.shape
+        np.testing.assert_allclose(add.grad.numpy()[:n], 0.5 * go.numpy()[:n], rtol=1e-6, atol=1e-6)
+        assert not add.grad.numpy()[n:].any()
